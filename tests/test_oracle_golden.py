@@ -1,0 +1,189 @@
+"""Pin oracle/ against the reference's own outputs (tests/golden/*.npz, made by make_golden.py).
+
+CPU-only.  The bar: integer outputs bit-equal; float outputs within 1e-12 relative (the oracle
+restates the same float64 arithmetic; only summation order inside the 2-D smoothing differs).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import spectral_gate_oracle as O
+from oracle import torchgate_oracle as TO
+from tests.synth_host import synth_small, synth_torchgate
+
+
+def relinf(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a, b = a.astype(dt), b.astype(dt)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def fish(golden_dir):
+    return np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
+
+
+@pytest.fixture(scope="module")
+def small(golden_dir):
+    return np.load(os.path.join(golden_dir, "synth_small.npz"))
+
+
+@pytest.fixture(scope="module")
+def tgs(golden_dir):
+    return np.load(os.path.join(golden_dir, "torchgate_small.npz"))
+
+
+def test_dft_primitive_matches_definition():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((5, 256))
+    assert relinf(O.rfft(x, 256), O.dft_matrix_rfft(x, 256)) < 1e-13
+    # zero-padding at the end when the segment is shorter than n
+    assert relinf(O.rfft(x[:, :100], 256), O.dft_matrix_rfft(x[:, :100], 256)) < 1e-13
+    X = O.rfft(x, 256)
+    assert relinf(O.irfft(X, 256), x) < 1e-13
+
+
+def test_smoothing_filter_is_integer_rational():
+    # taps * (nf+1)^2 (nt+1)^2 are the integers (nf+1-|a|)(nt+1-|b|)  
+    for nf, nt in [(5, 9), (10, 4), (16, 3), (5, 8), (1, 3), (4, 1)]:
+        f = O.smoothing_filter(nf, nt)
+        D = (nf + 1) ** 2 * (nt + 1) ** 2
+        a = (nf + 1 - np.abs(np.arange(-nf, nf + 1)))[:, None]
+        b = (nt + 1 - np.abs(np.arange(-nt, nt + 1)))[None, :]
+        assert np.abs(f * D - a * b).max() < 1e-9
+        assert abs(f.sum() - 1) < 1e-14
+
+
+def test_fish_cfg1_stationary_int16_bit_equal(fish):
+    info = {}
+    out = O.reduce_noise(fish["y"], int(fish["sr"]), cfg=O.GateConfig(sr=int(fish["sr"]), stationary=True), info=info)
+    assert out.dtype == np.int16
+    assert np.array_equal(out, fish["out_stationary"])
+    assert np.abs(info["thresh"] - fish["thresh"]).max() < 1e-9
+    assert (info["n_grad_freq"], info["n_grad_time"]) == (5, 8)     # 11 x 17 filter at 44.1 kHz
+
+
+def test_fish_cfg1_nonstationary_int16_bit_equal(fish):
+    out = O.reduce_noise(fish["y"], int(fish["sr"]), cfg=O.GateConfig(sr=int(fish["sr"]), stationary=False))
+    assert np.array_equal(out, fish["out_nonstationary"])
+
+
+def test_fish_cfg1_float32(fish):
+    y = (fish["y"] / 32768).astype(np.float32)
+    info = {}
+    out = O.reduce_noise(y, int(fish["sr"]), cfg=O.GateConfig(sr=int(fish["sr"]), stationary=True), info=info)
+    assert out.dtype == np.float32
+    assert relinf(out, fish["out_stationary_f32"]) < 1e-7      # equal up to the final float32 cast
+    assert np.abs(info["thresh"] - fish["thresh_f32"]).max() < 1e-9
+
+
+def test_synth_input_is_reproducible(small, tgs):
+    assert np.array_equal(synth_small(), small["y"])
+    assert np.array_equal(synth_torchgate(), tgs["x"])
+
+
+CH = dict(chunk_size=12000, padding=1500)
+
+
+def test_small_stationary_chunked(small):
+    y, sr = small["y"], int(small["sr"])
+    info = {}
+    out = O.reduce_noise(y, sr, cfg=O.GateConfig(sr=sr, stationary=True, **CH), info=info)
+    assert relinf(out, small["out_stat_chunked"]) < 1e-7
+    assert np.abs(info["thresh"] - small["thresh_stat_chunked"]).max() < 1e-9
+    # n_jobs does not change the reference's result
+    assert np.array_equal(small["out_stat_chunked"], small["out_stat_njobs2"])
+    out64 = O.reduce_noise(y, sr, cfg=O.GateConfig(sr=sr, stationary=True, **CH), return_float64=True)
+    assert relinf(out64.astype(np.float32), small["out_stat_chunked"]) < 1e-7
+
+
+def test_small_nonstationary_chunked(small):
+    y, sr = small["y"], int(small["sr"])
+    out = O.reduce_noise(y, sr, cfg=O.GateConfig(sr=sr, stationary=False, **CH))
+    assert relinf(out, small["out_nonstat_chunked"]) < 1e-7
+
+
+def test_small_ynoise_prop_decrease(small):
+    y, sr = small["y"], int(small["sr"])
+    info = {}
+    out = O.reduce_noise(y, sr, y_noise=y[:, 3000:11000],
+                         cfg=O.GateConfig(sr=sr, stationary=True, prop_decrease=0.8, **CH), info=info)
+    assert relinf(out, small["out_stat_ynoise_p08"]) < 1e-7
+    assert np.abs(info["thresh"] - small["thresh_stat_ynoise"]).max() < 1e-9
+
+
+def test_small_nonstationary_2048_f64(small):
+    y, sr = small["y"].astype(np.float64), int(small["sr"])
+    out = O.reduce_noise(y, sr, cfg=O.GateConfig(sr=sr, stationary=False, n_fft=2048, time_constant_s=0.5,
+                                                 prop_decrease=0.9))
+    assert out.dtype == np.float64
+    assert relinf(out, small["out_nonstat_2048_f64"]) < 1e-12
+
+
+def test_small_single_chunk_flat_and_nosmooth(small):
+    y, sr = small["y"], int(small["sr"])
+    out = O.reduce_noise(y[0], sr, cfg=O.GateConfig(sr=sr, stationary=True))
+    assert out.shape == (y.shape[1],)
+    assert relinf(out, small["out_stat_single_chunk"]) < 1e-7
+    out = O.reduce_noise(y, sr, cfg=O.GateConfig(sr=sr, stationary=True, freq_mask_smooth_hz=None,
+                                                 time_mask_smooth_ms=None, **CH))
+    assert relinf(out, small["out_stat_nosmooth"]) < 1e-7
+
+
+def test_prop_decrease_zero_is_identity(small):
+    # notebook 1.0 cells 36-40: prop_decrease=0 returns the input "by eye".  Exactly: the mask is
+    # all ones, and the zero-padded smoothing attenuates the lowest/highest n_grad_freq bins and
+    # the chunk borders (which the chunk centre never sees).  With smoothing off it is the STFT
+    # round trip, i.e. the identity to rounding.
+    y, sr = small["y"], int(small["sr"])
+    out = O.reduce_noise(y, sr, cfg=O.GateConfig(sr=sr, stationary=True, prop_decrease=0.0,
+                                                 freq_mask_smooth_hz=None, time_mask_smooth_ms=None, **CH),
+                         return_float64=True)
+    assert relinf(out, y) < 1e-12
+    out = O.reduce_noise(y, sr, cfg=O.GateConfig(sr=sr, stationary=True, prop_decrease=0.0, **CH),
+                         return_float64=True)
+    assert relinf(out, y) < 0.2          # only the band edges differ
+
+
+def test_errors_match_reference():
+    with pytest.raises(ValueError, match="freq_mask_smooth_hz needs to be at least"):
+        O.smoothing_extents(48000, 1024, 256, 50, 50)
+    with pytest.raises(ValueError, match="time_mask_smooth_ms needs to be at least"):
+        O.smoothing_extents(48000, 1024, 256, 500, 1)
+    with pytest.raises(ValueError, match="Waveform must be in shape"):
+        O.reduce_noise(np.zeros((2, 2, 100)), 16000)
+
+
+# ---- TorchGate surface ---------------------------------------------------------------------
+# The reference builds its window / smoothing taps in float32 and (stationary) smooths the mask
+# in float32 even for float64 input, so the float64 oracle pins it to ~1e-7, not 1e-12.
+TG_TOL = 2e-6
+
+
+def test_torchgate_stationary(tgs):
+    x, sr = tgs["x"], int(tgs["sr"])
+    out = TO.torchgate_forward(x.astype(np.float64), sr, window=tgs["window"], filt=tgs["filt"])
+    assert out.shape == tgs["out_stat_f64"].shape == (3, (x.shape[1] // 256) * 256)
+    assert relinf(out, tgs["out_stat_f64"]) < TG_TOL
+    assert relinf(out, tgs["out_stat_f32"]) < 20 * TG_TOL
+    # default (numpy-built) tables differ from torch's by <= 1 ulp(float32)
+    out2 = TO.torchgate_forward(x.astype(np.float64), sr)
+    assert relinf(out2, tgs["out_stat_f64"]) < TG_TOL
+
+
+def test_torchgate_nonstationary(tgs):
+    x, sr = tgs["x"], int(tgs["sr"])
+    out = TO.torchgate_forward(x.astype(np.float64), sr, nonstationary=True, window=tgs["window"], filt=tgs["filt"])
+    assert relinf(out, tgs["out_nonstat_f64"]) < TG_TOL
+    assert relinf(out, tgs["out_nonstat_f32"]) < 20 * TG_TOL
+
+
+def test_torchgate_xn(tgs):
+    x, sr = tgs["x"].astype(np.float64), int(tgs["sr"])
+    out = TO.torchgate_forward(x, sr, xn=x[:1, :6000], prop_decrease=0.7, window=tgs["window"], filt=tgs["filt"])
+    assert relinf(out, tgs["out_stat_xn_p07_f64"]) < TG_TOL
+    with pytest.raises(Exception, match="x must be bigger than"):
+        TO.torchgate_forward(x[:, :1000], sr)
