@@ -1,0 +1,139 @@
+/* b200gate.h -- C ABI of libb200gate.so, the B200-native spectral-gating operator.
+ *
+ * Drop-in boundary.  Each entry point replaces one piece of the reference
+ * (timsainb/noisereduce @ 51c8534, paths relative to /root/reference):
+ *
+ *   b200gate_create            <- SpectralGate.__init__ geometry + smoothing-filter extents
+ *                                 (noisereduce/spectralgate/base.py:33-128) and the TorchGate
+ *                                 constructor (noisereduce/torchgate/torchgate.py:32-71)
+ *   b200gate_noise_stats       <- the one-time noise statistics of SpectralGateStationary.__init__
+ *                                 (noisereduce/spectralgate/stationary.py:47-81)
+ *   b200gate_run               <- SpectralGate.get_traces() -> filter_chunk -> _do_filter over all
+ *                                 chunks and channels (base.py:130-226; stationary.py:83-131;
+ *                                 nonstationary.py:47-115), i.e. the body of reduce_noise()
+ *                                 (noisereduce/noisereduce.py:185), and TorchGate.forward
+ *                                 (torchgate.py:200-264) when params.surface == B200GATE_SURFACE_TORCH
+ *
+ * Conventions: plain pointers and sizes, no torch / numpy types.  All buffers are caller-owned; the
+ * library owns only its handle and device workspace.  Every function returns B200GATE_OK (0) or a
+ * negative error code; b200gate_last_error() gives the message.  A handle serialises its work on the
+ * CUDA stream passed in (0 = legacy default stream); handles are independent, so one per thread /
+ * per rank is the threading model.  There is no CPU fallback: without a CUDA device
+ * b200gate_create fails with B200GATE_ERR_CUDA.
+ */
+#ifndef B200GATE_H
+#define B200GATE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GATE_ABI_VERSION 1
+
+enum {
+    B200GATE_OK = 0,
+    B200GATE_ERR_ARG = -1,          /* bad argument / unsupported geometry                       */
+    B200GATE_ERR_CUDA = -2,         /* CUDA runtime error (message has the CUDA error string)    */
+    B200GATE_ERR_STATE = -3,        /* call order (e.g. stationary run before noise statistics)  */
+    B200GATE_ERR_NOMEM = -4
+};
+
+enum { B200GATE_F32 = 0, B200GATE_I16 = 1, B200GATE_F64 = 2 };     /* sample dtypes */
+enum { B200GATE_SURFACE_NUMPY = 0, B200GATE_SURFACE_TORCH = 1 };   /* which reference semantics */
+
+/* Resolved operator parameters.  The Python shims resolve defaults exactly as the reference does
+ * (win_length = n_fft, hop_length = win_length // 4, n_grad_* from Hz / ms) and raise the
+ * reference's own exceptions; the library re-validates and rejects what this build cannot run. */
+typedef struct b200gate_params {
+    int32_t abi_version;        /* B200GATE_ABI_VERSION                                          */
+    int32_t surface;            /* B200GATE_SURFACE_*                                            */
+    int32_t stationary;         /* 1: stationary gate, 0: non-stationary gate                    */
+    int32_t n_fft;
+    int32_t win_length;
+    int32_t hop_length;
+    int32_t n_grad_freq;        /* smoothing half-widths; 0,0 = mask smoothing disabled          */
+    int32_t n_grad_time;
+    int32_t std_ddof;           /* 0 numpy surface (np.std), 1 torch surface (std_mean)          */
+    int32_t clip_noise;         /* clip_noise_stationary                                         */
+    int32_t n_movemean;         /* torch surface, non-stationary                                 */
+    int32_t reserved0;
+    int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
+    int64_t padding;
+    double sr;
+    double prop_decrease;
+    double n_std_thresh;        /* n_std_thresh_stationary                                       */
+    double top_db;              /* 80 numpy surface, 40 torch surface                            */
+    double time_constant_s;     /* numpy surface, non-stationary                                 */
+    double thresh_n_mult;       /* thresh_n_mult_nonstationary / n_thresh_nonstationary          */
+    double sigmoid_slope;       /* sigmoid_slope_nonstationary / 1 / temp_coeff_nonstationary    */
+    double workspace_limit_bytes; /* 0: library default; bounds the per-batch device workspace   */
+} b200gate_params;
+
+typedef struct b200gate_handle b200gate_handle;
+
+/* Counters of the last b200gate_run (device-side exactness bookkeeping and launch counts). */
+typedef struct b200gate_stats {
+    int64_t units;                  /* (chunk, channel) units processed                           */
+    int64_t frames;                 /* STFT frames analysed                                       */
+    int64_t kernel_launches;        /* kernels launched by the last run                           */
+    int64_t bins_rechecked_fp64;    /* mask decisions inside the FP32 guard band, redone in FP64  */
+    int64_t bins_unresolved;        /* ... still inside 1e-12 relative after FP64 (expected 0)    */
+    int64_t rowfloor_flags;         /* (unit, bin) rows lifted by the top_db floor                */
+    int64_t rowfloor_ambiguous;     /* ... whose FP32 decision was inside the guard band (exp. 0) */
+    double last_run_ms;             /* device time of the last run, CUDA events on its stream     */
+    double last_h2d_ms, last_d2h_ms;
+} b200gate_stats;
+
+int b200gate_create(const b200gate_params* params, b200gate_handle** out);
+void b200gate_destroy(b200gate_handle* h);
+const char* b200gate_last_error(const b200gate_handle* h);   /* h == NULL: last create() error */
+
+/* Stationary noise statistics (stationary.py:47-81): channel mean in the input dtype, clip to
+ * chunk_size, STFT, dB with top_db floor, per-bin mean/std over time, thresh = mean + n_std*std.
+ * y_noise: [C][N] samples, row stride `stride` elements, host or device memory. */
+int b200gate_noise_stats(b200gate_handle* h, const void* y_noise, int dtype, int64_t C, int64_t N,
+                         int64_t stride, int is_device, void* cuda_stream);
+/* Same, from an already collapsed (channel-mean) noise clip of n samples in float64 or float32:
+ * used by multi-GPU callers that build the channel mean across ranks themselves. */
+int b200gate_noise_stats_collapsed(b200gate_handle* h, const void* noise_mean, int dtype, int64_t n,
+                                   int is_device, void* cuda_stream);
+/* Channel-order partial sum of the first `n` samples of `C` channels, continuing from *acc_inout
+ * (device buffer of n elements: float32 for F32 input, float64 otherwise; ignored if init != 0).
+ * Lets ranks chain the reference's sequential float32 channel sum exactly. */
+int b200gate_channel_sum(b200gate_handle* h, const void* y, int dtype, int64_t C, int64_t n,
+                         int64_t stride, int is_device, void* acc_inout_device, int init,
+                         void* cuda_stream);
+int b200gate_set_noise_threshold(b200gate_handle* h, const double* thresh_db, int32_t n_bins);
+int b200gate_get_noise_threshold(const b200gate_handle* h, double* thresh_db, int32_t n_bins);
+int b200gate_get_noise_mean_std(const b200gate_handle* h, double* mean_db, double* std_db, int32_t n_bins);
+
+/* Torch surface only: install the analysis/synthesis window the caller built with
+ * torch.hann_window (float32, win_length values), so tables match the reference bit for bit. */
+int b200gate_set_window(b200gate_handle* h, const float* window, int32_t win_length);
+
+/* The operator.  in/out: [C][N] samples of `dtype` with row strides in elements; host or device
+ * pointers (is_device).  out may not alias in.  For the torch surface out holds [C][(N/hop)*hop].
+ * Returns after the work is enqueued for device pointers; for host pointers it returns after the
+ * result is in `out`. */
+int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64_t C, int64_t N,
+                 int64_t in_stride, int64_t out_stride, int is_device, void* cuda_stream);
+
+int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out);
+
+/* ---- parity-test taps (tests/ only; read back stage outputs of the last run) ---------------- */
+/* Select the (chunk, channel) unit whose stages the next run keeps.  chunk < 0 disables. */
+int b200gate_debug_select_unit(b200gate_handle* h, int64_t chunk, int64_t channel);
+/* Frames of the tapped unit; bits: [T][words] packed mask decisions (bit f%32 of word f/32),
+ * with the top_db row floor already folded in.  mask: [T][F] smoothed multiplicative mask.
+ * spec: [T][F][2] float, the FP32 STFT (re, im) as the analysis kernel saw it. */
+int b200gate_debug_dims(const b200gate_handle* h, int64_t* T, int32_t* F, int32_t* words);
+int b200gate_debug_read_bits(b200gate_handle* h, uint32_t* bits);
+int b200gate_debug_read_mask(b200gate_handle* h, float* mask);
+int b200gate_debug_read_spec(b200gate_handle* h, float* spec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GATE_H */

@@ -1,0 +1,55 @@
+"""Build libb200gate.so (the product library) with nvcc for sm_100a, in-tree.
+
+    python -m noisereduce_b200.csrc.build            # or: python noisereduce_b200/csrc/build.py
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with gpurun.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(os.path.dirname(HERE), "libb200gate.so")
+SOURCES = ["gate_host.cu"]
+DEPS = ["gate_host.cu", "gate_kernels.cuh", "warp_fft.cuh", "cuda_compat.h", os.path.join(ROOT, "include", "b200gate.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-Xptxas", "-v",
+    "--use_fast_math" if False else "-DB200_NO_FAST_MATH",
+]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    for d in DEPS:
+        p = d if os.path.isabs(d) else os.path.join(HERE, d)
+        if os.path.getmtime(p) > t:
+            return True
+    return False
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", HERE, "-o", OUT] + \
+          [os.path.join(HERE, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if res.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libb200gate.so")
+    if verbose:
+        print(log)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

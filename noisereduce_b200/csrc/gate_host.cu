@@ -1,0 +1,677 @@
+// gate_host.cu -- C ABI (include/b200gate.h) and host planner of libb200gate.
+//
+// The planner turns the reference's chunk loop (noisereduce/spectralgate/base.py:167-226) into a
+// table of independent (chunk, channel) units, sizes the device workspace, and launches
+// k1_analyze -> k_rowfloor -> k_smooth -> k2_synthesize per batch of units on the caller's stream.
+#include "../../include/b200gate.h"
+#include "gate_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+const double kEps64 = 2.220446049250313e-16;       // np.finfo(np.float64).eps (spectralgate/utils.py:11)
+const double kEps32 = 5.9604644775390625e-08;      // 2^-24, FP32 unit roundoff
+const double kKappa = 16.0;                        // guard band: |dX| <= kappa * eps32 * ||frame pair||_2
+std::string g_create_error;
+
+}  // namespace
+
+struct b200gate_handle {
+    b200gate_params p{};
+    std::string err;
+    int num_sm = 148;
+    int F = kF;
+    // device tables
+    float *d_wa = nullptr, *d_ws = nullptr, *d_invn = nullptr, *d_thr4 = nullptr, *d_gco = nullptr,
+          *d_floor4 = nullptr, *d_ef = nullptr;
+    float2* d_tw = nullptr;
+    double *d_thr2_64 = nullptr, *d_wa64 = nullptr;
+    double2* d_cs64 = nullptr;
+    float ws_to_w = 0.f;
+    bool have_thresh = false;
+    std::vector<double> thr, mean, sd;
+    // workspace
+    char* d_ws_buf = nullptr;
+    size_t ws_bytes = 0;
+    float *d_in = nullptr, *d_out = nullptr;       // staging for host / non-f32 callers
+    size_t in_bytes = 0, out_bytes = 0;
+    void* d_raw = nullptr;                         // raw-dtype staging
+    size_t raw_bytes = 0;
+    Counters* d_cnt = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    b200gate_stats stats{};
+    // debug taps
+    long long dbg_chunk = -1, dbg_channel = -1;
+    long long dbg_T = 0;
+    float *d_dbg_spec = nullptr, *d_dbg_mask = nullptr;
+    unsigned* d_dbg_bits = nullptr;
+    size_t dbg_T_alloc = 0;
+};
+
+namespace {
+
+int fail(b200gate_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(h, call)                                                                            \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail((h), B200GATE_ERR_CUDA, "%s failed: %s (%s:%d)", #call,               \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                           \
+    } while (0)
+
+template <class T>
+int upload(b200gate_handle* h, T** dptr, const std::vector<T>& v) {
+    if (!*dptr) CK(h, cudaMalloc((void**)dptr, v.size() * sizeof(T)));
+    CK(h, cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return B200GATE_OK;
+}
+
+int ensure(b200gate_handle* h, void** p, size_t* have, size_t need) {
+    if (*have >= need) return B200GATE_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return fail(h, B200GATE_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+    *have = need;
+    return B200GATE_OK;
+}
+
+// Tables that depend only on the geometry: windows, twiddles, overlap-add norm, edge factors.
+int build_static_tables(b200gate_handle* h) {
+    const int N = h->p.n_fft, H = h->p.hop_length;
+    std::vector<double> w(N);
+    double sw = 0.0;
+    for (int n = 0; n < N; ++n) {
+        w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)N);    // periodic Hann (scipy 'hann', fftbins)
+        sw += w[n];
+    }
+    std::vector<float> wa(N), ws(N), invn(H);
+    std::vector<double> wa64(N);
+    for (int n = 0; n < N; ++n) {
+        wa64[n] = w[n] / sw;
+        wa[n] = (float)(w[n] / sw);
+        ws[n] = (float)(w[n] * sw / (double)N);
+    }
+    h->ws_to_w = (float)((double)N / sw);
+    for (int r = 0; r < H; ++r) {
+        double s = 0.0;
+        for (int i = 0; i * H + r < N; ++i) s += w[i * H + r] * w[i * H + r];
+        invn[r] = (float)(s > 1e-10 ? 1.0 / s : 1.0);
+    }
+    std::vector<float2> tw(32 * 32);
+    for (int q = 0; q < 32; ++q)
+        for (int l = 0; l < 32; ++l) {
+            const long double th = 2.0L * M_PIl * (long double)(l * q) / 1024.0L;
+            tw[q * 32 + l] = make_float2((float)cosl(th), (float)(-sinl(th)));
+        }
+    std::vector<double2> cs(N);
+    for (int m = 0; m < N; ++m) {
+        const long double th = 2.0L * M_PIl * (long double)m / (long double)N;
+        cs[m] = make_double2((double)cosl(th), (double)sinl(th));
+    }
+    const int nf = h->p.n_grad_freq;
+    std::vector<float> ef(kFPad, 0.f);
+    for (int f = 0; f < kF; ++f) {
+        long s = 0;
+        for (int d = -nf; d <= nf; ++d)
+            if (f - d >= 0 && f - d < kF) s += nf + 1 - abs(d);
+        ef[f] = (float)((double)s / (double)((nf + 1) * (nf + 1)));
+    }
+    int rc;
+    if ((rc = upload(h, &h->d_wa, wa))) return rc;
+    if ((rc = upload(h, &h->d_ws, ws))) return rc;
+    if ((rc = upload(h, &h->d_invn, invn))) return rc;
+    if ((rc = upload(h, &h->d_tw, tw))) return rc;
+    if ((rc = upload(h, &h->d_cs64, cs))) return rc;
+    if ((rc = upload(h, &h->d_wa64, wa64))) return rc;
+    if ((rc = upload(h, &h->d_ef, ef))) return rc;
+    return B200GATE_OK;
+}
+
+// Tables that depend on the noise threshold (stationary.py:79-81), in the linear power domain:
+// dB > thresh  <=>  |X| + eps > 10^(thresh/20)  <=>  |X|^2 > T_amp^2.
+int build_threshold_tables(b200gate_handle* h) {
+    std::vector<float> thr4(kFPad, INFINITY), gco(kFPad, 0.f), floor4(kFPad, INFINITY);
+    std::vector<double> t2(kF);
+    for (int f = 0; f < kF; ++f) {
+        double T = pow(10.0, h->thr[f] / 20.0) - kEps64;
+        if (!(T > 0.0)) T = 0.0;
+        double Tf = pow(10.0, (h->thr[f] + h->p.top_db) / 20.0) - kEps64;
+        if (!(Tf > 0.0)) Tf = 0.0;
+        t2[f] = T * T;
+        thr4[f] = (float)(4.0 * T * T);
+        gco[f] = (float)(8.0 * T * kKappa * kEps32);
+        floor4[f] = (float)(4.0 * Tf * Tf);
+    }
+    int rc;
+    if ((rc = upload(h, &h->d_thr4, thr4))) return rc;
+    if ((rc = upload(h, &h->d_gco, gco))) return rc;
+    if ((rc = upload(h, &h->d_floor4, floor4))) return rc;
+    if ((rc = upload(h, &h->d_thr2_64, t2))) return rc;
+    h->have_thresh = true;
+    return B200GATE_OK;
+}
+
+Tables device_tables(const b200gate_handle* h) {
+    Tables tb{};
+    tb.wa = h->d_wa; tb.ws = h->d_ws; tb.tw = h->d_tw; tb.invn = h->d_invn;
+    tb.thr4 = h->d_thr4; tb.gco = h->d_gco; tb.floor4 = h->d_floor4; tb.ef = h->d_ef;
+    tb.thr2_64 = h->d_thr2_64; tb.wa64 = h->d_wa64; tb.cs64 = h->d_cs64;
+    tb.ws_to_w = h->ws_to_w;
+    return tb;
+}
+
+size_t dtype_size(int dtype) { return dtype == B200GATE_F32 ? 4 : dtype == B200GATE_I16 ? 2 : dtype == B200GATE_F64 ? 8 : 0; }
+
+int grid_1d(long long n, int block, int cap) {
+    long long g = (n + block - 1) / block;
+    return (int)std::max(1LL, std::min<long long>(g, cap));
+}
+
+// collapsed noise clip (float64, device) -> thresholds
+int noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, cudaStream_t st) {
+    const int H = h->p.hop_length;
+    const int Tn = (int)(n / H) + 1;                     // scipy: (n + 2*(W/2) - W)/H + 1
+    double *d_db = nullptr, *d_res = nullptr;
+    CK(h, cudaMalloc((void**)&d_db, (size_t)Tn * kF * sizeof(double)));
+    CK(h, cudaMalloc((void**)&d_res, 3 * kF * sizeof(double)));
+    K0Args a{};
+    a.yn = d_yn; a.n = n; a.H = H; a.Tn = Tn; a.wa64 = h->d_wa64; a.cs64 = h->d_cs64; a.eps = kEps64; a.db = d_db;
+    B200_LAUNCH(k0_stft_db, dim3(Tn), dim3(256), kN * sizeof(double2), st, a);
+    B200_LAUNCH(k0_stats, dim3(kF), dim3(256), 0, st, d_db, Tn, h->p.top_db, h->p.std_ddof, h->p.n_std_thresh,
+                d_res, d_res + kF, d_res + 2 * kF);
+    CK(h, cudaGetLastError());
+    std::vector<double> res(3 * kF);
+    CK(h, cudaMemcpyAsync(res.data(), d_res, res.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    cudaFree(d_db);
+    cudaFree(d_res);
+    h->mean.assign(res.begin(), res.begin() + kF);
+    h->sd.assign(res.begin() + kF, res.begin() + 2 * kF);
+    h->thr.assign(res.begin() + 2 * kF, res.end());
+    return build_threshold_tables(h);
+}
+
+template <typename Tin, typename Tacc>
+void launch_channel_sum(const void* y, long long C, long long n, long long stride, void* acc, int init, cudaStream_t st) {
+    auto kern = k0_channel_sum<Tin, Tacc>;
+    B200_LAUNCH(kern, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const Tin*)y, C, n, stride, (Tacc*)acc, init);
+}
+
+// device-resident (or staged) y -> running channel-order sum in acc
+int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, long long n, long long stride,
+                     int is_device, void* acc, int init, cudaStream_t st) {
+    const size_t es = dtype_size(dtype);
+    const void* src = y;
+    long long sstride = stride;
+    void* tmp = nullptr;
+    if (!is_device) {
+        CK(h, cudaMalloc(&tmp, (size_t)C * n * es));
+        CK(h, cudaMemcpy2DAsync(tmp, (size_t)n * es, y, (size_t)stride * es, (size_t)n * es, (size_t)C,
+                                cudaMemcpyHostToDevice, st));
+        src = tmp;
+        sstride = n;
+    }
+    if (dtype == B200GATE_F32) launch_channel_sum<float, float>(src, C, n, sstride, acc, init, st);
+    else if (dtype == B200GATE_I16) launch_channel_sum<short, double>(src, C, n, sstride, acc, init, st);
+    else launch_channel_sum<double, double>(src, C, n, sstride, acc, init, st);
+    CK(h, cudaGetLastError());
+    if (tmp) {
+        CK(h, cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+    return B200GATE_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
+    if (!p || !out) return fail(nullptr, B200GATE_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (p->abi_version != B200GATE_ABI_VERSION)
+        return fail(nullptr, B200GATE_ERR_ARG, "ABI version %d, library is %d", p->abi_version, B200GATE_ABI_VERSION);
+    if (p->surface != B200GATE_SURFACE_NUMPY)
+        return fail(nullptr, B200GATE_ERR_ARG, "surface %d is not built into this library yet", p->surface);
+    if (!p->stationary)
+        return fail(nullptr, B200GATE_ERR_ARG, "the non-stationary gate is not built into this library yet");
+    if (p->n_fft != kN || p->win_length != p->n_fft || p->hop_length * 4 != p->n_fft)
+        return fail(nullptr, B200GATE_ERR_ARG,
+                    "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d: this build runs "
+                    "n_fft=1024, win_length=n_fft, hop_length=n_fft/4",
+                    p->n_fft, p->win_length, p->hop_length);
+    if (p->n_grad_freq < 0 || p->n_grad_time < 0 || p->n_grad_freq > 64 || p->n_grad_time > 64)
+        return fail(nullptr, B200GATE_ERR_ARG, "smoothing extents out of range (%d, %d)", p->n_grad_freq, p->n_grad_time);
+    if ((long long)(p->n_grad_freq + 1) * (p->n_grad_freq + 1) * (p->n_grad_time + 1) * (p->n_grad_time + 1) > 65535)
+        return fail(nullptr, B200GATE_ERR_ARG, "smoothing filter too large for 16-bit mask numerators");
+    if (p->padding < 0) return fail(nullptr, B200GATE_ERR_ARG, "padding must be >= 0");
+    if (!(p->prop_decrease >= 0.0 && p->prop_decrease <= 1.0))
+        return fail(nullptr, B200GATE_ERR_ARG, "prop_decrease must be in [0, 1]");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, B200GATE_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    b200gate_handle* h = new b200gate_handle();
+    h->p = *p;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->num_sm = prop.multiProcessorCount;
+    int rc = build_static_tables(h);
+    if (rc == B200GATE_OK) {
+        e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
+        if (e != cudaSuccess) rc = fail(h, B200GATE_ERR_CUDA, "cudaMalloc counters: %s", cudaGetErrorString(e));
+    }
+    if (rc == B200GATE_OK) {
+        cudaEventCreate(&h->ev0);
+        cudaEventCreate(&h->ev1);
+#ifndef B200_CUSIM_BUILD
+        cudaFuncSetAttribute(k1_analyze<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats() * 4);
+        cudaFuncSetAttribute(k2_synthesize<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
+        cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+#endif
+    }
+    if (rc != B200GATE_OK) {
+        g_create_error = h->err;
+        b200gate_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return B200GATE_OK;
+}
+
+void b200gate_destroy(b200gate_handle* h) {
+    if (!h) return;
+    void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
+                    h->d_wa64, h->d_cs64, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
+                    h->d_dbg_mask, h->d_dbg_bits};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+const char* b200gate_last_error(const b200gate_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b200gate_set_noise_threshold(b200gate_handle* h, const double* thresh_db, int32_t n_bins) {
+    if (!h || !thresh_db) return B200GATE_ERR_ARG;
+    if (n_bins != kF) return fail(h, B200GATE_ERR_ARG, "expected %d bins, got %d", kF, n_bins);
+    h->thr.assign(thresh_db, thresh_db + kF);
+    h->mean.assign(kF, NAN);
+    h->sd.assign(kF, NAN);
+    return build_threshold_tables(h);
+}
+
+int b200gate_get_noise_threshold(const b200gate_handle* h, double* thresh_db, int32_t n_bins) {
+    if (!h || !thresh_db || n_bins != kF || !h->have_thresh) return B200GATE_ERR_STATE;
+    memcpy(thresh_db, h->thr.data(), kF * sizeof(double));
+    return B200GATE_OK;
+}
+
+int b200gate_get_noise_mean_std(const b200gate_handle* h, double* mean_db, double* std_db, int32_t n_bins) {
+    if (!h || n_bins != kF || !h->have_thresh) return B200GATE_ERR_STATE;
+    if (mean_db) memcpy(mean_db, h->mean.data(), kF * sizeof(double));
+    if (std_db) memcpy(std_db, h->sd.data(), kF * sizeof(double));
+    return B200GATE_OK;
+}
+
+int b200gate_set_window(b200gate_handle* h, const float*, int32_t) {
+    return fail(h, B200GATE_ERR_ARG, "b200gate_set_window: torch surface not built yet");
+}
+
+int b200gate_channel_sum(b200gate_handle* h, const void* y, int dtype, int64_t C, int64_t n, int64_t stride,
+                         int is_device, void* acc, int init, void* stream) {
+    if (!h || !y || !acc || C <= 0 || n <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
+    return channel_sum_impl(h, y, dtype, C, n, stride, is_device, acc, init, (cudaStream_t)stream);
+}
+
+int b200gate_noise_stats_collapsed(b200gate_handle* h, const void* noise_mean, int dtype, int64_t n, int is_device,
+                                   void* stream) {
+    if (!h || !noise_mean || n <= 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
+    if (dtype != B200GATE_F32 && dtype != B200GATE_F64) return fail(h, B200GATE_ERR_ARG, "collapsed noise must be f32 or f64");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = dtype_size(dtype);
+    void* d_src = nullptr;
+    double* d_yn = nullptr;
+    CK(h, cudaMalloc((void**)&d_yn, (size_t)n * sizeof(double)));
+    const void* src = noise_mean;
+    if (!is_device) {
+        CK(h, cudaMalloc(&d_src, (size_t)n * es));
+        CK(h, cudaMemcpyAsync(d_src, noise_mean, (size_t)n * es, cudaMemcpyHostToDevice, st));
+        src = d_src;
+    }
+    if (dtype == B200GATE_F32)
+        { auto kern_ = k0_mean_to_f64<float>; B200_LAUNCH(kern_, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const float*)src, (long long)n, 1LL, d_yn); }
+    else
+        { auto kern_ = k0_mean_to_f64<double>; B200_LAUNCH(kern_, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const double*)src, (long long)n, 1LL, d_yn); }
+    int rc = noise_stats_from_mean(h, d_yn, n, st);
+    cudaFree(d_yn);
+    if (d_src) cudaFree(d_src);
+    return rc;
+}
+
+int b200gate_noise_stats(b200gate_handle* h, const void* y_noise, int dtype, int64_t C, int64_t N, int64_t stride,
+                         int is_device, void* stream) {
+    if (!h || !y_noise || C <= 0 || N <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long n = N;
+    if (h->p.clip_noise && h->p.chunk_size > 0 && n > h->p.chunk_size) n = h->p.chunk_size;   // stationary.py:63-64
+    const bool f32 = (dtype == B200GATE_F32);
+    void* d_acc = nullptr;
+    double* d_yn = nullptr;
+    CK(h, cudaMalloc(&d_acc, (size_t)n * (f32 ? 4 : 8)));
+    CK(h, cudaMalloc((void**)&d_yn, (size_t)n * sizeof(double)));
+    int rc = channel_sum_impl(h, y_noise, dtype, C, n, stride, is_device, d_acc, 1, st);
+    if (rc == B200GATE_OK) {
+        if (f32)
+            { auto kern_ = k0_mean_to_f64<float>; B200_LAUNCH(kern_, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const float*)d_acc, n, (long long)C, d_yn); }
+        else
+            { auto kern_ = k0_mean_to_f64<double>; B200_LAUNCH(kern_, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const double*)d_acc, n, (long long)C, d_yn); }
+        rc = noise_stats_from_mean(h, d_yn, n, st);
+    }
+    cudaFree(d_acc);
+    cudaFree(d_yn);
+    return rc;
+}
+
+int b200gate_debug_select_unit(b200gate_handle* h, int64_t chunk, int64_t channel) {
+    if (!h) return B200GATE_ERR_ARG;
+    h->dbg_chunk = chunk;
+    h->dbg_channel = channel;
+    return B200GATE_OK;
+}
+
+int b200gate_debug_dims(const b200gate_handle* h, int64_t* T, int32_t* F, int32_t* words) {
+    if (!h) return B200GATE_ERR_ARG;
+    if (T) *T = h->dbg_T;
+    if (F) *F = kF;
+    if (words) *words = kFW;
+    return B200GATE_OK;
+}
+
+int b200gate_debug_read_bits(b200gate_handle* h, uint32_t* bits) {
+    if (!h || !bits || !h->d_dbg_bits || h->dbg_T <= 0) return B200GATE_ERR_STATE;
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(bits, h->d_dbg_bits, (size_t)h->dbg_T * kFW * 4, cudaMemcpyDeviceToHost));
+    return B200GATE_OK;
+}
+int b200gate_debug_read_mask(b200gate_handle* h, float* mask) {
+    if (!h || !mask || !h->d_dbg_mask || h->dbg_T <= 0) return B200GATE_ERR_STATE;
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(mask, h->d_dbg_mask, (size_t)h->dbg_T * kF * 4, cudaMemcpyDeviceToHost));
+    return B200GATE_OK;
+}
+int b200gate_debug_read_spec(b200gate_handle* h, float* spec) {
+    if (!h || !spec || !h->d_dbg_spec || h->dbg_T <= 0) return B200GATE_ERR_STATE;
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(spec, h->d_dbg_spec, (size_t)h->dbg_T * kF * 8, cudaMemcpyDeviceToHost));
+    return B200GATE_OK;
+}
+
+int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out) {
+    if (!h || !out) return B200GATE_ERR_ARG;
+    *out = h->stats;
+    return B200GATE_OK;
+}
+
+int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64_t C, int64_t N, int64_t in_stride,
+                 int64_t out_stride, int is_device, void* stream) {
+    if (!h || !in || !out || C <= 0 || N <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
+    if (in_stride < N || out_stride < N) return fail(h, B200GATE_ERR_ARG, "row strides must be >= N");
+    if (!h->have_thresh) return fail(h, B200GATE_ERR_STATE, "stationary gate: call b200gate_noise_stats first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const b200gate_params& p = h->p;
+    const size_t es = dtype_size(dtype);
+    h->stats = b200gate_stats{};
+    long long launches = 0;
+
+    // ---- stage to float32 device rows ------------------------------------------------------
+    const float* x = nullptr;
+    float* y = nullptr;
+    long long xs = in_stride, ys = out_stride;
+    const bool direct = is_device && dtype == B200GATE_F32;
+    if (direct) {
+        x = (const float*)in;
+        y = (float*)out;
+    } else {
+        int rc;
+        if ((rc = ensure(h, (void**)&h->d_in, &h->in_bytes, (size_t)C * N * 4))) return rc;
+        if ((rc = ensure(h, (void**)&h->d_out, &h->out_bytes, (size_t)C * N * 4))) return rc;
+        x = h->d_in;
+        y = h->d_out;
+        xs = ys = N;
+        const void* raw = in;
+        long long rs = in_stride;
+        if (!is_device) {
+            if (dtype == B200GATE_F32) {
+                CK(h, cudaMemcpy2DAsync(h->d_in, (size_t)N * 4, in, (size_t)in_stride * 4, (size_t)N * 4, (size_t)C,
+                                        cudaMemcpyHostToDevice, st));
+                raw = nullptr;
+            } else {
+                if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * N * es))) return rc;
+                CK(h, cudaMemcpy2DAsync(h->d_raw, (size_t)N * es, in, (size_t)in_stride * es, (size_t)N * es, (size_t)C,
+                                        cudaMemcpyHostToDevice, st));
+                raw = h->d_raw;
+                rs = N;
+            }
+        }
+        if (raw) {
+            const int gr = grid_1d((long long)C * N, 256, h->num_sm * 16);
+            if (dtype == B200GATE_I16)
+                { auto kern_ = k_to_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const short*)raw, h->d_in, (long long)C, (long long)N, rs, (long long)N); }
+            else if (dtype == B200GATE_F64)
+                { auto kern_ = k_to_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const double*)raw, h->d_in, (long long)C, (long long)N, rs, (long long)N); }
+            else   // f32 on device with a stride we cannot use directly never happens (direct path)
+                { auto kern_ = k_to_f32<float>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)raw, h->d_in, (long long)C, (long long)N, rs, (long long)N); }
+            ++launches;
+        }
+    }
+    float h2d_ms = 0.f;
+    cudaEvent_t evk0 = h->ev0, evk1 = h->ev1;
+
+    // ---- geometry (base.py:167-226) -----------------------------------------------------------
+    Geom g{};
+    g.H = p.hop_length;
+    g.C = (int)C;
+    g.n_total = N;
+    const bool chunked = p.chunk_size > 0 && N > p.chunk_size;
+    g.step = chunked ? p.chunk_size : N;
+    g.n_chunks = chunked ? (int)((N - 1) / p.chunk_size) + 1 : 1;
+    g.pad = p.padding;
+    g.Lp = g.step + 2 * g.pad;
+    g.T = (int)(g.Lp / g.H) + 1;
+    g.in_stride = xs;
+    g.out_stride = ys;
+    const long long U = (long long)g.n_chunks * C;
+    if (U > 0x7fffffffLL || g.Lp / g.H > 0x3fffffffLL) return fail(h, B200GATE_ERR_ARG, "problem too large");
+
+    // frames whose masks k2 needs (same for every full chunk)
+    const long long sig_len = (long long)(g.T - 1) * g.H;
+    long long jp_hi = std::min(g.pad + g.step, sig_len);
+    int tf_lo = 0, tf_hi = 0;
+    int h_lo = 0, h_hi = 0;
+    if (jp_hi > g.pad) {
+        h_lo = (int)((g.pad + kN / 2) / g.H);
+        h_hi = (int)((jp_hi + kN / 2 + g.H - 1) / g.H);
+        tf_lo = std::max(0, h_lo - 3);
+        tf_hi = std::min(h_hi, g.T);
+    }
+    const bool tail_zeros = (g.pad + g.step > sig_len);     // stationary.py:126 leaves the tail zero
+    if (tail_zeros) {
+        for (long long c = 0; c < C; ++c) CK(h, cudaMemsetAsync(y + c * ys, 0, (size_t)N * 4, st));
+    }
+
+    // ---- workspace / batching ---------------------------------------------------------------------
+    const size_t per_unit = (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64;
+    double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
+    long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
+    ub = std::min(ub, U);
+    {
+        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, per_unit * (size_t)ub);
+        if (rc) return rc;
+    }
+    unsigned* d_bits = (unsigned*)h->d_ws_buf;
+    unsigned* d_rowmax = d_bits + (size_t)ub * g.T * kFW;
+    unsigned* d_rowflag = d_rowmax + (size_t)ub * kFPad;
+    unsigned short* d_num = (unsigned short*)(d_rowflag + (size_t)ub * kFW);
+
+    CK(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), st));
+    const long long dbg_u = (h->dbg_chunk >= 0 && h->dbg_chunk < g.n_chunks && h->dbg_channel >= 0 && h->dbg_channel < C)
+                                ? h->dbg_chunk * C + h->dbg_channel : -1;
+    if (dbg_u >= 0) {
+        if (h->dbg_T_alloc < (size_t)g.T) {
+            if (h->d_dbg_spec) cudaFree(h->d_dbg_spec);
+            if (h->d_dbg_mask) cudaFree(h->d_dbg_mask);
+            if (h->d_dbg_bits) cudaFree(h->d_dbg_bits);
+            CK(h, cudaMalloc((void**)&h->d_dbg_spec, (size_t)g.T * kF * 8));
+            CK(h, cudaMalloc((void**)&h->d_dbg_mask, (size_t)g.T * kF * 4));
+            CK(h, cudaMalloc((void**)&h->d_dbg_bits, (size_t)g.T * kFW * 4));
+            h->dbg_T_alloc = g.T;
+        }
+        CK(h, cudaMemsetAsync(h->d_dbg_spec, 0, (size_t)g.T * kF * 8, st));
+        CK(h, cudaMemsetAsync(h->d_dbg_mask, 0, (size_t)g.T * kF * 4, st));
+        h->dbg_T = g.T;
+    } else {
+        h->dbg_T = 0;
+    }
+
+    const Tables tb = device_tables(h);
+    const int nf = p.n_grad_freq, nt = p.n_grad_time;
+    const double D = (double)(nf + 1) * (nf + 1) * (nt + 1) * (nt + 1);
+    const int resident = h->num_sm * 3;
+
+    cudaEventRecord(evk0, st);
+    for (long long u0 = 0; u0 < U; u0 += ub) {
+        const int nu = (int)std::min(ub, U - u0);
+        g.u0 = (int)u0;
+        g.n_units = nu;
+        DebugTap dbg{};
+        dbg.ul = (dbg_u >= u0 && dbg_u < u0 + nu) ? (int)(dbg_u - u0) : -1;
+        dbg.spec = h->d_dbg_spec;
+        dbg.mask = h->d_dbg_mask;
+
+        CK(h, cudaMemsetAsync(d_rowmax, 0, (size_t)nu * kFPad * 4, st));
+        // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
+        K1Args a1{};
+        a1.g = g; a1.tb = tb; a1.x = x; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
+        {
+            long long want = (long long)resident * kWarps * 4;
+            long long run = ((long long)nu * g.T + want - 1) / want;
+            run = std::max(8LL, std::min(64LL, run));
+            run += run & 1;
+            a1.run = (int)run;
+            a1.n_runs = (g.T + a1.run - 1) / a1.run;
+        }
+        const long long items1 = (long long)nu * a1.n_runs;
+        B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, resident)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
+        B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
+                    (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
+        launches += 2;
+        if (tf_hi > tf_lo) {
+            SmoothArgs sa{};
+            sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
+            sa.bits = d_bits; sa.rowflag = d_rowflag; sa.num = d_num;
+            const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+            B200_LAUNCH(k_smooth, dim3(tiles, nu), dim3(256), smooth_smem_bytes(sa.TT, nf, nt), st, sa);
+            K2Args a2{};
+            a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.num = d_num;
+            a2.pD = (float)(p.prop_decrease / D);
+            a2.one_minus_p = (float)(1.0 - p.prop_decrease);
+            a2.nt = nt;
+            a2.dbg = dbg;
+            {
+                const long long hops = h_hi - h_lo;
+                long long want = (long long)resident * kWarps * 4;
+                long long run = ((long long)nu * hops + want - 1) / want;
+                run = std::max(16LL, std::min(128LL, run));
+                run += run & 1;
+                a2.run = (int)run;
+                a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
+            }
+            const long long items2 = (long long)nu * a2.n_runs;
+            B200_LAUNCH(k2_synthesize<8>, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
+                        k2_smem_floats(g.H) * 4, st, a2);
+            launches += 2;
+        }
+        if (dbg.ul >= 0) {
+            // tapped mask words with the row floor folded in, as the smoothing kernel consumes them
+            std::vector<unsigned> fl(kFW);
+            CK(h, cudaStreamSynchronize(st));
+            CK(h, cudaMemcpy(fl.data(), d_rowflag + (size_t)dbg.ul * kFW, kFW * 4, cudaMemcpyDeviceToHost));
+            std::vector<unsigned> bb((size_t)g.T * kFW);
+            CK(h, cudaMemcpy(bb.data(), d_bits + (size_t)dbg.ul * g.T * kFW, bb.size() * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < bb.size(); ++i) bb[i] |= fl[i % kFW];
+            CK(h, cudaMemcpy(h->d_dbg_bits, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice));
+        }
+        CK(h, cudaGetLastError());
+    }
+    cudaEventRecord(evk1, st);
+
+    // ---- results back -------------------------------------------------------------------------------
+    if (!direct) {
+        const void* res = y;
+        if (dtype != B200GATE_F32) {
+            int rc;
+            if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * N * es))) return rc;
+            const int gr = grid_1d((long long)C * N, 256, h->num_sm * 16);
+            void* dst = is_device ? out : h->d_raw;
+            const long long ds = is_device ? out_stride : N;
+            if (dtype == B200GATE_I16)
+                { auto kern_ = k_from_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (short*)dst, (long long)C, (long long)N, ys, ds); }
+            else
+                { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (double*)dst, (long long)C, (long long)N, ys, ds); }
+            ++launches;
+            res = h->d_raw;
+        } else if (is_device) {
+            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * 4, y, (size_t)ys * 4, (size_t)N * 4, (size_t)C,
+                                    cudaMemcpyDeviceToDevice, st));
+        }
+        if (!is_device)
+            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, res, (size_t)N * es, (size_t)N * es, (size_t)C,
+                                    cudaMemcpyDeviceToHost, st));
+    }
+    CK(h, cudaGetLastError());
+
+    // ---- stats (forces completion; device callers pay one sync for exactness bookkeeping) -----------
+    Counters cnt{};
+    CK(h, cudaMemcpyAsync(&cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, evk0, evk1);
+    h->stats.units = U;
+    h->stats.frames = U * g.T;
+    h->stats.kernel_launches = launches;
+    h->stats.bins_rechecked_fp64 = (int64_t)cnt.rechecked;
+    h->stats.bins_unresolved = (int64_t)cnt.unresolved;
+    h->stats.rowfloor_flags = (int64_t)cnt.floor_flags;
+    h->stats.rowfloor_ambiguous = (int64_t)cnt.floor_ambiguous;
+    h->stats.last_run_ms = ms;
+    h->stats.last_h2d_ms = h2d_ms;
+    return B200GATE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,674 @@
+// gate_kernels.cuh -- sm_100a kernels of the spectral-gating hot path (n_fft = 1024 family).
+//
+// Reference semantics restated by these kernels (paths relative to /root/reference):
+//   framing / STFT          scipy.signal.stft as called at noisereduce/spectralgate/stationary.py:87-93
+//   dB floor + threshold    spectralgate/utils.py:11-16, stationary.py:96-110
+//   mask smoothing          base.py:7-29 filter, fftconvolve(..., "same") at stationary.py:114
+//   apply + iSTFT           stationary.py:117-126 (scipy.signal.istft)
+//   chunk geometry          base.py:130-156, :167-226
+//
+// Work decomposition.  A *unit* is one (chunk, channel) pair -- the reference's _do_filter runs them
+// independently (stationary.py:86), so they are the grid.  Inside a unit every warp is an autonomous
+// worker that owns a run of consecutive STFT frames; it transforms TWO real frames per 1024-point
+// complex FFT (frame a in the real part, frame b = next frame in the imaginary part) held entirely in
+// its registers (warp_fft.cuh).  No warp ever waits for another warp.
+//
+//   k1_analyze    frames -> FFT -> |X|^2 against per-bin power thresholds -> 1 bit/bin mask words
+//                 (+ per-(unit,bin) running max for the top_db floor, + FP64 re-decision of bins
+//                 whose FP32 margin is inside a proven guard band, so decisions equal the float64
+//                 reference's)
+//   k_rowfloor    top_db floor:  max_t dB - top_db > thresh  <=>  lift the whole row
+//   k_smooth      separable triangular smoothing of the binary mask in exact integer arithmetic
+//                 (the reference's FFT convolution approximates exactly these rationals)
+//   k2_synthesize frames -> FFT -> mask apply on the packed spectrum -> inverse FFT -> window ->
+//                 overlap-add in registers -> normalise -> store the chunk centre
+#pragma once
+#include "warp_fft.cuh"
+
+namespace b200 {
+
+constexpr int kN = 1024;            // n_fft handled by this kernel family
+constexpr int kF = kN / 2 + 1;      // 513 bins
+constexpr int kFW = (kF + 31) / 32; // 17 mask words per frame
+constexpr int kFPad = kFW * 32;     // 544: padded bin count (tables, mask row pitch)
+constexpr int kWarps = 4;           // warps per CTA for k1/k2 (each warp is independent)
+constexpr int kThreads = kWarps * 32;
+
+struct Geom {
+    int H;                  // hop
+    int C;                  // channels
+    int T;                  // frames per padded chunk: Lp / H + 1
+    int n_chunks;
+    long long n_total;      // samples per channel
+    long long step;         // chunk_size (or n_total when there is a single chunk)
+    long long pad;          // padding
+    long long Lp;           // padded chunk length: step + 2 pad
+    long long in_stride, out_stride;   // elements between channel rows
+    int u0, n_units;        // this batch: units [u0, u0 + n_units); u = chunk * C + channel
+};
+
+struct Tables {              // device pointers, built once per handle
+    const float* wa;         // [N] analysis window / sum(w)
+    const float* ws;         // [N] synthesis window * sum(w) / N
+    const float2* tw;        // [32*32] radix-32 inter-pass twiddles
+    const float* invn;       // [H] 1 / sum_i w^2[i H + r]  (interior overlap-add norm)
+    const float* thr4;       // [FPad] 4 * T_amp^2, T_amp = 10^(thresh/20) - eps
+    const float* gco;        // [FPad] guard-band coefficient: 4 * T_amp * kappa * eps32
+    const float* floor4;     // [FPad] 4 * (10^((thresh + top_db)/20) - eps)^2
+    const float* ef;         // [FPad] frequency edge factor of the smoothing filter
+    const double* thr2_64;   // [F]  T_amp^2 in float64
+    const double* wa64;      // [N]  analysis window / sum(w), float64
+    const double2* cs64;     // [N]  (cos, sin)(2 pi m / N), float64
+    float ws_to_w;           // raw window = ws * ws_to_w
+};
+
+struct Counters {
+    unsigned long long rechecked, unresolved, floor_flags, floor_ambiguous;
+};
+
+struct DebugTap {
+    int ul;                  // local unit index to tap, -1 = off
+    float* spec;             // [T][F][2]
+    float* mask;             // [T][F]
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One sample of the zero-extended padded chunk (base.py:130-142 zeros outside [0, n_total);
+// scipy boundary='zeros' outside [0, Lp)).  j: chunk-local index, i1: global index of j = 0.
+__device__ __forceinline__ float chunk_sample(const float* __restrict__ xrow, long long j, long long i1,
+                                              long long Lp, long long n_total) {
+    const long long g = i1 + j;
+    return (j >= 0 && j < Lp && g >= 0 && g < n_total) ? __ldg(xrow + g) : 0.0f;
+}
+
+// Load the rows of a frame pair (frame t in rows 0..31, frame t+1 in rows HR..31+HR), window them
+// and pack them as one complex signal.  Returns the L2 norm^2 contribution of this lane.
+template <int HR>
+__device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32], const float* __restrict__ xrow,
+                                                 long long base, long long i1, long long Lp, long long n_total,
+                                                 const float* __restrict__ s_wa, int lane, bool va, bool vb) {
+    float xr[32 + HR];
+#pragma unroll
+    for (int r = 0; r < 32 + HR; ++r) xr[r] = chunk_sample(xrow, base + lane + 32 * r, i1, Lp, n_total);
+    float e = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const float w = s_wa[lane + 32 * r];
+        re[r] = va ? xr[r] * w : 0.f;
+        im[r] = vb ? xr[r + HR] * w : 0.f;
+        e = fmaf(re[r], re[r], e);
+        e = fmaf(im[r], im[r], e);
+    }
+    return e;
+}
+
+// Exact (float64) re-decision of one bin of one frame: direct DFT of the windowed samples.
+// Warp-cooperative; every lane returns the same value.  2 = above threshold, 1 = not above,
+// 0 = unresolved even in float64 (|P - T^2| <= 1e-12 T^2).
+__device__ __forceinline__ int recheck_bin_fp64(const float* __restrict__ xrow, long long base, long long i1,
+                                                long long Lp, long long n_total, int k, const Tables& tb, int lane) {
+    double sr = 0.0, si = 0.0;
+    for (int n = lane; n < kN; n += 32) {
+        const double x = (double)chunk_sample(xrow, base + n, i1, Lp, n_total) * tb.wa64[n];
+        const double2 cs = tb.cs64[(k * n) & (kN - 1)];
+        sr = fma(x, cs.x, sr);
+        si = fma(-x, cs.y, si);
+    }
+    sr = warp_sum(sr);
+    si = warp_sum(si);
+    const double P = sr * sr + si * si;
+    const double T2 = tb.thr2_64[k];
+    if (fabs(P - T2) <= 1e-12 * T2) return 0;
+    return P > T2 ? 2 : 1;
+}
+
+// =============================================================================================
+// k1: analysis.  bits[(ul*T + t)*FW + w] bit b  <=>  raw |X[32w+b, t]| above the bin threshold.
+// =============================================================================================
+struct K1Args {
+    Geom g;
+    Tables tb;
+    const float* x;            // [C][in_stride] float32 samples
+    unsigned* bits;            // [n_units][T][FW]
+    unsigned* rowmax;          // [n_units][FPad]  max_t 4|X|^2 as float bits (>= 0 so uint order works)
+    Counters* cnt;
+    DebugTap dbg;
+    int run;                   // frames per work item (even)
+    int n_runs;                // ceil(T / run)
+};
+
+constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats; }
+
+template <int HR>
+__global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
+    B200_DYN_SMEM(float, smem);
+    float* s_wa = smem;
+    float2* s_tw = reinterpret_cast<float2*>(smem + kN);
+    float* s_thr4 = smem + 3 * kN;
+    float* s_gco = s_thr4 + kFPad;
+    float* s_tiles = s_gco + kFPad;
+    for (int i = threadIdx.x; i < kN; i += kThreads) {
+        s_wa[i] = a.tb.wa[i];
+        s_tw[i] = a.tb.tw[i];
+    }
+    for (int i = threadIdx.x; i < kFPad; i += kThreads) {
+        s_thr4[i] = a.tb.thr4[i];
+        s_gco[i] = a.tb.gco[i];
+    }
+    __syncthreads();
+
+    const Geom& g = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = s_tiles + warp * kExchFloats;
+    const int H = g.H;
+    const int pl = (32 - lane) & 31;                 // partner lane holding the mirrored bins
+    const long long n_items = (long long)g.n_units * a.n_runs;
+
+    for (long long item = (long long)blockIdx.x * kWarps + warp; item < n_items;
+         item += (long long)gridDim.x * kWarps) {
+        const int ul = (int)(item / a.n_runs);
+        const int run = (int)(item - (long long)ul * a.n_runs);
+        const int u = g.u0 + ul;
+        const int ic = u / g.C, c = u - ic * g.C;
+        const long long i1 = (long long)ic * g.step - g.pad;
+        const float* xrow = a.x + (long long)c * g.in_stride;
+        const int t0 = run * a.run;
+        const int t1 = min(t0 + a.run, g.T);
+        float mx[kFW];
+#pragma unroll
+        for (int q = 0; q < kFW; ++q) mx[q] = 0.f;
+
+        for (int t = t0; t < t1; t += 2) {
+            const bool vb = (t + 1 < t1);
+            const long long base = (long long)t * H - kN / 2;
+            float re[32], im[32];
+            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, true, vb);
+            const float S = sqrtf(warp_sum(e));
+            warp_fft1024<false>(re, im, tile, s_tw, lane);
+
+            unsigned wordA = 0u, wordB = 0u;
+#pragma unroll
+            for (int q = 0; q < kFW; ++q) {
+                const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
+                const float zr = re[sA], zi = im[sA];
+                float pr = __shfl_sync(0xffffffffu, re[sP], pl);
+                float pi = __shfl_sync(0xffffffffu, im[sP], pl);
+                if (lane == 0) { pr = re[s0]; pi = im[s0]; }
+                // 2 X_a = Z + conj(Zp),  2 X_b = (Z - conj(Zp)) / i
+                const float ar = zr + pr, ai = zi - pi;
+                const float br = zi + pi, bi = pr - zr;
+                const float PA = fmaf(ar, ar, ai * ai);
+                const float PB = fmaf(br, br, bi * bi);
+                const int k = lane + 32 * q;
+                const bool valid = (q < 16) || (lane == 0);
+                const float th = s_thr4[k];
+                const float gg = fmaf(s_gco[k], S, th * 8.0e-7f);
+                const float dA = PA - th, dB = PB - th;
+                bool bitA = valid && (dA > 0.f);
+                bool bitB = valid && vb && (dB > 0.f);
+                unsigned ambA = __ballot_sync(0xffffffffu, valid && fabsf(dA) <= gg);
+                unsigned ambB = __ballot_sync(0xffffffffu, valid && vb && fabsf(dB) <= gg);
+                if (ambA | ambB) {                    // warp-uniform, rare: redo those bins in float64
+                    unsigned nre = 0, nun = 0;
+                    while (ambA) {
+                        const int src = __ffs((int)ambA) - 1;
+                        ambA &= ambA - 1;
+                        const int r = recheck_bin_fp64(xrow, base, i1, g.Lp, g.n_total, src + 32 * q, a.tb, lane);
+                        ++nre;
+                        if (r == 0) ++nun; else if (lane == src) bitA = (r == 2);
+                    }
+                    while (ambB) {
+                        const int src = __ffs((int)ambB) - 1;
+                        ambB &= ambB - 1;
+                        const int r = recheck_bin_fp64(xrow, base + H, i1, g.Lp, g.n_total, src + 32 * q, a.tb, lane);
+                        ++nre;
+                        if (r == 0) ++nun; else if (lane == src) bitB = (r == 2);
+                    }
+                    if (lane == 0) {
+                        atomicAdd(&a.cnt->rechecked, (unsigned long long)nre);
+                        if (nun) atomicAdd(&a.cnt->unresolved, (unsigned long long)nun);
+                    }
+                }
+                const unsigned wA = __ballot_sync(0xffffffffu, bitA);
+                const unsigned wB = __ballot_sync(0xffffffffu, bitB);
+                if (lane == q) { wordA = wA; wordB = wB; }
+                if (valid) mx[q] = fmaxf(mx[q], vb ? fmaxf(PA, PB) : PA);
+                if (a.dbg.ul == ul && valid && k < kF) {     // parity tap: the FP32 STFT itself
+                    float* sp = a.dbg.spec + ((long long)t * kF + k) * 2;
+                    sp[0] = 0.5f * ar; sp[1] = 0.5f * ai;
+                    if (vb) { sp[2 * kF] = 0.5f * br; sp[2 * kF + 1] = 0.5f * bi; }
+                }
+            }
+            if (lane < kFW) {
+                unsigned* dst = a.bits + ((long long)ul * g.T + t) * kFW + lane;
+                dst[0] = wordA;
+                if (vb) dst[kFW] = wordB;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kFW; ++q)
+            if ((q < 16) || (lane == 0))
+                atomicMax(a.rowmax + (long long)ul * kFPad + lane + 32 * q, __float_as_uint(mx[q]));
+    }
+}
+
+// =============================================================================================
+// top_db floor (spectralgate/utils.py:16): clamped dB > thresh  <=>  raw > thresh  OR
+// (row max over the chunk's frames - top_db > thresh).  One thread per (unit, mask word).
+// =============================================================================================
+__global__ void k_rowfloor(int n_units, const unsigned* __restrict__ rowmax, const float* __restrict__ floor4,
+                           unsigned* __restrict__ rowflag, Counters* cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_units * kFW) return;
+    const int ul = i / kFW, w = i - ul * kFW;
+    unsigned word = 0u, nflag = 0u, namb = 0u;
+    for (int b = 0; b < 32; ++b) {
+        const int f = w * 32 + b;
+        if (f >= kF) break;
+        const float v = __uint_as_float(rowmax[(long long)ul * kFPad + f]);
+        const float tf = floor4[f];
+        if (v > tf) { word |= 1u << b; ++nflag; }
+        if (fabsf(v - tf) <= tf * 1.0e-5f) ++namb;
+    }
+    rowflag[i] = word;
+    if (nflag) atomicAdd(&cnt->floor_flags, (unsigned long long)nflag);
+    if (namb) atomicAdd(&cnt->floor_ambiguous, (unsigned long long)namb);
+}
+
+// =============================================================================================
+// Mask smoothing in integers.  K = tri_f (x) tri_t / ((nf+1)^2 (nt+1)^2) with tri_n[k] = n+1-|k|
+// (base.py:14-28), so  smoothed = p * num / D + (1-p) * edge,  num = sum tri_f tri_t bit.
+// Output: num as uint16 [n_units][T][FPad] for frames [tf_lo, tf_hi).
+// Time direction: per-bin streaming second-difference recurrence (tri = box * box);
+// frequency direction: direct taps from the shared-memory tile.
+// =============================================================================================
+struct SmoothArgs {
+    int n_units, T;
+    int nf, nt;
+    int tf_lo, tf_hi;          // frames that need masks
+    int TT;                    // output frames per tile
+    const unsigned* bits;      // [n_units][T][FW]
+    const unsigned* rowflag;   // [n_units][FW]
+    unsigned short* num;       // [n_units][T][FPad]
+};
+
+__host__ __device__ inline int smooth_rows(int TT, int nt) { return TT + 2 * nt + 2 * (nt + 1); }
+__host__ __device__ inline int smooth_cpitch(int nf) { return (kFPad + 2 * nf + 2) | 1; }   // odd #shorts/2 not needed; keep simple
+inline size_t smooth_smem_bytes(int TT, int nf, int nt) {
+    return (size_t)smooth_rows(TT, nt) * kFW * 4 + (size_t)TT * smooth_cpitch(nf) * 2 + 16;
+}
+
+__global__ void __launch_bounds__(256) k_smooth(const SmoothArgs a) {
+    B200_DYN_SMEM(unsigned, smem);
+    const int nt = a.nt, nf = a.nf, aa = nt + 1;
+    const int rows = smooth_rows(a.TT, nt);
+    const int cp = smooth_cpitch(nf);
+    unsigned* s_bits = smem;                                                   // [rows][FW]
+    unsigned short* s_c = reinterpret_cast<unsigned short*>(smem + rows * kFW);  // [TT][cp]
+    const int ul = blockIdx.y;
+    const int t0 = a.tf_lo + blockIdx.x * a.TT;
+    if (t0 >= a.tf_hi) return;
+    const int tt_n = min(a.TT, a.tf_hi - t0);
+    // row rho <-> frame tau = t0 - nt - 2aa + rho ; the first 2aa rows are "before the stream" = 0
+    const int tau0 = t0 - nt - 2 * aa;
+    for (int i = threadIdx.x; i < rows * kFW; i += blockDim.x) {
+        const int rho = i / kFW, w = i - rho * kFW;
+        const int tau = tau0 + rho;
+        unsigned v = 0u;
+        if (rho >= 2 * aa && tau >= 0 && tau < a.T)
+            v = a.bits[((long long)ul * a.T + tau) * kFW + w] | a.rowflag[ul * kFW + w];
+        s_bits[i] = v;
+    }
+    for (int i = threadIdx.x; i < a.TT * cp; i += blockDim.x) s_c[i] = 0;
+    __syncthreads();
+    // time direction: c[f, t] = sum_b tri_t[b] m[f, t-b];  s2[tau] = c[., tau - nt]
+    for (int f = threadIdx.x; f < kF; f += blockDim.x) {
+        const int w = f >> 5, sh = f & 31;
+        int d1 = 0, s2 = 0;
+        const int steps = tt_n + 2 * nt;
+        for (int s = 0; s < steps; ++s) {
+            const int rho = 2 * aa + s;
+            const int e = (int)((s_bits[rho * kFW + w] >> sh) & 1u)
+                        - 2 * (int)((s_bits[(rho - aa) * kFW + w] >> sh) & 1u)
+                        + (int)((s_bits[(rho - 2 * aa) * kFW + w] >> sh) & 1u);
+            d1 += e;
+            s2 += d1;
+            const int tt = s - 2 * nt;
+            if (tt >= 0) s_c[tt * cp + nf + f] = (unsigned short)s2;
+        }
+    }
+    __syncthreads();
+    // frequency direction
+    for (int i = threadIdx.x; i < tt_n * kFPad; i += blockDim.x) {
+        const int tt = i / kFPad, f = i - tt * kFPad;
+        int acc = 0;
+        if (f < kF) {
+            const unsigned short* cr = s_c + tt * cp + f;      // cr[nf + d] = c[f + d]
+            for (int d = -nf; d <= nf; ++d) acc += (nf + 1 - (d < 0 ? -d : d)) * (int)cr[nf + d];
+        }
+        a.num[((long long)ul * a.T + t0 + tt) * kFPad + f] = (unsigned short)acc;
+    }
+}
+
+// =============================================================================================
+// k2: synthesis.
+// =============================================================================================
+struct K2Args {
+    Geom g;
+    Tables tb;
+    const float* x;
+    float* y;                      // [C][out_stride] float32
+    const unsigned short* num;     // [n_units][T][FPad] integer mask numerators
+    float pD;                      // prop_decrease / D
+    float one_minus_p;             // 1 - prop_decrease
+    int nt;                        // time half-width (edge factor of the first/last frames)
+    int run;                       // output hops per work item
+    int n_runs;
+    DebugTap dbg;
+};
+
+constexpr int k2_smem_floats(int H) { return 2 * kN + 2 * kN + H + kFPad + kWarps * kExchFloats; }
+
+// time edge factor of the zero-padded smoothing: sum of the triangle taps that stay inside [0, T)
+__device__ __forceinline__ float time_edge(int t, int T, int nt) {
+    int s = 0;
+    for (int b = -nt; b <= nt; ++b)
+        if (t - b >= 0 && t - b < T) s += nt + 1 - (b < 0 ? -b : b);
+    return (float)s / (float)((nt + 1) * (nt + 1));
+}
+
+template <int HR>
+__global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
+    constexpr int NH = 32 / HR;             // frames overlapping one hop (win / hop)
+    B200_DYN_SMEM(float, smem);
+    const Geom& g = a.g;
+    const int H = g.H;
+    float* s_wa = smem;
+    float* s_ws = smem + kN;
+    float2* s_tw = reinterpret_cast<float2*>(smem + 2 * kN);
+    float* s_invn = smem + 4 * kN;
+    float* s_ef = s_invn + H;
+    float* s_tiles = s_ef + kFPad;
+    for (int i = threadIdx.x; i < kN; i += kThreads) {
+        s_wa[i] = a.tb.wa[i];
+        s_ws[i] = a.tb.ws[i];
+        s_tw[i] = a.tb.tw[i];
+    }
+    for (int i = threadIdx.x; i < H; i += kThreads) s_invn[i] = a.tb.invn[i];
+    for (int i = threadIdx.x; i < kFPad; i += kThreads) s_ef[i] = a.tb.ef[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = s_tiles + warp * kExchFloats;
+    const int pl = (32 - lane) & 31;
+    const long long n_items = (long long)g.n_units * a.n_runs;
+    const bool blend = (a.one_minus_p != 0.f);
+
+    for (long long item = (long long)blockIdx.x * kWarps + warp; item < n_items;
+         item += (long long)gridDim.x * kWarps) {
+        const int ul = (int)(item / a.n_runs);
+        const int run = (int)(item - (long long)ul * a.n_runs);
+        const int u = g.u0 + ul;
+        const int ic = u / g.C, c = u - ic * g.C;
+        const long long i1 = (long long)ic * g.step - g.pad;
+        long long out_len = g.n_total - (long long)ic * g.step;
+        if (out_len > g.step) out_len = g.step;
+        // valid chunk-local output range [pad, jp_hi), in padded (frame) coordinates + N/2
+        long long jp_hi = g.pad + out_len;
+        const long long sig_len = (long long)(g.T - 1) * H;          // istft output length
+        if (jp_hi > sig_len) jp_hi = sig_len;                        // beyond it the reference leaves zeros
+        if (jp_hi <= g.pad) continue;
+        const long long jlo = g.pad + kN / 2, jhi = jp_hi + kN / 2;
+        const int h_lo = (int)(jlo / H), h_hi = (int)((jhi + H - 1) / H);
+        const int hs = h_lo + run * a.run;
+        const int he = min(hs + a.run, h_hi);
+        if (hs >= he) continue;
+        const int t_start = max(0, hs - (NH - 1));
+        const int t_last = min(he - 1, g.T - 1);
+        const float* xrow = a.x + (long long)c * g.in_stride;
+        float* yrow = a.y + (long long)c * g.out_stride;
+        const unsigned short* mrow = a.num + (long long)ul * g.T * kFPad;
+
+        float acc[32 + HR];
+#pragma unroll
+        for (int r = 0; r < 32 + HR; ++r) acc[r] = 0.f;
+
+        for (int t = t_start; t < he; t += 2) {
+            const bool va = (t <= t_last), vb = (t + 1 <= t_last);
+            if (va) {                                   // vb implies va
+                const long long base = (long long)t * H - kN / 2;
+                float re[32], im[32];
+                load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, va, vb);
+                warp_fft1024<false>(re, im, tile, s_tw, lane);
+
+                const unsigned short* mA = mrow + (long long)t * kFPad;
+                const unsigned short* mB = mrow + (long long)(vb ? t + 1 : t) * kFPad;
+                float eta = 0.f, etb = 0.f;
+                if (blend) {
+                    eta = a.one_minus_p * time_edge(t, g.T, a.nt);
+                    etb = a.one_minus_p * time_edge(t + 1, g.T, a.nt);
+                }
+#pragma unroll
+                for (int q = 0; q < kFW; ++q) {
+                    const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
+                    const int k = lane + 32 * q;                 // < FPad, rows are padded
+                    float ma = fmaf((float)mA[k], a.pD, eta * s_ef[k]);
+                    float mb = fmaf((float)mB[k], a.pD, etb * s_ef[k]);
+                    if (!vb) mb = 0.f;
+                    if (a.dbg.ul == ul && k < kF && ((q < 16) || lane == 0)) {
+                        a.dbg.mask[(long long)t * kF + k] = ma;
+                        if (vb) a.dbg.mask[(long long)(t + 1) * kF + k] = mb;
+                    }
+                    const float s = 0.5f * (ma + mb), d = 0.5f * (ma - mb);
+                    const float zr = re[sA], zi = im[sA];
+                    if (q < 16) {
+                        float pr = __shfl_sync(0xffffffffu, re[sP], pl);
+                        float pi = __shfl_sync(0xffffffffu, im[sP], pl);
+                        if (lane == 0) { pr = re[s0]; pi = im[s0]; }
+                        // Z'[k] = s Z[k] + d conj(Z[N-k]);  Z'[N-k] = s Z[N-k] + d conj(Z[k])
+                        const float own_r = fmaf(d, pr, s * zr), own_i = fmaf(-d, pi, s * zi);
+                        const float oth_r = fmaf(d, zr, s * pr), oth_i = fmaf(-d, zi, s * pi);
+                        const float nr = __shfl_sync(0xffffffffu, oth_r, pl);
+                        const float ni = __shfl_sync(0xffffffffu, oth_i, pl);
+                        re[sA] = own_r;
+                        im[sA] = own_i;
+                        if (lane != 0) { re[sP] = nr; im[sP] = ni; }
+                        else if (q != 0) { re[s0] = oth_r; im[s0] = oth_i; }
+                    } else if (lane == 0) {                      // bin N/2 mirrors onto itself
+                        re[sA] = fmaf(d, zr, s * zr);
+                        im[sA] = fmaf(-d, zi, s * zi);
+                    }
+                }
+                // inverse FFT by the swap trick; afterwards re = N a'[n], im = N b'[n] at slot brev5(q)
+                warp_fft1024<true>(im, re, tile, s_tw, lane);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float w = s_ws[lane + 32 * q];
+                    acc[q] = fmaf(re[brev5(q)], w, acc[q]);
+                    acc[q + HR] = fmaf(im[brev5(q)], w, acc[q + HR]);
+                }
+            }
+            // hops t and t+1 are now complete (all frames <= t+1 have been added)
+#pragma unroll
+            for (int r = 0; r < 2 * HR; ++r) {
+                const int hop = t + r / HR;
+                if (hop >= hs && hop < he) {
+                    const int ro = (r % HR) * 32 + lane;
+                    const long long jp = (long long)hop * H + ro - kN / 2;       // chunk-local output index
+                    if (jp >= g.pad && jp < jp_hi) {
+                        float inv;
+                        if (hop >= NH - 1 && hop <= g.T - 1) {
+                            inv = s_invn[ro];
+                        } else {                                                  // first / last hops
+                            float nrm = 0.f;
+                            for (int i = 0; i < NH; ++i) {
+                                const int tf = hop - i;
+                                if (tf >= 0 && tf <= g.T - 1) {
+                                    const float w = s_ws[i * H + ro] * a.tb.ws_to_w;
+                                    nrm = fmaf(w, w, nrm);
+                                }
+                            }
+                            inv = nrm > 1e-10f ? 1.0f / nrm : 1.0f;
+                        }
+                        yrow[i1 + jp] = acc[r] * inv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 32 - HR; ++r) acc[r] = acc[r + 2 * HR];
+#pragma unroll
+            for (int r = 32 - HR; r < 32 + HR; ++r) acc[r] = 0.f;
+        }
+    }
+}
+
+// =============================================================================================
+// dtype conversion at the edges (base.py:140 promotes every chunk to float64; :218-226 casts back)
+// =============================================================================================
+template <typename Tin>
+__global__ void k_to_f32(const Tin* __restrict__ src, float* __restrict__ dst, long long C, long long n,
+                         long long sstride, long long dstride) {
+    const long long total = C * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long c = i / n, j = i - c * n;
+        dst[c * dstride + j] = (float)src[c * sstride + j];
+    }
+}
+template <typename Tout>
+__device__ __forceinline__ Tout cast_out(float v);
+template <> __device__ __forceinline__ double cast_out<double>(float v) { return (double)v; }
+template <> __device__ __forceinline__ short cast_out<short>(float v) {
+    // numpy float -> int16 astype: C truncation toward zero, wrapping the low 16 bits
+    return (short)(int)v;
+}
+template <typename Tout>
+__global__ void k_from_f32(const float* __restrict__ src, Tout* __restrict__ dst, long long C, long long n,
+                           long long sstride, long long dstride) {
+    const long long total = C * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long c = i / n, j = i - c * n;
+        dst[c * dstride + j] = cast_out<Tout>(src[c * sstride + j]);
+    }
+}
+
+// =============================================================================================
+// K0: one-time stationary noise statistics (stationary.py:61-81), float64.
+// =============================================================================================
+// sequential channel sum in channel order (np.mean(axis=0) adds rows in order; float32 stays float32)
+template <typename Tin, typename Tacc>
+__global__ void k0_channel_sum(const Tin* __restrict__ y, long long C, long long n, long long stride,
+                               Tacc* __restrict__ acc, int init) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        Tacc s = init ? (Tacc)0 : acc[i];
+        for (long long c = 0; c < C; ++c) s = s + (Tacc)y[c * stride + i];
+        acc[i] = s;
+    }
+}
+template <typename Tacc>
+__global__ void k0_mean_to_f64(const Tacc* __restrict__ acc, long long n, long long C, double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = (double)(acc[i] / (Tacc)C);          // division in the accumulation dtype, as numpy
+}
+
+// One CTA per frame: float64 radix-2 FFT in shared memory -> dB (utils.py:15), [Tn][F].
+struct K0Args {
+    const double* yn;      // [n] collapsed noise clip
+    long long n;
+    int H, Tn;
+    const double* wa64;
+    const double2* cs64;
+    double eps;
+    double* db;            // [Tn][F]
+};
+__global__ void __launch_bounds__(256) k0_stft_db(const K0Args a) {
+    B200_DYN_SMEM(double2, s);                      // [N]
+    const int t = blockIdx.x;
+    const long long base = (long long)t * a.H - kN / 2;
+    for (int n = threadIdx.x; n < kN; n += blockDim.x) {
+        const long long j = base + n;
+        const double v = (j >= 0 && j < a.n) ? a.yn[j] * a.wa64[n] : 0.0;
+        int r = 0;
+        for (int b = 0; b < 10; ++b) r |= ((n >> b) & 1) << (9 - b);
+        s[r] = make_double2(v, 0.0);
+    }
+    __syncthreads();
+    for (int len = 2; len <= kN; len <<= 1) {
+        const int half = len >> 1, stride = kN / len;
+        for (int i = threadIdx.x; i < kN / 2; i += blockDim.x) {
+            const int blk = i / half, o = i - blk * half;
+            const int ia = blk * len + o, ib = ia + half;
+            const double2 w = a.cs64[o * stride];                 // exp(-i th) = cos - i sin
+            const double2 x = s[ia], y = s[ib];
+            const double yr = y.x * w.x + y.y * w.y, yi = y.y * w.x - y.x * w.y;
+            s[ia] = make_double2(x.x + yr, x.y + yi);
+            s[ib] = make_double2(x.x - yr, x.y - yi);
+        }
+        __syncthreads();
+    }
+    for (int f = threadIdx.x; f < kF; f += blockDim.x) {
+        const double2 v = s[f];
+        a.db[(long long)t * kF + f] = 20.0 * log10(sqrt(v.x * v.x + v.y * v.y) + a.eps);
+    }
+}
+
+// One CTA per bin: top_db floor, mean, std (ddof), thresh.
+__global__ void __launch_bounds__(256) k0_stats(const double* __restrict__ db, int Tn, double top_db, int ddof,
+                                                double n_std, double* __restrict__ mean_out,
+                                                double* __restrict__ std_out, double* __restrict__ thr_out) {
+    __shared__ double red[256];
+    const int f = blockIdx.x;
+    double m = -1.0e300;
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) m = fmax(m, db[(long long)t * kF + f]);
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    const double fl = red[0] - top_db;
+    __syncthreads();
+    double sum = 0.0;
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) sum += fmax(db[(long long)t * kF + f], fl);
+    red[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double mean = red[0] / Tn;
+    __syncthreads();
+    double ss = 0.0;
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+        const double d = fmax(db[(long long)t * kF + f], fl) - mean;
+        ss += d * d;
+    }
+    red[threadIdx.x] = ss;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double sd = sqrt(red[0] / (double)(Tn - ddof));
+        mean_out[f] = mean;
+        std_out[f] = sd;
+        thr_out[f] = mean + sd * n_std;
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,139 @@
+// warp_fft.cuh -- a 1024-point complex FFT held entirely by ONE warp (32 lanes x 32 points).
+//
+// Layout.  A lane owns the 32 points  n = lane + 32*r  (r = register slot), so every global/shared
+// access of "slot r across the warp" is one coalesced 128-byte row.  The transform is two radix-32
+// passes (1024 = 32 x 32, Stockham auto-sort):
+//
+//   pass 1:  V[lane][q] = DFT32_r( x[lane + 32 r] )                     (registers only)
+//   twiddle: V[lane][q] *= exp(-2 pi i * lane * q / 1024)               (table tw[q][lane], smem)
+//   exchange: a 32x32 transpose through a per-warp 32x33 float tile     (the ONLY data movement)
+//   pass 2:  X[lane + 32 q] = DFT32_r( V[r][lane] )                     (registers only)
+//
+// Only __syncwarp() is needed: a warp never waits for another warp.  The radix-32 butterfly is a
+// fully unrolled radix-2 DIF network whose 32-point twiddles are compile-time immediates.
+//
+// Bit-reversal is never executed: the DIF network leaves frequency q in register slot brev5(q); all
+// callers index slots through brev5() with compile-time q, and dft32<true> accepts bit-reversed
+// slots and returns natural ones, so forward/inverse chains need no permutation instructions.
+//
+// Inverse transform: ifft(z) = swap(fft(swap(z))) / N with swap(a + ib) = b + ia, i.e. simply call
+// warp_fft1024(im, re) -- the scaling is folded into the synthesis window by the callers.
+#pragma once
+#include "cuda_compat.h"
+
+namespace b200 {
+
+constexpr int kFftN = 1024;
+constexpr int kExchFloats = 32 * 33;   // per-warp exchange tile (one plane at a time)
+
+__host__ __device__ __forceinline__ constexpr int brev5(int i) {
+    return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+// cos / sin of 2*pi*m/32, m = 0..15 (folds to an immediate once the loops are unrolled)
+__host__ __device__ __forceinline__ constexpr float cos32(int m) {
+    return m == 0 ? 1.0f : m == 1 ? 0.98078528040323044913f : m == 2 ? 0.92387953251128675613f
+         : m == 3 ? 0.83146961230254523708f : m == 4 ? 0.70710678118654752440f
+         : m == 5 ? 0.55557023301960222474f : m == 6 ? 0.38268343236508977173f
+         : m == 7 ? 0.19509032201612826785f : m == 8 ? 0.0f
+         : m == 9 ? -0.19509032201612826785f : m == 10 ? -0.38268343236508977173f
+         : m == 11 ? -0.55557023301960222474f : m == 12 ? -0.70710678118654752440f
+         : m == 13 ? -0.83146961230254523708f : m == 14 ? -0.92387953251128675613f
+         : -0.98078528040323044913f;
+}
+__host__ __device__ __forceinline__ constexpr float sin32(int m) {
+    return m == 0 ? 0.0f : m == 1 ? 0.19509032201612826785f : m == 2 ? 0.38268343236508977173f
+         : m == 3 ? 0.55557023301960222474f : m == 4 ? 0.70710678118654752440f
+         : m == 5 ? 0.83146961230254523708f : m == 6 ? 0.92387953251128675613f
+         : m == 7 ? 0.98078528040323044913f : m == 8 ? 1.0f
+         : m == 9 ? 0.98078528040323044913f : m == 10 ? 0.92387953251128675613f
+         : m == 11 ? 0.83146961230254523708f : m == 12 ? 0.70710678118654752440f
+         : m == 13 ? 0.55557023301960222474f : m == 14 ? 0.38268343236508977173f
+         : 0.19509032201612826785f;
+}
+
+// 32-point DFT over the register slots of one thread (radix-2 decimation in frequency).
+//   BREV_IN == false: logical input i in slot i          -> frequency q in slot brev5(q)
+//   BREV_IN == true : logical input i in slot brev5(i)   -> frequency q in slot q
+template <bool BREV_IN>
+__device__ __forceinline__ void dft32(float (&re)[32], float (&im)[32]) {
+#pragma unroll
+    for (int len = 32; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+        const int step = 32 / len;
+#pragma unroll
+        for (int blk = 0; blk < 32; blk += len) {
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const int ia = BREV_IN ? brev5(blk + i) : (blk + i);
+                const int ib = BREV_IN ? brev5(blk + i + half) : (blk + i + half);
+                const int m = i * step;                       // twiddle W32^m = cos32(m) - i sin32(m)
+                const float ar = re[ia], ai = im[ia], br = re[ib], bi = im[ib];
+                re[ia] = ar + br;
+                im[ia] = ai + bi;
+                const float dr = ar - br, di = ai - bi;
+                if (m == 0) {
+                    re[ib] = dr;
+                    im[ib] = di;
+                } else if (m == 8) {                           // * (-i)
+                    re[ib] = di;
+                    im[ib] = -dr;
+                } else if (m == 4) {                           // * (1 - i)/sqrt2
+                    re[ib] = (dr + di) * 0.70710678118654752440f;
+                    im[ib] = (di - dr) * 0.70710678118654752440f;
+                } else if (m == 12) {                          // * (-1 - i)/sqrt2
+                    re[ib] = (di - dr) * 0.70710678118654752440f;
+                    im[ib] = -(dr + di) * 0.70710678118654752440f;
+                } else {
+                    const float c = cos32(m), s = sin32(m);
+                    re[ib] = fmaf(di, s, dr * c);              // (dr + i di)(c - i s)
+                    im[ib] = fmaf(-dr, s, di * c);
+                }
+            }
+        }
+    }
+}
+
+// Twiddle by exp(-2 pi i lane q / 1024) and transpose lanes <-> slots through shared memory.
+//   SLOTS_BREV: the element for index q currently sits in slot brev5(q) (true after dft32<false>).
+// On return slot r holds element (r, lane) of the twiddled matrix, natural order.
+// tw: [32][32] float2, tw[q*32 + lane] = (cos, -sin)(2 pi lane q / 1024)   (shared memory)
+// tile: this warp's private 32x33 float tile.
+template <bool SLOTS_BREV>
+__device__ __forceinline__ void twiddle_transpose(float (&re)[32], float (&im)[32], float* __restrict__ tile,
+                                                  const float2* __restrict__ tw, int lane) {
+#pragma unroll
+    for (int q = 1; q < 32; ++q) {
+        const int s = SLOTS_BREV ? brev5(q) : q;
+        const float2 w = tw[q * 32 + lane];
+        const float a = re[s], b = im[s];
+        re[s] = fmaf(-b, w.y, a * w.x);
+        im[s] = fmaf(a, w.y, b * w.x);
+    }
+    float* row = tile + lane * 33;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) row[q] = re[SLOTS_BREV ? brev5(q) : q];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) re[r] = tile[r * 33 + lane];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) row[q] = im[SLOTS_BREV ? brev5(q) : q];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) im[r] = tile[r * 33 + lane];
+    __syncwarp();
+}
+
+// Forward 1024-point FFT.  IN_BREV == false: input point lane+32r in slot r.
+//                          IN_BREV == true : input point lane+32r in slot brev5(r).
+// Output: X[lane + 32 q] in slot brev5(q).
+template <bool IN_BREV>
+__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], float* __restrict__ tile,
+                                             const float2* __restrict__ tw, int lane) {
+    dft32<IN_BREV>(re, im);                               // -> brev slots (false) / natural (true)
+    twiddle_transpose<!IN_BREV>(re, im, tile, tw, lane);
+    dft32<false>(re, im);                                 // natural in -> brev out
+}
+
+}  // namespace b200

@@ -1,0 +1,133 @@
+"""Host-side mirror of noisereduce/spectralgate/base.py:32 (class SpectralGate).
+
+Same constructor arguments, attributes, defaults and exceptions as the reference; the chunk loop,
+joblib fan-out and temp-file memmap (base.py:167-226) are replaced by ONE call into libb200gate,
+which runs every (chunk, channel) unit of the reference's chunk table on the GPU.
+"""
+import numpy as np
+
+from .. import _cabi
+
+
+class SpectralGate:
+    def __init__(
+        self,
+        y,
+        sr,
+        prop_decrease,
+        chunk_size,
+        padding,
+        n_fft,
+        win_length,
+        hop_length,
+        time_constant_s,
+        freq_mask_smooth_hz,
+        time_mask_smooth_ms,
+        tmp_folder,
+        use_tqdm,
+        n_jobs,
+    ):
+        self.sr = sr
+        self.flat = False
+        y = np.array(y)
+        # reshape data to (#channels, #frames)                      (base.py:54-62)
+        if len(y.shape) == 1:
+            self.y = np.expand_dims(y, 0)
+            self.flat = True
+        elif len(y.shape) > 2:
+            raise ValueError("Waveform must be in shape (# frames, # channels)")
+        else:
+            self.y = y
+        self._dtype = y.dtype
+        self.n_channels, self.n_frames = self.y.shape
+        self._chunk_size = chunk_size
+        self.padding = padding
+        # accepted for signature compatibility; the GPU grid replaces joblib / tqdm / the temp memmap
+        self.n_jobs = n_jobs
+        self.use_tqdm = use_tqdm
+        self._tmp_folder = tmp_folder
+
+        self._n_fft = n_fft
+        self._win_length = self._n_fft if win_length is None else win_length          # base.py:79-86
+        self._hop_length = self._win_length // 4 if hop_length is None else hop_length
+        self._time_constant_s = time_constant_s
+        self._prop_decrease = prop_decrease
+
+        self._n_grad_freq = 0
+        self._n_grad_time = 0
+        if (freq_mask_smooth_hz is None) & (time_mask_smooth_ms is None):               # base.py:92-97
+            self.smooth_mask = False
+        else:
+            self._generate_mask_smoothing_filter(freq_mask_smooth_hz, time_mask_smooth_ms)
+        self._gate = None
+
+    def _generate_mask_smoothing_filter(self, freq_mask_smooth_hz, time_mask_smooth_ms):
+        """base.py:99-128 -- same integer arithmetic and the same ValueErrors.  Only the extents are
+        kept: the taps are the rationals (n+1-|k|)/(n+1)^2 and the kernels apply them in integers."""
+        if freq_mask_smooth_hz is None:
+            n_grad_freq = 1
+        else:
+            n_grad_freq = int(freq_mask_smooth_hz / (self.sr / (self._n_fft / 2)))
+            if n_grad_freq < 1:
+                raise ValueError(
+                    "freq_mask_smooth_hz needs to be at least {}Hz".format(int((self.sr / (self._n_fft / 2))))
+                )
+        if time_mask_smooth_ms is None:
+            n_grad_time = 1
+        else:
+            n_grad_time = int(time_mask_smooth_ms / ((self._hop_length / self.sr) * 1000))
+            if n_grad_time < 1:
+                raise ValueError(
+                    "time_mask_smooth_ms needs to be at least {}ms".format(int((self._hop_length / self.sr) * 1000))
+                )
+        if (n_grad_time == 1) & (n_grad_freq == 1):
+            self.smooth_mask = False
+        else:
+            self.smooth_mask = True
+            self._n_grad_freq, self._n_grad_time = n_grad_freq, n_grad_time
+
+    # -- parameters handed to the C ABI ------------------------------------------------------------
+    def _gate_params(self):
+        return dict(
+            surface=_cabi.SURFACE_NUMPY,
+            n_fft=int(self._n_fft),
+            win_length=int(self._win_length),
+            hop_length=int(self._hop_length),
+            n_grad_freq=int(self._n_grad_freq) if self.smooth_mask else 0,
+            n_grad_time=int(self._n_grad_time) if self.smooth_mask else 0,
+            chunk_size=int(self._chunk_size) if self._chunk_size is not None else 0,
+            padding=int(self.padding),
+            sr=float(self.sr),
+            prop_decrease=float(self._prop_decrease),
+            top_db=80.0,                     # spectralgate/utils.py:11
+            std_ddof=0,
+        )
+
+    def _samples_for_device(self, y2d):
+        """float32 / int16 / float64 go to the library as they are; any other dtype takes the
+        reference's own route -- promoted to float64 (base.py:140) -- and is cast back on return."""
+        if y2d.dtype in (np.float32, np.int16, np.float64):
+            return np.ascontiguousarray(y2d)
+        return np.ascontiguousarray(y2d, dtype=np.float64)
+
+    def _run(self, y2d):
+        x = self._samples_for_device(y2d)
+        out = self._gate.run_host(x)
+        if out.dtype != self._dtype:
+            with np.errstate(invalid="ignore"):
+                out = out.astype(self._dtype)                  # base.py:218-226
+        return out
+
+    def get_traces(self, start_frame=None, end_frame=None):
+        """base.py:167-226.  With both bounds None this is the whole recording (what reduce_noise
+        calls); a sub-range reproduces the reference's chunk-grid-anchored result by slicing."""
+        if start_frame is None:
+            start_frame = 0
+        if end_frame is None:
+            end_frame = self.n_frames
+        full = self._run(self.y)
+        if self._chunk_size is not None and end_frame - start_frame > self._chunk_size:
+            res = full[:, start_frame:end_frame]
+        else:
+            res = full[:, 0:end_frame]                          # base.py:222 ignores start_frame
+        return res.flatten() if self.flat else res

@@ -1,0 +1,56 @@
+"""Mirror of noisereduce/spectralgate/stationary.py:7 (SpectralGateStationary) on libb200gate."""
+import numpy as np
+
+from .. import _cabi
+from .base import SpectralGate
+
+
+class SpectralGateStationary(SpectralGate):
+    def __init__(
+        self,
+        y,
+        sr,
+        y_noise,
+        n_std_thresh_stationary,
+        chunk_size,
+        clip_noise_stationary,
+        padding,
+        n_fft,
+        win_length,
+        hop_length,
+        time_constant_s,
+        freq_mask_smooth_hz,
+        time_mask_smooth_ms,
+        tmp_folder,
+        prop_decrease,
+        use_tqdm,
+        n_jobs,
+    ):
+        super().__init__(
+            y=y, sr=sr, chunk_size=chunk_size, padding=padding, n_fft=n_fft, win_length=win_length,
+            hop_length=hop_length, time_constant_s=time_constant_s, freq_mask_smooth_hz=freq_mask_smooth_hz,
+            time_mask_smooth_ms=time_mask_smooth_ms, tmp_folder=tmp_folder, prop_decrease=prop_decrease,
+            use_tqdm=use_tqdm, n_jobs=n_jobs,
+        )
+        self.n_std_thresh_stationary = n_std_thresh_stationary
+
+        if y_noise is None:                                     # stationary.py:47-59
+            noise = self.y
+        else:
+            y_noise = np.array(y_noise)
+            if len(y_noise.shape) == 1:
+                noise = np.expand_dims(y_noise, 0)
+            elif len(y.shape) > 2:
+                raise ValueError("Waveform must be in shape (# frames, # channels)")
+            else:
+                noise = y_noise
+
+        params = self._gate_params()
+        params.update(stationary=1, n_std_thresh=float(n_std_thresh_stationary),
+                      clip_noise=1 if clip_noise_stationary else 0)
+        self._gate = _cabi.Gate(**params)
+        # stationary.py:61-81 on the device: channel mean in the input dtype, clip, STFT, dB with the
+        # 80 dB floor, per-bin mean / std over time, threshold
+        self._gate.noise_stats_host(self._samples_for_device(noise))
+        self.mean_freq_noise, self.std_freq_noise = self._gate.noise_mean_std()
+        self.noise_thresh = self._gate.noise_threshold()
