@@ -58,7 +58,8 @@ typedef struct b200gate_params {
     int32_t std_ddof;           /* 0 numpy surface (np.std), 1 torch surface (std_mean)          */
     int32_t clip_noise;         /* clip_noise_stationary                                         */
     int32_t n_movemean;         /* torch surface, non-stationary                                 */
-    int32_t reserved0;
+    int32_t debug_guard_scale;  /* tests only: multiplies the FP32 guard band (0 = 1x), forcing more
+                                 * bins through the FP64 re-decision path                          */
     int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
     int64_t padding;
     double sr;
@@ -84,6 +85,7 @@ typedef struct b200gate_stats {
     int64_t rowfloor_ambiguous;     /* ... whose FP32 decision was inside the guard band (exp. 0) */
     double last_run_ms;             /* device time of the last run, CUDA events on its stream     */
     double last_h2d_ms, last_d2h_ms;
+    double k1_ms, smooth_ms, k2_ms; /* per-kernel device time summed over the run's batches       */
 } b200gate_stats;
 
 int b200gate_create(const b200gate_params* params, b200gate_handle** out);

@@ -34,7 +34,7 @@ class Params(C.Structure):
         ("abi_version", C.c_int32), ("surface", C.c_int32), ("stationary", C.c_int32),
         ("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop_length", C.c_int32),
         ("n_grad_freq", C.c_int32), ("n_grad_time", C.c_int32), ("std_ddof", C.c_int32),
-        ("clip_noise", C.c_int32), ("n_movemean", C.c_int32), ("reserved0", C.c_int32),
+        ("clip_noise", C.c_int32), ("n_movemean", C.c_int32), ("debug_guard_scale", C.c_int32),
         ("chunk_size", C.c_int64), ("padding", C.c_int64),
         ("sr", C.c_double), ("prop_decrease", C.c_double), ("n_std_thresh", C.c_double),
         ("top_db", C.c_double), ("time_constant_s", C.c_double), ("thresh_n_mult", C.c_double),
@@ -48,6 +48,7 @@ class Stats(C.Structure):
         ("bins_rechecked_fp64", C.c_int64), ("bins_unresolved", C.c_int64),
         ("rowfloor_flags", C.c_int64), ("rowfloor_ambiguous", C.c_int64),
         ("last_run_ms", C.c_double), ("last_h2d_ms", C.c_double), ("last_d2h_ms", C.c_double),
+        ("k1_ms", C.c_double), ("smooth_ms", C.c_double), ("k2_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -154,6 +155,13 @@ class Gate:
 
     def noise_stats_device(self, ptr, dtype, C_, N, stride, stream=None):
         self._check(self.lib.dll.b200gate_noise_stats(self._h, ptr, dtype_code(dtype), C_, N, stride, 1, stream))
+
+    def channel_sum_device(self, ptr, dtype, C_, n, stride, acc_ptr, init, stream=None):
+        self._check(self.lib.dll.b200gate_channel_sum(
+            self._h, ptr, dtype_code(dtype), C_, n, stride, 1, acc_ptr, 1 if init else 0, stream))
+
+    def noise_stats_collapsed_device(self, ptr, dtype, n, stream=None):
+        self._check(self.lib.dll.b200gate_noise_stats_collapsed(self._h, ptr, dtype_code(dtype), n, 1, stream))
 
     def set_noise_threshold(self, thresh_db):
         t = np.ascontiguousarray(thresh_db, dtype=np.float64)

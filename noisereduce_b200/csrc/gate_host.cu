@@ -49,6 +49,7 @@ struct b200gate_handle {
     size_t raw_bytes = 0;
     Counters* d_cnt = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> stage_ev;             // 4 per batch: k1 start, k1 end(+rowfloor), smooth end, k2 end
     b200gate_stats stats{};
     // debug taps
     long long dbg_chunk = -1, dbg_channel = -1;
@@ -160,7 +161,7 @@ int build_threshold_tables(b200gate_handle* h) {
         if (!(Tf > 0.0)) Tf = 0.0;
         t2[f] = T * T;
         thr4[f] = (float)(4.0 * T * T);
-        gco[f] = (float)(8.0 * T * kKappa * kEps32);
+        gco[f] = (float)(8.0 * T * kKappa * kEps32 * (h->p.debug_guard_scale > 0 ? h->p.debug_guard_scale : 1));
         floor4[f] = (float)(4.0 * Tf * Tf);
     }
     int rc;
@@ -312,6 +313,7 @@ void b200gate_destroy(b200gate_handle* h) {
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
     delete h;
 }
 
@@ -564,8 +566,15 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const double D = (double)(nf + 1) * (nf + 1) * (nt + 1) * (nt + 1);
     const int resident = h->num_sm * 3;
 
+    const size_t n_batches = (size_t)((U + ub - 1) / ub);
+    while (h->stage_ev.size() < 4 * n_batches) {
+        cudaEvent_t e;
+        CK(h, cudaEventCreate(&e));
+        h->stage_ev.push_back(e);
+    }
+    size_t bi = 0;
     cudaEventRecord(evk0, st);
-    for (long long u0 = 0; u0 < U; u0 += ub) {
+    for (long long u0 = 0; u0 < U; u0 += ub, ++bi) {
         const int nu = (int)std::min(ub, U - u0);
         g.u0 = (int)u0;
         g.n_units = nu;
@@ -575,6 +584,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         dbg.mask = h->d_dbg_mask;
 
         CK(h, cudaMemsetAsync(d_rowmax, 0, (size_t)nu * kFPad * 4, st));
+        cudaEventRecord(h->stage_ev[4 * bi + 0], st);
         // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
         K1Args a1{};
         a1.g = g; a1.tb = tb; a1.x = x; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
@@ -591,12 +601,16 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
                     (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
         launches += 2;
+        cudaEventRecord(h->stage_ev[4 * bi + 1], st);
+        cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+        cudaEventRecord(h->stage_ev[4 * bi + 3], st);
         if (tf_hi > tf_lo) {
             SmoothArgs sa{};
             sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
             sa.bits = d_bits; sa.rowflag = d_rowflag; sa.num = d_num;
             const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
             B200_LAUNCH(k_smooth, dim3(tiles, nu), dim3(256), smooth_smem_bytes(sa.TT, nf, nt), st, sa);
+            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
             K2Args a2{};
             a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.num = d_num;
             a2.pD = (float)(p.prop_decrease / D);
@@ -615,6 +629,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const long long items2 = (long long)nu * a2.n_runs;
             B200_LAUNCH(k2_synthesize<8>, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
                         k2_smem_floats(g.H) * 4, st, a2);
+            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
             launches += 2;
         }
         if (dbg.ul >= 0) {
@@ -670,6 +685,15 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     h->stats.rowfloor_flags = (int64_t)cnt.floor_flags;
     h->stats.rowfloor_ambiguous = (int64_t)cnt.floor_ambiguous;
     h->stats.last_run_ms = ms;
+    for (size_t b = 0; b < n_batches; ++b) {
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        cudaEventElapsedTime(&t1, h->stage_ev[4 * b + 0], h->stage_ev[4 * b + 1]);
+        cudaEventElapsedTime(&t2, h->stage_ev[4 * b + 1], h->stage_ev[4 * b + 2]);
+        cudaEventElapsedTime(&t3, h->stage_ev[4 * b + 2], h->stage_ev[4 * b + 3]);
+        h->stats.k1_ms += t1;
+        h->stats.smooth_ms += t2;
+        h->stats.k2_ms += t3;
+    }
     h->stats.last_h2d_ms = h2d_ms;
     return B200GATE_OK;
 }

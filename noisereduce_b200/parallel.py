@@ -1,0 +1,50 @@
+"""Multi-GPU: one process per GPU, channels sharded across ranks.
+
+Every (chunk, channel) unit is independent, so the data path needs no collective.  The only
+cross-rank dependency is the stationary noise threshold, which the reference computes from the mean
+over ALL channels in channel order and in the input dtype (stationary.py:61-64).  To reproduce that
+float32 sum bit for bit, ranks chain it: rank r continues the running sum of rank r-1 with its own
+channels (one 2.4 MB point-to-point hop per rank), the last rank divides, and the collapsed noise clip
+is broadcast.  The result is gathered with ONE all_gather of the final waveform (north_star).
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the plumbing.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def chained_noise_stats(dg, x_local: torch.Tensor, rank: int, world: int, group=None):
+    """Exact multi-rank version of SpectralGateStationary.__init__'s noise statistics."""
+    p = dg.gate.params
+    C, N = x_local.shape
+    n = N
+    if p.clip_noise and p.chunk_size > 0 and n > p.chunk_size:
+        n = int(p.chunk_size)
+    acc = torch.zeros(n, dtype=torch.float32, device=x_local.device)
+    if rank > 0:
+        dist.recv(acc, src=rank - 1, group=group)
+    stream = torch.cuda.current_stream().cuda_stream if x_local.is_cuda else None
+    dg.gate.channel_sum_device(x_local.data_ptr(), np.float32, C, n, x_local.stride(0), acc.data_ptr(),
+                               init=(rank == 0), stream=stream)
+    if x_local.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    if rank < world - 1:
+        dist.send(acc, dst=rank + 1, group=group)
+    mean = acc / np.float32(world * C) if rank == world - 1 else acc      # numpy: sum / count in float32
+    dist.broadcast(mean, src=world - 1, group=group)
+    dg.gate.noise_stats_collapsed_device(mean.data_ptr(), np.float32, n, stream=stream)
+    return mean
+
+
+def sharded_reduce_noise(dg, x_local: torch.Tensor, rank: int, world: int, gather=True, group=None):
+    """Denoise this rank's channel shard; optionally all-gather the [world*C, N] result."""
+    if dg.stationary:
+        chained_noise_stats(dg, x_local, rank, world, group)
+    y_local = dg.run(x_local)
+    if not gather or world == 1:
+        return y_local
+    full = torch.empty((world * x_local.shape[0], x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
+    dist.all_gather_into_tensor(full, y_local, group=group)
+    return full

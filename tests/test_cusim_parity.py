@@ -1,0 +1,121 @@
+"""Kernel-logic parity on the CPU simulator build (tests/cusim) -- runs in the GPU-less container.
+
+These run the PRODUCT's .cu sources (compiled by g++ against the cusim shim) on tiny inputs and
+compare them with oracle/.  They guard indexing / barrier / shuffle logic and the host planner; the
+real-hardware parity tests are tests/test_gpu_parity.py (-m gpu).
+"""
+import numpy as np
+import pytest
+
+from noisereduce_b200 import _cabi
+from oracle import spectral_gate_oracle as O
+from tests import parity_cases as P
+from tests.cusim_util import cusim_library
+from tests.synth_host import synth_small
+
+SR = 16000
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return cusim_library()
+
+
+def _assert_stationary(res, exact_bits=True):
+    assert res["spec_err"] < P.SPEC_TOL
+    if exact_bits:
+        assert res["mask0_mismatch"] == 0
+    assert res["mask_err"] < P.MASK_TOL
+    assert res["out_relinf"] < P.OUT_TOL_TIGHT
+    assert res["stats"]["bins_unresolved"] == 0
+    assert res["stats"]["rowfloor_ambiguous"] == 0
+    assert res["thresh_err_db"] < P.THRESH_TOL_DB
+
+
+def test_stationary_chunked_two_channels(lib):
+    y = synth_small(C=2, n=12000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=5000, padding=600)
+    res = P.check_stationary(lib, y, cfg, tap_unit=(1, 1))
+    _assert_stationary(res)
+    assert res["stats"]["units"] == 6 and res["mask0_on_frac"] > 0.05
+    # last chunk (shorter valid span) and first chunk (left zero padding)
+    _assert_stationary(P.check_stationary(lib, y, cfg, tap_unit=(2, 0)))
+    _assert_stationary(P.check_stationary(lib, y, cfg, tap_unit=(0, 1)))
+
+
+def test_stationary_own_thresholds_end_to_end(lib):
+    y = synth_small(C=2, n=9000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=4000, padding=500)
+    res = P.check_stationary(lib, y, cfg, tap_unit=(0, 0), inject_thresh=False)
+    assert res["thresh_err_db"] < P.THRESH_TOL_DB
+    assert res["out_relinf"] < P.OUT_TOL
+
+
+def test_stationary_single_chunk_blend_and_ynoise(lib):
+    y = synth_small(C=1, n=7000)
+    cfg = O.GateConfig(sr=SR, stationary=True, prop_decrease=0.8)          # defaults: one padded chunk
+    res = P.check_stationary(lib, y, cfg, y_noise=y[:, 1000:5000])
+    _assert_stationary(res)
+    assert res["stats"]["units"] == 1
+
+
+def test_stationary_no_smoothing_and_tiny_padding(lib):
+    y = synth_small(C=1, n=6000)
+    cfg = O.GateConfig(sr=SR, stationary=True, freq_mask_smooth_hz=None, time_mask_smooth_ms=None,
+                       chunk_size=2500, padding=100)      # padding < hop: tail zeros + edge overlap-add norms
+    res = P.check_stationary(lib, y, cfg, tap_unit=(1, 0))
+    _assert_stationary(res)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=2500, padding=0)
+    _assert_stationary(P.check_stationary(lib, y, cfg, tap_unit=(2, 0)))
+
+
+def test_fp64_redecision_path_gives_same_bits(lib):
+    y = synth_small(C=1, n=5000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=None, padding=300)
+    res = P.check_stationary(lib, y, cfg, debug_guard_scale=100000)
+    assert res["stats"]["bins_rechecked_fp64"] > 100        # the knob forced many bins through FP64
+    _assert_stationary(res)
+
+
+def test_top_db_row_floor(lib):
+    # a steady loud tone sits > 80 dB above the noise threshold of its bin: the whole row is lifted
+    n = 6000
+    t = np.arange(n) / SR
+    rng = np.random.default_rng(5)
+    y = (1e-5 * rng.standard_normal(n) + 0.9 * np.sin(2 * np.pi * 1000 * t)).astype(np.float32)[None, :]
+    noise = (1e-5 * rng.standard_normal(4000)).astype(np.float32)[None, :]
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=None, padding=300)
+    res = P.check_stationary(lib, y, cfg, y_noise=noise)
+    assert res["stats"]["rowfloor_flags"] > 0
+    _assert_stationary(res)
+
+
+def test_int16_and_float64_io(lib):
+    y = synth_small(C=2, n=6000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=2500, padding=400)
+    yi = (y * 20000).astype(np.int16)
+    res = P.check_stationary(lib, yi, cfg)
+    assert res["out_dtype_ok"] and res["out_max_lsb"] <= 1
+    res = P.check_stationary(lib, y.astype(np.float64), cfg)
+    assert res["out_dtype_ok"] and res["out_relinf"] < P.OUT_TOL_TIGHT
+
+
+def test_python_surface_on_simulator(lib, monkeypatch):
+    """reduce_noise() host logic (shapes, dtypes, defaults, errors) with the simulator library."""
+    monkeypatch.setattr(_cabi, "_LIB", lib)
+    import noisereduce_b200 as nr
+    y = synth_small(C=2, n=6000)
+    out = nr.reduce_noise(y=y, sr=SR, stationary=True, chunk_size=2500, padding=400, n_jobs=4, use_tqdm=True)
+    ref = O.reduce_noise(y, SR, cfg=O.GateConfig(sr=SR, stationary=True, chunk_size=2500, padding=400))
+    assert out.shape == y.shape and out.dtype == y.dtype
+    assert P.relinf(out, ref) < P.OUT_TOL
+    flat = nr.reduce_noise(y=y[0], sr=SR, stationary=True)
+    assert flat.shape == (6000,)
+    with pytest.raises(ValueError, match="Waveform must be in shape"):
+        nr.reduce_noise(y=np.zeros((2, 2, 100), np.float32), sr=SR, stationary=True)
+    with pytest.raises(ValueError, match="freq_mask_smooth_hz needs to be at least"):
+        nr.reduce_noise(y=y, sr=SR, stationary=True, freq_mask_smooth_hz=10)
+    with pytest.raises(ValueError, match="n_jobs must be 1"):
+        nr.reduce_noise(y=y, sr=SR, stationary=True, use_torch=True, n_jobs=2)
+    with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
+        nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=512)

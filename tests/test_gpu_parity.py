@@ -1,0 +1,106 @@
+"""Parity on a real B200 (-m gpu), through the C ABI of the nvcc-built libb200gate.so."""
+import os
+
+import numpy as np
+import pytest
+
+from noisereduce_b200 import _cabi
+from oracle import spectral_gate_oracle as O
+from tests import parity_cases as P
+from tests.synth_host import synth_small
+
+pytestmark = pytest.mark.gpu
+SR = 16000
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _cabi.library()          # the product library; raises if it was not built
+
+
+def _assert_stationary(res):
+    assert res["spec_err"] < P.SPEC_TOL, res
+    assert res["mask0_mismatch"] == 0, res
+    assert res["mask_err"] < P.MASK_TOL, res
+    assert res["out_relinf"] < P.OUT_TOL_TIGHT, res
+    assert res["stats"]["bins_unresolved"] == 0 and res["stats"]["rowfloor_ambiguous"] == 0, res
+    assert res["thresh_err_db"] < P.THRESH_TOL_DB, res
+
+
+def test_small_cases_match_simulator_suite(lib):
+    y = synth_small(C=2, n=12000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=5000, padding=600)
+    for unit in [(1, 1), (2, 0), (0, 1)]:
+        _assert_stationary(P.check_stationary(lib, y, cfg, tap_unit=unit))
+    cfg = O.GateConfig(sr=SR, stationary=True, prop_decrease=0.8)
+    _assert_stationary(P.check_stationary(lib, y[:1, :7000], cfg, y_noise=y[:1, 1000:5000]))
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=2500, padding=0)
+    _assert_stationary(P.check_stationary(lib, y[:1, :6000], cfg, tap_unit=(2, 0)))
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=None, padding=300)
+    res = P.check_stationary(lib, y[:1, :5000], cfg, debug_guard_scale=100000)
+    assert res["stats"]["bins_rechecked_fp64"] > 100
+    _assert_stationary(res)
+
+
+def test_config2_shaped_chunks_mask_bit_exact(lib):
+    """48 kHz, default chunk_size / padding (config 2 geometry: T = 2579 frames, 11 x 19 filter),
+    3 channels x 1.3 M samples = 3 chunks: first / interior / last chunk taps."""
+    sr = 48000
+    rng = np.random.default_rng(1000)
+    n = 1_300_000
+    t = np.arange(n) / sr
+    y = 0.05 * rng.standard_normal((3, n))
+    for c in range(3):
+        y[c] += 0.25 * ((t % 2.0) < 0.5) * np.sin(2 * np.pi * 440 * 2 ** (c / 12) * t)
+    y = y.astype(np.float32)
+    cfg = O.GateConfig(sr=sr, stationary=True)
+    worst = 0.0
+    for unit in [(0, 0), (1, 2), (2, 1)]:
+        res = P.check_stationary(lib, y, cfg, tap_unit=unit)
+        _assert_stationary(res)
+        assert res["T"] == 2579
+        worst = max(worst, res["out_relinf"])
+    print("config-2 geometry: worst rel-inf", worst, "rechecked", res["stats"]["bins_rechecked_fp64"])
+    # the library's own thresholds, end to end
+    res = P.check_stationary(lib, y, cfg, tap_unit=(1, 0), inject_thresh=False)
+    assert res["out_relinf"] < P.OUT_TOL
+    assert res["mask0_mismatch"] <= 2          # threshold noise of the reference's float32 noise STFT
+
+
+def test_golden_fish_and_small(lib, golden_dir):
+    import noisereduce_b200 as nr
+    f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
+    out = nr.reduce_noise(y=f["y"], sr=int(f["sr"]), stationary=True)
+    assert out.dtype == np.int16 and out.shape == f["y"].shape
+    assert np.abs(out.astype(np.int32) - f["out_stationary"].astype(np.int32)).max() <= 1      # <= 1 LSB
+    yf = (f["y"] / 32768).astype(np.float32)
+    out = nr.reduce_noise(y=yf, sr=int(f["sr"]), stationary=True)
+    assert P.relinf(out, f["out_stationary_f32"]) < P.OUT_TOL
+    s = np.load(os.path.join(golden_dir, "synth_small.npz"))
+    kw = dict(chunk_size=12000, padding=1500)
+    y, sr = s["y"], int(s["sr"])
+    assert P.relinf(nr.reduce_noise(y=y, sr=sr, stationary=True, **kw), s["out_stat_chunked"]) < P.OUT_TOL
+    assert P.relinf(nr.reduce_noise(y=y, sr=sr, stationary=True, y_noise=y[:, 3000:11000], prop_decrease=0.8, **kw),
+                    s["out_stat_ynoise_p08"]) < P.OUT_TOL
+    assert P.relinf(nr.reduce_noise(y=y[0], sr=sr, stationary=True), s["out_stat_single_chunk"]) < P.OUT_TOL
+    assert P.relinf(nr.reduce_noise(y=y, sr=sr, stationary=True, freq_mask_smooth_hz=None,
+                                    time_mask_smooth_ms=None, **kw), s["out_stat_nosmooth"]) < P.OUT_TOL
+
+
+def test_device_pointer_path_and_properties(lib):
+    """Device-resident tensors through the same C call; linearity-in-scale and chunk independence."""
+    import torch
+    from noisereduce_b200.device import DeviceGate
+    sr = 48000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = 0.05 * torch.randn((4, 2_000_000), device="cuda", generator=g)
+    dg = DeviceGate(sr=sr, stationary=True)
+    dg.noise_stats(x)
+    y = dg.run(x)
+    torch.cuda.synchronize()
+    ref = O.reduce_noise(x[:1].cpu().numpy(), sr, cfg=O.GateConfig(sr=sr, stationary=True),
+                         thresh_override=dg.gate.noise_threshold(), return_float64=True)
+    assert P.relinf(y[:1].cpu().numpy(), ref) < P.OUT_TOL_TIGHT
+    # idempotent launch: same input -> bit-identical output (no races in the overlap-add seams)
+    y2 = dg.run(x)
+    assert torch.equal(y, y2)

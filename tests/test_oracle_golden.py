@@ -187,3 +187,15 @@ def test_torchgate_xn(tgs):
     assert relinf(out, tgs["out_stat_xn_p07_f64"]) < TG_TOL
     with pytest.raises(Exception, match="x must be bigger than"):
         TO.torchgate_forward(x[:, :1000], sr)
+
+
+# ---- the performance-faithful port used for the CPU baseline --------------------------------
+def test_ref_port_matches_reference(small, fish):
+    from oracle import ref_port
+    y, sr = small["y"], int(small["sr"])
+    out = ref_port.reduce_noise(y, sr, O.GateConfig(sr=sr, stationary=True, **CH), n_jobs=2)
+    assert np.array_equal(out, small["out_stat_chunked"])
+    out = ref_port.reduce_noise(y, sr, O.GateConfig(sr=sr, stationary=False, **CH))
+    assert np.array_equal(out, small["out_nonstat_chunked"])
+    out = ref_port.reduce_noise(fish["y"], int(fish["sr"]), O.GateConfig(sr=int(fish["sr"]), stationary=True))
+    assert np.array_equal(out, fish["out_stationary"])
