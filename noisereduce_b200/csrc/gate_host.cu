@@ -256,8 +256,6 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         return fail(nullptr, B200GATE_ERR_ARG, "ABI version %d, library is %d", p->abi_version, B200GATE_ABI_VERSION);
     if (p->surface != B200GATE_SURFACE_NUMPY)
         return fail(nullptr, B200GATE_ERR_ARG, "surface %d is not built into this library yet", p->surface);
-    if (!p->stationary)
-        return fail(nullptr, B200GATE_ERR_ARG, "the non-stationary gate is not built into this library yet");
     if (p->n_fft != kN || p->win_length != p->n_fft || p->hop_length * 4 != p->n_fft)
         return fail(nullptr, B200GATE_ERR_ARG,
                     "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d: this build runs "
@@ -291,7 +289,10 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaEventCreate(&h->ev1);
 #ifndef B200_CUSIM_BUILD
         cudaFuncSetAttribute(k1_analyze<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats() * 4);
-        cudaFuncSetAttribute(k2_synthesize<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
+        cudaFuncSetAttribute(k2_synthesize<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
+        cudaFuncSetAttribute(k2_synthesize<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
+        cudaFuncSetAttribute(k1n_magnitude<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
+        cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 #endif
     }
@@ -444,7 +445,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                  int64_t out_stride, int is_device, void* stream) {
     if (!h || !in || !out || C <= 0 || N <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
     if (in_stride < N || out_stride < N) return fail(h, B200GATE_ERR_ARG, "row strides must be >= N");
-    if (!h->have_thresh) return fail(h, B200GATE_ERR_STATE, "stationary gate: call b200gate_noise_stats first");
+    if (h->p.stationary && !h->have_thresh)
+        return fail(h, B200GATE_ERR_STATE, "stationary gate: call b200gate_noise_stats first");
     cudaStream_t st = (cudaStream_t)stream;
     const b200gate_params& p = h->p;
     const size_t es = dtype_size(dtype);
@@ -528,7 +530,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     }
 
     // ---- workspace / batching ---------------------------------------------------------------------
-    const size_t per_unit = (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64;
+    const bool stat = p.stationary != 0;
+    const size_t per_unit = stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
+                                 : 2 * (size_t)g.T * kFPad * 4 + 64;
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
@@ -540,6 +544,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     unsigned* d_rowmax = d_bits + (size_t)ub * g.T * kFW;
     unsigned* d_rowflag = d_rowmax + (size_t)ub * kFPad;
     unsigned short* d_num = (unsigned short*)(d_rowflag + (size_t)ub * kFW);
+    float* d_mag = (float*)h->d_ws_buf;                        // non-stationary: |X|, later the final mask
+    float* d_m0 = d_mag + (size_t)ub * g.T * kFPad;            //                 forward sweep / sigmoid mask
 
     CK(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), st));
     const long long dbg_u = (h->dbg_chunk >= 0 && h->dbg_chunk < g.n_chunks && h->dbg_channel >= 0 && h->dbg_channel < C)
@@ -583,56 +589,113 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         dbg.spec = h->d_dbg_spec;
         dbg.mask = h->d_dbg_mask;
 
-        CK(h, cudaMemsetAsync(d_rowmax, 0, (size_t)nu * kFPad * 4, st));
-        cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-        // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
-        K1Args a1{};
-        a1.g = g; a1.tb = tb; a1.x = x; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
-        {
-            long long want = (long long)resident * kWarps * 4;
-            long long run = ((long long)nu * g.T + want - 1) / want;
-            run = std::max(8LL, std::min(64LL, run));
-            run += run & 1;
-            a1.run = (int)run;
-            a1.n_runs = (g.T + a1.run - 1) / a1.run;
-        }
-        const long long items1 = (long long)nu * a1.n_runs;
-        B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, resident)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
-        B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
-                    (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
-        launches += 2;
-        cudaEventRecord(h->stage_ev[4 * bi + 1], st);
-        cudaEventRecord(h->stage_ev[4 * bi + 2], st);
-        cudaEventRecord(h->stage_ev[4 * bi + 3], st);
-        if (tf_hi > tf_lo) {
-            SmoothArgs sa{};
-            sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
-            sa.bits = d_bits; sa.rowflag = d_rowflag; sa.num = d_num;
-            const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-            B200_LAUNCH(k_smooth, dim3(tiles, nu), dim3(256), smooth_smem_bytes(sa.TT, nf, nt), st, sa);
-            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
-            K2Args a2{};
-            a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.num = d_num;
-            a2.pD = (float)(p.prop_decrease / D);
-            a2.one_minus_p = (float)(1.0 - p.prop_decrease);
-            a2.nt = nt;
-            a2.dbg = dbg;
+        if (stat) {
+            CK(h, cudaMemsetAsync(d_rowmax, 0, (size_t)nu * kFPad * 4, st));
+            cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+            // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
+            K1Args a1{};
+            a1.g = g; a1.tb = tb; a1.x = x; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
             {
-                const long long hops = h_hi - h_lo;
                 long long want = (long long)resident * kWarps * 4;
-                long long run = ((long long)nu * hops + want - 1) / want;
-                run = std::max(16LL, std::min(128LL, run));
+                long long run = ((long long)nu * g.T + want - 1) / want;
+                run = std::max(8LL, std::min(64LL, run));
                 run += run & 1;
-                a2.run = (int)run;
-                a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
+                a1.run = (int)run;
+                a1.n_runs = (g.T + a1.run - 1) / a1.run;
             }
-            const long long items2 = (long long)nu * a2.n_runs;
-            B200_LAUNCH(k2_synthesize<8>, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
-                        k2_smem_floats(g.H) * 4, st, a2);
-            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+            const long long items1 = (long long)nu * a1.n_runs;
+            B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, resident)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
+            B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
+                        (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
             launches += 2;
+            cudaEventRecord(h->stage_ev[4 * bi + 1], st);
+            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+            if (tf_hi > tf_lo) {
+                SmoothArgs sa{};
+                sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
+                sa.bits = d_bits; sa.rowflag = d_rowflag; sa.num = d_num;
+                const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                B200_LAUNCH(k_smooth, dim3(tiles, nu), dim3(256), smooth_smem_bytes(sa.TT, nf, nt), st, sa);
+                cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+                K2Args a2{};
+                a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.num = d_num;
+                a2.pD = (float)(p.prop_decrease / D);
+                a2.one_minus_p = (float)(1.0 - p.prop_decrease);
+                a2.nt = nt;
+                a2.dbg = dbg;
+                {
+                    const long long hops = h_hi - h_lo;
+                    long long want = (long long)resident * kWarps * 4;
+                    long long run = ((long long)nu * hops + want - 1) / want;
+                    run = std::max(16LL, std::min(128LL, run));
+                    run += run & 1;
+                    a2.run = (int)run;
+                    a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
+                }
+                const long long items2 = (long long)nu * a2.n_runs;
+                auto kern2 = k2_synthesize<8, false>;
+                B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
+                            k2_smem_floats(g.H) * 4, st, a2);
+                cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+                launches += 2;
+            }
+        } else {
+            cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+            K1nArgs a1{};
+            a1.g = g; a1.tb = tb; a1.x = x; a1.mag = d_mag; a1.dbg = dbg;
+            {
+                long long want = (long long)resident * kWarps * 4;
+                long long run = ((long long)nu * g.T + want - 1) / want;
+                run = std::max(8LL, std::min(64LL, run));
+                run += run & 1;
+                a1.run = (int)run;
+                a1.n_runs = (g.T + a1.run - 1) / a1.run;
+            }
+            B200_LAUNCH(k1n_magnitude<8>, dim3(grid_1d((long long)nu * a1.n_runs, kWarps, resident)), dim3(kThreads),
+                        k1n_smem_floats() * 4, st, a1);
+            cudaEventRecord(h->stage_ev[4 * bi + 1], st);
+            IirArgs ia{};
+            ia.n_units = nu; ia.T = g.T;
+            {
+                const double tfr = p.time_constant_s * p.sr / (double)g.H;        // nonstationary.py:109-114
+                ia.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
+            }
+            ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
+            ia.mag = d_mag; ia.m0 = d_m0;
+            B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
+            launches += 2;
+            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+            if (tf_hi > tf_lo) {
+                SmoothFArgs sa{};
+                sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
+                sa.p = (float)p.prop_decrease; sa.one_minus_p = (float)(1.0 - p.prop_decrease);
+                sa.m0 = d_m0; sa.m2 = d_mag;
+                const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, nf), st, sa);
+                cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+                K2Args a2{};
+                a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.fmask = d_mag;
+                a2.nt = nt;
+                a2.dbg = dbg;
+                {
+                    const long long hops = h_hi - h_lo;
+                    long long want = (long long)resident * kWarps * 4;
+                    long long run = ((long long)nu * hops + want - 1) / want;
+                    run = std::max(16LL, std::min(128LL, run));
+                    run += run & 1;
+                    a2.run = (int)run;
+                    a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
+                }
+                auto kern2 = k2_synthesize<8, true>;
+                B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
+                            k2_smem_floats(g.H) * 4, st, a2);
+                cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+                launches += 2;
+            }
         }
-        if (dbg.ul >= 0) {
+        if (dbg.ul >= 0 && stat) {
             // tapped mask words with the row floor folded in, as the smoothing kernel consumes them
             std::vector<unsigned> fl(kFW);
             CK(h, cudaStreamSynchronize(st));

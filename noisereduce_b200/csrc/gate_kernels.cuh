@@ -369,7 +369,8 @@ struct K2Args {
     Tables tb;
     const float* x;
     float* y;                      // [C][out_stride] float32
-    const unsigned short* num;     // [n_units][T][FPad] integer mask numerators
+    const unsigned short* num;     // [n_units][T][FPad] integer mask numerators (stationary)
+    const float* fmask;            // [n_units][T][FPad] final float masks (non-stationary)
     float pD;                      // prop_decrease / D
     float one_minus_p;             // 1 - prop_decrease
     int nt;                        // time half-width (edge factor of the first/last frames)
@@ -388,7 +389,7 @@ __device__ __forceinline__ float time_edge(int t, int T, int nt) {
     return (float)s / (float)((nt + 1) * (nt + 1));
 }
 
-template <int HR>
+template <int HR, bool FMASK>
 __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
     constexpr int NH = 32 / HR;             // frames overlapping one hop (win / hop)
     B200_DYN_SMEM(float, smem);
@@ -438,7 +439,8 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         const int t_last = min(he - 1, g.T - 1);
         const float* xrow = a.x + (long long)c * g.in_stride;
         float* yrow = a.y + (long long)c * g.out_stride;
-        const unsigned short* mrow = a.num + (long long)ul * g.T * kFPad;
+        const unsigned short* mrow = FMASK ? nullptr : a.num + (long long)ul * g.T * kFPad;
+        const float* frow = FMASK ? a.fmask + (long long)ul * g.T * kFPad : nullptr;
 
         float acc[32 + HR];
 #pragma unroll
@@ -452,10 +454,9 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                 load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, va, vb);
                 warp_fft1024<false>(re, im, tile, s_tw, lane);
 
-                const unsigned short* mA = mrow + (long long)t * kFPad;
-                const unsigned short* mB = mrow + (long long)(vb ? t + 1 : t) * kFPad;
+                const long long offA = (long long)t * kFPad, offB = (long long)(vb ? t + 1 : t) * kFPad;
                 float eta = 0.f, etb = 0.f;
-                if (blend) {
+                if (!FMASK && blend) {
                     eta = a.one_minus_p * time_edge(t, g.T, a.nt);
                     etb = a.one_minus_p * time_edge(t + 1, g.T, a.nt);
                 }
@@ -463,8 +464,14 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                 for (int q = 0; q < kFW; ++q) {
                     const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
                     const int k = lane + 32 * q;                 // < FPad, rows are padded
-                    float ma = fmaf((float)mA[k], a.pD, eta * s_ef[k]);
-                    float mb = fmaf((float)mB[k], a.pD, etb * s_ef[k]);
+                    float ma, mb;
+                    if (FMASK) {
+                        ma = frow[offA + k];
+                        mb = frow[offB + k];
+                    } else {
+                        ma = fmaf((float)mrow[offA + k], a.pD, eta * s_ef[k]);
+                        mb = fmaf((float)mrow[offB + k], a.pD, etb * s_ef[k]);
+                    }
                     if (!vb) mb = 0.f;
                     if (a.dbg.ul == ul && k < kF && ((q < 16) || lane == 0)) {
                         a.dbg.mask[(long long)t * kF + k] = ma;
@@ -530,6 +537,167 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
 #pragma unroll
             for (int r = 32 - HR; r < 32 + HR; ++r) acc[r] = 0.f;
         }
+    }
+}
+
+
+// =============================================================================================
+// Non-stationary gate (nonstationary.py:47-97).
+//   k1n_magnitude  frames -> FFT -> |X|                         [n_units][T][FPad] float32
+//   k_iir_sigmoid  filtfilt([b],[1,b-1]) along time per bin (forward sweep started at x[0], backward
+//                  sweep over the forward output started at its last value -- nonstationary.py:106-115),
+//                  then sigmoid(((|X| - S)/S - n_mult) * slope)  (spectralgate/utils.py:4-8)
+//   k_smooth_f     separable triangular smoothing (zero padded), then  m * p + (1 - p)
+// =============================================================================================
+struct K1nArgs {
+    Geom g;
+    Tables tb;
+    const float* x;
+    float* mag;                // [n_units][T][FPad]
+    DebugTap dbg;
+    int run, n_runs;
+};
+
+constexpr int k1n_smem_floats() { return kN + 2 * kN + kWarps * kExchFloats; }
+
+template <int HR>
+__global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
+    B200_DYN_SMEM(float, smem);
+    float* s_wa = smem;
+    float2* s_tw = reinterpret_cast<float2*>(smem + kN);
+    float* s_tiles = smem + 3 * kN;
+    for (int i = threadIdx.x; i < kN; i += kThreads) {
+        s_wa[i] = a.tb.wa[i];
+        s_tw[i] = a.tb.tw[i];
+    }
+    __syncthreads();
+    const Geom& g = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = s_tiles + warp * kExchFloats;
+    const int H = g.H;
+    const int pl = (32 - lane) & 31;
+    const long long n_items = (long long)g.n_units * a.n_runs;
+    for (long long item = (long long)blockIdx.x * kWarps + warp; item < n_items;
+         item += (long long)gridDim.x * kWarps) {
+        const int ul = (int)(item / a.n_runs);
+        const int run = (int)(item - (long long)ul * a.n_runs);
+        const int u = g.u0 + ul;
+        const int ic = u / g.C, c = u - ic * g.C;
+        const long long i1 = (long long)ic * g.step - g.pad;
+        const float* xrow = a.x + (long long)c * g.in_stride;
+        const int t0 = run * a.run;
+        const int t1 = min(t0 + a.run, g.T);
+        for (int t = t0; t < t1; t += 2) {
+            const bool vb = (t + 1 < t1);
+            const long long base = (long long)t * H - kN / 2;
+            float re[32], im[32];
+            load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, true, vb);
+            warp_fft1024<false>(re, im, tile, s_tw, lane);
+            float* dstA = a.mag + ((long long)ul * g.T + t) * kFPad;
+#pragma unroll
+            for (int q = 0; q < kFW; ++q) {
+                const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
+                const float zr = re[sA], zi = im[sA];
+                float pr = __shfl_sync(0xffffffffu, re[sP], pl);
+                float pi = __shfl_sync(0xffffffffu, im[sP], pl);
+                if (lane == 0) { pr = re[s0]; pi = im[s0]; }
+                const float ar = zr + pr, ai = zi - pi;
+                const float br = zi + pi, bi = pr - zr;
+                const int k = lane + 32 * q;
+                const bool valid = (q < 16) || (lane == 0);
+                const float ma = valid ? 0.5f * sqrtf(fmaf(ar, ar, ai * ai)) : 0.f;
+                const float mb = valid ? 0.5f * sqrtf(fmaf(br, br, bi * bi)) : 0.f;
+                dstA[k] = ma;
+                if (vb) dstA[kFPad + k] = mb;
+                if (a.dbg.ul == ul && valid && k < kF) {
+                    float* sp = a.dbg.spec + ((long long)t * kF + k) * 2;
+                    sp[0] = 0.5f * ar; sp[1] = 0.5f * ai;
+                    if (vb) { sp[2 * kF] = 0.5f * br; sp[2 * kF + 1] = 0.5f * bi; }
+                }
+            }
+        }
+    }
+}
+
+struct IirArgs {
+    int n_units, T;
+    double b;                  // nonstationary.py:114
+    float n_mult, slope;       // thresh_n_mult_nonstationary, sigmoid_slope_nonstationary
+    const float* mag;          // [n_units][T][FPad]
+    float* m0;                 // [n_units][T][FPad]: forward sweep, then overwritten by the sigmoid mask
+};
+
+__global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.n_units * kFPad) return;
+    const int ul = (int)(idx / kFPad), f = (int)(idx - (long long)ul * kFPad);
+    const float* A = a.mag + (long long)ul * a.T * kFPad + f;
+    float* M = a.m0 + (long long)ul * a.T * kFPad + f;
+    if (f >= kF) {
+        for (int t = 0; t < a.T; ++t) M[(long long)t * kFPad] = 0.f;
+        return;
+    }
+    const double b = a.b, omb = 1.0 - a.b;
+    double s = (double)A[0];
+#pragma unroll 8
+    for (int t = 0; t < a.T; ++t) {
+        s = b * (double)A[(long long)t * kFPad] + omb * s;
+        M[(long long)t * kFPad] = (float)s;
+    }
+    s = (double)M[(long long)(a.T - 1) * kFPad];
+#pragma unroll 8
+    for (int t = a.T - 1; t >= 0; --t) {
+        s = b * (double)M[(long long)t * kFPad] + omb * s;
+        const double r = ((double)A[(long long)t * kFPad] - s) / s;
+        M[(long long)t * kFPad] = (float)(1.0 / (1.0 + exp(-(r - (double)a.n_mult) * (double)a.slope)));
+    }
+}
+
+struct SmoothFArgs {
+    int n_units, T;
+    int nf, nt;
+    int tf_lo, tf_hi, TT;
+    float p, one_minus_p;
+    const float* m0;           // [n_units][T][FPad]
+    float* m2;                 // [n_units][T][FPad]
+};
+__host__ __device__ inline int smoothf_cpitch(int nf) { return kFPad + 2 * nf + 1; }
+inline size_t smoothf_smem_bytes(int TT, int nf) { return (size_t)TT * smoothf_cpitch(nf) * 4; }
+
+__global__ void __launch_bounds__(256) k_smooth_f(const SmoothFArgs a) {
+    B200_DYN_SMEM(float, s_c);                         // [TT][cp]
+    const int nt = a.nt, nf = a.nf, cp = smoothf_cpitch(nf);
+    const int ul = blockIdx.y;
+    const int t0 = a.tf_lo + blockIdx.x * a.TT;
+    if (t0 >= a.tf_hi) return;
+    const int tt_n = min(a.TT, a.tf_hi - t0);
+    for (int i = threadIdx.x; i < a.TT * cp; i += blockDim.x) s_c[i] = 0.f;
+    __syncthreads();
+    const float* src = a.m0 + (long long)ul * a.T * kFPad;
+    for (int i = threadIdx.x; i < tt_n * kFPad; i += blockDim.x) {
+        const int tt = i / kFPad, f = i - tt * kFPad;
+        if (f >= kF) continue;
+        const int t = t0 + tt;
+        float acc = 0.f;
+        for (int bb = -nt; bb <= nt; ++bb) {
+            const int tq = t - bb;
+            if (tq >= 0 && tq < a.T) acc = fmaf((float)(nt + 1 - (bb < 0 ? -bb : bb)), src[(long long)tq * kFPad + f], acc);
+        }
+        s_c[tt * cp + nf + f] = acc;
+    }
+    __syncthreads();
+    const float invD = 1.0f / ((float)((nf + 1) * (nf + 1)) * (float)((nt + 1) * (nt + 1)));
+    float* dst = a.m2 + (long long)ul * a.T * kFPad;
+    for (int i = threadIdx.x; i < tt_n * kFPad; i += blockDim.x) {
+        const int tt = i / kFPad, f = i - tt * kFPad;
+        float v = 0.f;
+        if (f < kF) {
+            const float* cr = s_c + tt * cp + f;
+            float acc = 0.f;
+            for (int d = -nf; d <= nf; ++d) acc = fmaf((float)(nf + 1 - (d < 0 ? -d : d)), cr[nf + d], acc);
+            v = fmaf(acc * invD, a.p, a.one_minus_p);           // nonstationary.py:82-84
+        }
+        dst[(long long)(t0 + tt) * kFPad + f] = v;
     }
 }
 

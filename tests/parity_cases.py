@@ -16,6 +16,7 @@ OUT_TOL = 1e-4            # rel-inf on the waveform: max|y - y_ref| / max|y_ref|
 OUT_TOL_TIGHT = 2e-6      # what the FP32 path actually achieves when the mask decisions agree
 SPEC_TOL = 2e-6           # FP32 STFT vs float64, relative to the largest bin
 MASK_TOL = 1e-6           # smoothed mask, absolute (values in [0, 1])
+MASK_TOL_NONSTAT = 2e-5   # sigmoid mask: slope 10 amplifies the FP32 error of (|X| - S) / S
 THRESH_TOL_DB = 1e-3      # our FP64 noise statistics vs the reference's float32-STFT statistics
 
 
@@ -71,5 +72,25 @@ def check_stationary(lib, y, cfg: O.GateConfig, tap_unit=(0, 0), y_noise=None, i
     res["out_relinf"] = relinf(out, ref)
     res["out"] = out
     res["ref"] = ref
+    gate.close()
+    return res
+
+
+def check_nonstationary(lib, y, cfg: O.GateConfig, tap_unit=(0, 0), **extra):
+    y2d = y if y.ndim == 2 else y[None, :]
+    taps = {tap_unit: O.Taps()}
+    ref = O.reduce_noise(y2d, cfg.sr, cfg=cfg, unit_taps=taps, return_float64=True)
+    gate = _cabi.Gate(lib=lib, **gate_params(cfg, **extra))
+    gate.debug_select_unit(*tap_unit)
+    out = gate.run_host(y2d)
+    d = gate.debug_read()
+    tp = taps[tap_unit]
+    res = dict(stats=gate.stats(), T=tp.X.shape[1])
+    res["spec_err"] = float(np.abs(d["X"] - tp.X).max() / np.abs(tp.X).max())
+    touched = d["mask"].any(axis=0)
+    res["mask_frames_checked"] = int(touched.sum())
+    res["mask_err"] = float(np.abs(d["mask"] - tp.mask)[:, touched].max()) if touched.any() else 0.0
+    res["out_dtype_ok"] = out.dtype == y2d.dtype
+    res["out_relinf"] = relinf(out, ref)
     gate.close()
     return res

@@ -100,6 +100,23 @@ def test_int16_and_float64_io(lib):
     assert res["out_dtype_ok"] and res["out_relinf"] < P.OUT_TOL_TIGHT
 
 
+def test_nonstationary_chunked(lib):
+    y = synth_small(C=2, n=12000)
+    cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=5000, padding=600, time_constant_s=0.2)
+    for unit in [(1, 1), (0, 0), (2, 1)]:
+        res = P.check_nonstationary(lib, y, cfg, tap_unit=unit)
+        assert res["spec_err"] < P.SPEC_TOL and res["mask_err"] < P.MASK_TOL_NONSTAT
+        assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5
+    # defaults (2 s time constant, one padded chunk), prop_decrease < 1, no smoothing
+    cfg = O.GateConfig(sr=SR, stationary=False, prop_decrease=0.7)
+    res = P.check_nonstationary(lib, y[:1, :7000], cfg)
+    assert res["mask_err"] < P.MASK_TOL_NONSTAT and res["out_relinf"] < P.OUT_TOL_TIGHT * 5
+    cfg = O.GateConfig(sr=SR, stationary=False, freq_mask_smooth_hz=None, time_mask_smooth_ms=None,
+                       chunk_size=3000, padding=200, thresh_n_mult_nonstationary=1.5, sigmoid_slope_nonstationary=5)
+    res = P.check_nonstationary(lib, y[:1, :7000], cfg, tap_unit=(1, 0))
+    assert res["mask_err"] < P.MASK_TOL_NONSTAT and res["out_relinf"] < P.OUT_TOL_TIGHT * 5
+
+
 def test_python_surface_on_simulator(lib, monkeypatch):
     """reduce_noise() host logic (shapes, dtypes, defaults, errors) with the simulator library."""
     monkeypatch.setattr(_cabi, "_LIB", lib)
@@ -111,6 +128,9 @@ def test_python_surface_on_simulator(lib, monkeypatch):
     assert P.relinf(out, ref) < P.OUT_TOL
     flat = nr.reduce_noise(y=y[0], sr=SR, stationary=True)
     assert flat.shape == (6000,)
+    out = nr.reduce_noise(y=y, sr=SR, chunk_size=2500, padding=400)          # default: non-stationary
+    ref = O.reduce_noise(y, SR, cfg=O.GateConfig(sr=SR, stationary=False, chunk_size=2500, padding=400))
+    assert P.relinf(out, ref) < P.OUT_TOL
     with pytest.raises(ValueError, match="Waveform must be in shape"):
         nr.reduce_noise(y=np.zeros((2, 2, 100), np.float32), sr=SR, stationary=True)
     with pytest.raises(ValueError, match="freq_mask_smooth_hz needs to be at least"):

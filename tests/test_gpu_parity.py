@@ -67,6 +67,32 @@ def test_config2_shaped_chunks_mask_bit_exact(lib):
     assert res["mask0_mismatch"] <= 2          # threshold noise of the reference's float32 noise STFT
 
 
+def test_nonstationary(lib, golden_dir):
+    import noisereduce_b200 as nr
+    y = synth_small(C=2, n=12000)
+    cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=5000, padding=600, time_constant_s=0.2)
+    for unit in [(1, 1), (0, 0), (2, 1)]:
+        res = P.check_nonstationary(lib, y, cfg, tap_unit=unit)
+        assert res["spec_err"] < P.SPEC_TOL and res["mask_err"] < P.MASK_TOL_NONSTAT, res
+        assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5, res
+    # config-3-like geometry at n_fft=1024: 48 kHz, default chunking, 2 s time constant
+    sr = 48000
+    rng = np.random.default_rng(1001)
+    n = 1_300_000
+    t = np.arange(n) / sr
+    yy = (0.05 * rng.standard_normal((2, n)) + 0.25 * ((t % 2.0) < 0.5) * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    cfg = O.GateConfig(sr=sr, stationary=False)
+    res = P.check_nonstationary(lib, yy, cfg, tap_unit=(1, 1))
+    assert res["mask_err"] < P.MASK_TOL_NONSTAT and res["out_relinf"] < P.OUT_TOL_TIGHT * 5, res
+    # golden: reference outputs
+    s = np.load(os.path.join(golden_dir, "synth_small.npz"))
+    out = nr.reduce_noise(y=s["y"], sr=int(s["sr"]), stationary=False, chunk_size=12000, padding=1500)
+    assert P.relinf(out, s["out_nonstat_chunked"]) < P.OUT_TOL
+    f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
+    out = nr.reduce_noise(y=f["y"], sr=int(f["sr"]), stationary=False)
+    assert np.abs(out.astype(np.int32) - f["out_nonstationary"].astype(np.int32)).max() <= 1
+
+
 def test_golden_fish_and_small(lib, golden_dir):
     import noisereduce_b200 as nr
     f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))

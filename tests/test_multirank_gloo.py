@@ -1,0 +1,64 @@
+"""N > 1 path on CPU: world_size 2, gloo, the simulator build standing in for the device.
+
+Checks the only cross-rank dependency of the path -- the reference's channel-order float32 noise
+mean (stationary.py:61-64) chained across ranks -- gives thresholds BIT-EQUAL to a single process
+holding all channels, and that the all-gathered waveform equals the single-process result.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SR = 16000
+KW = dict(chunk_size=2500, padding=400)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    from noisereduce_b200.device import DeviceGate
+    from noisereduce_b200.parallel import sharded_reduce_noise
+    from tests.cusim_util import cusim_library
+    from tests.synth_host import synth_small
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    y = torch.from_numpy(synth_small(C=4, n=6000))
+    cpr = y.shape[0] // world
+    x_local = y[rank * cpr: (rank + 1) * cpr].contiguous()
+    dg = DeviceGate(sr=SR, stationary=True, lib=cusim_library(), **KW)
+    full = sharded_reduce_noise(dg, x_local, rank, world)
+    thr = dg.gate.noise_threshold()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, thr)
+    if rank == 0:
+        np.savez(result_path, full=full.numpy(), thr0=gathered[0], thr1=gathered[1])
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one_process(tmp_path):
+    from noisereduce_b200.device import DeviceGate
+    from tests.cusim_util import cusim_library
+    from tests.synth_host import synth_small
+    cusim_library()                                   # build once, before forking workers
+    result = str(tmp_path / "res.npz")
+    mp.spawn(_worker, args=(2, _free_port(), result), nprocs=2, join=True)
+    r = np.load(result)
+    y = torch.from_numpy(synth_small(C=4, n=6000))
+    dg = DeviceGate(sr=SR, stationary=True, lib=cusim_library(), **KW)
+    dg.noise_stats(y)
+    single = dg.run(y).numpy()
+    thr = dg.gate.noise_threshold()
+    assert np.array_equal(r["thr0"], thr) and np.array_equal(r["thr1"], thr)     # bit-equal thresholds
+    assert np.array_equal(r["full"], single)                                    # identical waveform
