@@ -99,8 +99,17 @@ __device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32
                                                  long long base, long long i1, long long Lp, long long n_total,
                                                  const float* __restrict__ s_wa, int lane, bool va, bool vb) {
     float xr[32 + HR];
+    const long long g0 = i1 + base;
+    const int span = 32 * (32 + HR);
+    if (base >= 0 && base + span <= Lp && g0 >= 0 && g0 + span <= n_total) {
+        // interior of the chunk and of the recording (all but the edge frames): plain coalesced rows
+        const float* p = xrow + g0 + lane;
 #pragma unroll
-    for (int r = 0; r < 32 + HR; ++r) xr[r] = chunk_sample(xrow, base + lane + 32 * r, i1, Lp, n_total);
+        for (int r = 0; r < 32 + HR; ++r) xr[r] = __ldg(p + 32 * r);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 32 + HR; ++r) xr[r] = chunk_sample(xrow, base + lane + 32 * r, i1, Lp, n_total);
+    }
     float e = 0.f;
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
@@ -113,11 +122,36 @@ __device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32
     return e;
 }
 
+// Pull the next frame pair's new samples (2 hops) towards L1 while this pair is being transformed.
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#ifndef B200_CUSIM_BUILD
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+template <int HR>
+__device__ __forceinline__ void prefetch_next_pair(const float* __restrict__ xrow, long long base_next, long long i1,
+                                                   long long Lp, long long n_total, int lane) {
+    // rows 32-HR .. 31+HR of the next pair are the ones this pair has not touched: 2*HR rows of 128 B
+    if (lane < 2 * HR) {
+        const long long j = base_next + 32LL * (32 - HR + lane);
+        const long long gidx = i1 + j;
+        if (j >= 0 && j + 32 <= Lp && gidx >= 0 && gidx + 32 <= n_total) prefetch_l1(xrow + gidx);
+    }
+}
+
+#ifdef B200_CUSIM_BUILD
+#define B200_NOINLINE __attribute__((noinline))
+#else
+#define B200_NOINLINE __noinline__
+#endif
+
 // Exact (float64) re-decision of one bin of one frame: direct DFT of the windowed samples.
 // Warp-cooperative; every lane returns the same value.  2 = above threshold, 1 = not above,
 // 0 = unresolved even in float64 (|P - T^2| <= 1e-12 T^2).
-__device__ __forceinline__ int recheck_bin_fp64(const float* __restrict__ xrow, long long base, long long i1,
-                                                long long Lp, long long n_total, int k, const Tables& tb, int lane) {
+__device__ B200_NOINLINE int recheck_bin_fp64(const float* __restrict__ xrow, long long base, long long i1,
+                                              long long Lp, long long n_total, int k, const Tables& tb, int lane) {
     double sr = 0.0, si = 0.0;
     for (int n = lane; n < kN; n += 32) {
         const double x = (double)chunk_sample(xrow, base + n, i1, Lp, n_total) * tb.wa64[n];
@@ -148,7 +182,7 @@ struct K1Args {
     int n_runs;                // ceil(T / run)
 };
 
-constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats; }
+constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats + kWarps * 2 * kFW + 8; }
 
 template <int HR>
 __global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
@@ -158,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
     float* s_thr4 = smem + 3 * kN;
     float* s_gco = s_thr4 + kFPad;
     float* s_tiles = s_gco + kFPad;
+    unsigned* s_amb_all = reinterpret_cast<unsigned*>(s_tiles + kWarps * kExchFloats);
     for (int i = threadIdx.x; i < kN; i += kThreads) {
         s_wa[i] = a.tb.wa[i];
         s_tw[i] = a.tb.tw[i];
@@ -171,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
     const Geom& g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = s_tiles + warp * kExchFloats;
+    unsigned* s_amb = s_amb_all + warp * 2 * kFW;
     const int H = g.H;
     const int pl = (32 - lane) & 31;                 // partner lane holding the mirrored bins
     const long long n_items = (long long)g.n_units * a.n_runs;
@@ -194,10 +230,12 @@ __global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
             float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, true, vb);
+            if (t + 2 < t1) prefetch_next_pair<HR>(xrow, base + 2LL * H, i1, g.Lp, g.n_total, lane);
             const float S = sqrtf(warp_sum(e));
-            warp_fft1024<false>(re, im, tile, s_tw, lane);
+            warp_fft1024(re, im, tile, s_tw, lane);
 
             unsigned wordA = 0u, wordB = 0u;
+            unsigned anyamb = 0u;
 #pragma unroll
             for (int q = 0; q < kFW; ++q) {
                 const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
@@ -215,39 +253,63 @@ __global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
                 const float th = s_thr4[k];
                 const float gg = fmaf(s_gco[k], S, th * 8.0e-7f);
                 const float dA = PA - th, dB = PB - th;
-                bool bitA = valid && (dA > 0.f);
-                bool bitB = valid && vb && (dB > 0.f);
-                unsigned ambA = __ballot_sync(0xffffffffu, valid && fabsf(dA) <= gg);
-                unsigned ambB = __ballot_sync(0xffffffffu, valid && vb && fabsf(dB) <= gg);
-                if (ambA | ambB) {                    // warp-uniform, rare: redo those bins in float64
-                    unsigned nre = 0, nun = 0;
-                    while (ambA) {
-                        const int src = __ffs((int)ambA) - 1;
-                        ambA &= ambA - 1;
-                        const int r = recheck_bin_fp64(xrow, base, i1, g.Lp, g.n_total, src + 32 * q, a.tb, lane);
-                        ++nre;
-                        if (r == 0) ++nun; else if (lane == src) bitA = (r == 2);
-                    }
-                    while (ambB) {
-                        const int src = __ffs((int)ambB) - 1;
-                        ambB &= ambB - 1;
-                        const int r = recheck_bin_fp64(xrow, base + H, i1, g.Lp, g.n_total, src + 32 * q, a.tb, lane);
-                        ++nre;
-                        if (r == 0) ++nun; else if (lane == src) bitB = (r == 2);
-                    }
-                    if (lane == 0) {
-                        atomicAdd(&a.cnt->rechecked, (unsigned long long)nre);
-                        if (nun) atomicAdd(&a.cnt->unresolved, (unsigned long long)nun);
+                const unsigned wA = __ballot_sync(0xffffffffu, valid && (dA > 0.f));
+                const unsigned wB = __ballot_sync(0xffffffffu, valid && vb && (dB > 0.f));
+                const bool amA = valid && fabsf(dA) <= gg, amB = valid && vb && fabsf(dB) <= gg;
+                if (lane == q) { wordA = wA; wordB = wB; }
+                if (__any_sync(0xffffffffu, amA || amB)) {   // rare: remember the bins inside the guard band
+                    const unsigned mA = __ballot_sync(0xffffffffu, amA);
+                    const unsigned mB = __ballot_sync(0xffffffffu, amB);
+                    anyamb |= 1u << q;
+                    if (lane == 0) { s_amb[2 * q] = mA; s_amb[2 * q + 1] = mB; }
+                }
+                if (valid) mx[q] = fmaxf(mx[q], vb ? fmaxf(PA, PB) : PA);
+            }
+            if (a.dbg.ul == ul) {                            // parity tap (tests): the FP32 STFT itself
+#pragma unroll 1
+                for (int q = 0; q < kFW; ++q) {
+                    float zr = 0.f, zi = 0.f, pr = 0.f, pi = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < kFW; ++qq)
+                        if (qq == q) {
+                            zr = re[brev5(qq)]; zi = im[brev5(qq)];
+                            pr = __shfl_sync(0xffffffffu, re[brev5(31 - qq)], pl);
+                            pi = __shfl_sync(0xffffffffu, im[brev5(31 - qq)], pl);
+                            if (lane == 0) { pr = re[brev5((32 - qq) & 31)]; pi = im[brev5((32 - qq) & 31)]; }
+                        }
+                    const int k = lane + 32 * q;
+                    if (((q < 16) || lane == 0) && k < kF) {
+                        float* sp = a.dbg.spec + ((long long)t * kF + k) * 2;
+                        sp[0] = 0.5f * (zr + pr); sp[1] = 0.5f * (zi - pi);
+                        if (vb) { sp[2 * kF] = 0.5f * (zi + pi); sp[2 * kF + 1] = 0.5f * (pr - zr); }
                     }
                 }
-                const unsigned wA = __ballot_sync(0xffffffffu, bitA);
-                const unsigned wB = __ballot_sync(0xffffffffu, bitB);
-                if (lane == q) { wordA = wA; wordB = wB; }
-                if (valid) mx[q] = fmaxf(mx[q], vb ? fmaxf(PA, PB) : PA);
-                if (a.dbg.ul == ul && valid && k < kF) {     // parity tap: the FP32 STFT itself
-                    float* sp = a.dbg.spec + ((long long)t * kF + k) * 2;
-                    sp[0] = 0.5f * ar; sp[1] = 0.5f * ai;
-                    if (vb) { sp[2 * kF] = 0.5f * br; sp[2 * kF + 1] = 0.5f * bi; }
+            }
+            if (anyamb) {                             // warp-uniform, rare: redo those bins in float64
+                __syncwarp();
+                unsigned nre = 0, nun = 0;
+                for (int q = 0; q < kFW; ++q) {
+                    if (!((anyamb >> q) & 1u)) continue;
+                    for (int fr = 0; fr < 2; ++fr) {
+                        unsigned m = s_amb[2 * q + fr];
+                        while (m) {
+                            const int src = __ffs((int)m) - 1;
+                            m &= m - 1;
+                            const int r = recheck_bin_fp64(xrow, base + (long long)fr * H, i1, g.Lp, g.n_total,
+                                                           src + 32 * q, a.tb, lane);
+                            ++nre;
+                            if (r == 0) { ++nun; continue; }
+                            if (lane == q) {
+                                unsigned& wd = fr ? wordB : wordA;
+                                wd = (r == 2) ? (wd | (1u << src)) : (wd & ~(1u << src));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    atomicAdd(&a.cnt->rechecked, (unsigned long long)nre);
+                    if (nun) atomicAdd(&a.cnt->unresolved, (unsigned long long)nun);
                 }
             }
             if (lane < kFW) {
@@ -452,68 +514,115 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                 const long long base = (long long)t * H - kN / 2;
                 float re[32], im[32];
                 load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, va, vb);
-                warp_fft1024<false>(re, im, tile, s_tw, lane);
-
+                if (t + 2 <= t_last) prefetch_next_pair<HR>(xrow, base + 2LL * H, i1, g.Lp, g.n_total, lane);
                 const long long offA = (long long)t * kFPad, offB = (long long)(vb ? t + 1 : t) * kFPad;
                 float eta = 0.f, etb = 0.f;
                 if (!FMASK && blend) {
                     eta = a.one_minus_p * time_edge(t, g.T, a.nt);
                     etb = a.one_minus_p * time_edge(t + 1, g.T, a.nt);
                 }
-#pragma unroll
-                for (int q = 0; q < kFW; ++q) {
-                    const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
-                    const int k = lane + 32 * q;                 // < FPad, rows are padded
-                    float ma, mb;
-                    if (FMASK) {
-                        ma = frow[offA + k];
-                        mb = frow[offB + k];
-                    } else {
-                        ma = fmaf((float)mrow[offA + k], a.pD, eta * s_ef[k]);
-                        mb = fmaf((float)mrow[offB + k], a.pD, etb * s_ef[k]);
-                    }
-                    if (!vb) mb = 0.f;
-                    if (a.dbg.ul == ul && k < kF && ((q < 16) || lane == 0)) {
+                if (a.dbg.ul == ul) {                        // parity tap (tests): the masks this pair applies
+#pragma unroll 1
+                    for (int k = lane; k < kF; k += 32) {
+                        float ma, mb;
+                        if (FMASK) {
+                            ma = frow[offA + k];
+                            mb = frow[offB + k];
+                        } else {
+                            ma = fmaf((float)mrow[offA + k], a.pD, eta * s_ef[k]);
+                            mb = fmaf((float)mrow[offB + k], a.pD, etb * s_ef[k]);
+                        }
                         a.dbg.mask[(long long)t * kF + k] = ma;
                         if (vb) a.dbg.mask[(long long)(t + 1) * kF + k] = mb;
                     }
-                    const float s = 0.5f * (ma + mb), d = 0.5f * (ma - mb);
-                    const float zr = re[sA], zi = im[sA];
-                    if (q < 16) {
-                        float pr = __shfl_sync(0xffffffffu, re[sP], pl);
-                        float pi = __shfl_sync(0xffffffffu, im[sP], pl);
-                        if (lane == 0) { pr = re[s0]; pi = im[s0]; }
-                        // Z'[k] = s Z[k] + d conj(Z[N-k]);  Z'[N-k] = s Z[N-k] + d conj(Z[k])
-                        const float own_r = fmaf(d, pr, s * zr), own_i = fmaf(-d, pi, s * zi);
-                        const float oth_r = fmaf(d, zr, s * pr), oth_i = fmaf(-d, zi, s * pi);
-                        const float nr = __shfl_sync(0xffffffffu, oth_r, pl);
-                        const float ni = __shfl_sync(0xffffffffu, oth_i, pl);
-                        re[sA] = own_r;
-                        im[sA] = own_i;
-                        if (lane != 0) { re[sP] = nr; im[sP] = ni; }
-                        else if (q != 0) { re[s0] = oth_r; im[s0] = oth_i; }
-                    } else if (lane == 0) {                      // bin N/2 mirrors onto itself
-                        re[sA] = fmaf(d, zr, s * zr);
-                        im[sA] = fmaf(-d, zi, s * zi);
+                }
+                // phase 0: forward FFT + mask apply; phase 1: inverse FFT.  One copy of the FFT code
+                // serves both: the apply step leaves Z' with real/imaginary parts exchanged and in
+                // natural slot order, so ifft(Z') = swap(fft(swap(Z'))) is the very same call.
+#pragma unroll 1
+                for (int ph = 0; ph < 2; ++ph) {
+                    warp_fft1024(re, im, tile, s_tw, lane);
+                    if (ph == 0) {
+#pragma unroll
+                        for (int q = 0; q < kFW; ++q) {
+                            const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
+                            const int k = lane + 32 * q;                 // < FPad, rows are padded
+                            float ma, mb;
+                            if (FMASK) {
+                                ma = frow[offA + k];
+                                mb = frow[offB + k];
+                            } else {
+                                ma = fmaf((float)mrow[offA + k], a.pD, eta * s_ef[k]);
+                                mb = fmaf((float)mrow[offB + k], a.pD, etb * s_ef[k]);
+                            }
+                            if (!vb) mb = 0.f;
+                            const float s = 0.5f * (ma + mb), d = 0.5f * (ma - mb);
+                            const float zr = re[sA], zi = im[sA];
+                            if (q < 16) {
+                                float pr = __shfl_sync(0xffffffffu, re[sP], pl);
+                                float pi = __shfl_sync(0xffffffffu, im[sP], pl);
+                                if (lane == 0) { pr = re[s0]; pi = im[s0]; }
+                                // Z'[k] = s Z[k] + d conj(Z[N-k]);  Z'[N-k] = s Z[N-k] + d conj(Z[k])
+                                const float own_r = fmaf(d, pr, s * zr), own_i = fmaf(-d, pi, s * zi);
+                                const float oth_r = fmaf(d, zr, s * pr), oth_i = fmaf(-d, zi, s * pi);
+                                const float nr = __shfl_sync(0xffffffffu, oth_r, pl);
+                                const float ni = __shfl_sync(0xffffffffu, oth_i, pl);
+                                re[sA] = own_r;
+                                im[sA] = own_i;
+                                if (lane != 0) { re[sP] = nr; im[sP] = ni; }
+                                else if (q != 0) { re[s0] = oth_r; im[s0] = oth_i; }
+                            } else if (lane == 0) {                      // bin N/2 mirrors onto itself
+                                re[sA] = fmaf(d, zr, s * zr);
+                                im[sA] = fmaf(-d, zi, s * zi);
+                            }
+                        }
+                        // brev slots -> natural slots with re <-> im exchanged, in place (2-cycles of brev5)
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            const int b = brev5(q);
+                            if (b == q) {
+                                const float tr = re[q];
+                                re[q] = im[q];
+                                im[q] = tr;
+                            } else if (q < b) {
+                                const float t1 = re[q], t2 = im[q];
+                                re[q] = im[b];
+                                im[q] = re[b];
+                                re[b] = t2;
+                                im[b] = t1;
+                            }
+                        }
                     }
                 }
-                // inverse FFT by the swap trick; afterwards re = N a'[n], im = N b'[n] at slot brev5(q)
-                warp_fft1024<true>(im, re, tile, s_tw, lane);
+                // now im = N a'[n], re = N b'[n] (n = lane + 32 q) at slot brev5(q)
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const float w = s_ws[lane + 32 * q];
-                    acc[q] = fmaf(re[brev5(q)], w, acc[q]);
-                    acc[q + HR] = fmaf(im[brev5(q)], w, acc[q + HR]);
+                    acc[q] = fmaf(im[brev5(q)], w, acc[q]);
+                    acc[q + HR] = fmaf(re[brev5(q)], w, acc[q + HR]);
                 }
             }
             // hops t and t+1 are now complete (all frames <= t+1 have been added)
+            {
+                const long long jp0 = (long long)t * H - kN / 2;             // chunk-local index of row 0, lane 0
+                if (t >= hs && t + 1 < he && t >= NH - 1 && t + 1 <= g.T - 1 && jp0 >= g.pad &&
+                    jp0 + 2 * H <= jp_hi) {
+                    // both hops interior and fully inside the chunk centre: 2*HR coalesced row stores
+                    float* dst = yrow + i1 + jp0 + lane;
 #pragma unroll
-            for (int r = 0; r < 2 * HR; ++r) {
-                const int hop = t + r / HR;
-                if (hop >= hs && hop < he) {
-                    const int ro = (r % HR) * 32 + lane;
-                    const long long jp = (long long)hop * H + ro - kN / 2;       // chunk-local output index
-                    if (jp >= g.pad && jp < jp_hi) {
+                    for (int r = 0; r < 2 * HR; ++r) dst[32 * r] = acc[r] * s_invn[(r % HR) * 32 + lane];
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < 2 * HR; ++r) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 2 * HR; ++rr)
+                            if (rr == r) v = acc[rr];
+                        const int hop = t + r / HR;
+                        if (hop < hs || hop >= he) continue;
+                        const int ro = (r % HR) * 32 + lane;
+                        const long long jp = (long long)hop * H + ro - kN / 2;   // chunk-local output index
+                        if (jp < g.pad || jp >= jp_hi) continue;
                         float inv;
                         if (hop >= NH - 1 && hop <= g.T - 1) {
                             inv = s_invn[ro];
@@ -528,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                             }
                             inv = nrm > 1e-10f ? 1.0f / nrm : 1.0f;
                         }
-                        yrow[i1 + jp] = acc[r] * inv;
+                        yrow[i1 + jp] = v * inv;
                     }
                 }
             }
@@ -592,7 +701,8 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
             load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, true, vb);
-            warp_fft1024<false>(re, im, tile, s_tw, lane);
+            if (t + 2 < t1) prefetch_next_pair<HR>(xrow, base + 2LL * H, i1, g.Lp, g.n_total, lane);
+            warp_fft1024(re, im, tile, s_tw, lane);
             float* dstA = a.mag + ((long long)ul * g.T + t) * kFPad;
 #pragma unroll
             for (int q = 0; q < kFW; ++q) {

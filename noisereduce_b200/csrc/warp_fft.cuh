@@ -125,15 +125,17 @@ __device__ __forceinline__ void twiddle_transpose(float (&re)[32], float (&im)[3
     __syncwarp();
 }
 
-// Forward 1024-point FFT.  IN_BREV == false: input point lane+32r in slot r.
-//                          IN_BREV == true : input point lane+32r in slot brev5(r).
-// Output: X[lane + 32 q] in slot brev5(q).
-template <bool IN_BREV>
+// Forward 1024-point FFT: input point lane+32r in slot r, output X[lane + 32 q] in slot brev5(q).
+// Both radix-32 passes run through ONE copy of the butterfly network (a 2-trip runtime loop): the
+// kernels are instruction-fetch sensitive (each warp walks its own instruction stream), so code
+// size matters more than the two saved branches.
 __device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], float* __restrict__ tile,
                                              const float2* __restrict__ tw, int lane) {
-    dft32<IN_BREV>(re, im);                               // -> brev slots (false) / natural (true)
-    twiddle_transpose<!IN_BREV>(re, im, tile, tw, lane);
-    dft32<false>(re, im);                                 // natural in -> brev out
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        dft32<false>(re, im);                                         // natural slots -> brev slots
+        if (pass == 0) twiddle_transpose<true>(re, im, tile, tw, lane);   // brev slots -> natural slots
+    }
 }
 
 }  // namespace b200
