@@ -293,7 +293,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaFuncSetAttribute(k2_synthesize<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
         cudaFuncSetAttribute(k1n_magnitude<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
         cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_smooth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 #endif
     }
     if (rc != B200GATE_OK) {
@@ -615,8 +615,31 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 SmoothArgs sa{};
                 sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
                 sa.bits = d_bits; sa.rowflag = d_rowflag; sa.num = d_num;
-                const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                B200_LAUNCH(k_smooth, dim3(tiles, nu), dim3(256), smooth_smem_bytes(sa.TT, nf, nt), st, sa);
+                const int ntaps = 2 * nf + 1;
+                if (nt + 1 <= 14 && ntaps <= 36) {
+                    SmoothPArgs pa{};
+                    pa.n_units = nu; pa.T = g.T; pa.nf = nf; pa.nt = nt; pa.tf_lo = tf_lo; pa.tf_hi = tf_hi;
+                    pa.bits = d_bits; pa.rowflag = d_rowflag; pa.num = d_num;
+                    unsigned char tb8[36] = {0};
+                    for (int d = -nf; d <= nf; ++d) tb8[d + nf] = (unsigned char)(nf + 1 - abs(d));
+                    memcpy(pa.taps, tb8, 36);
+                    // strips: enough CTAs to fill the machine, long enough to amortise the 2 nt warm-up frames
+                    const int groups = (nu + kSmoothUnits - 1) / kSmoothUnits;
+                    int n_strips = std::max(1, std::min((tf_hi - tf_lo + 127) / 128, (h->num_sm * 4 + groups - 1) / groups));
+                    pa.strip = (tf_hi - tf_lo + n_strips - 1) / n_strips;
+                    n_strips = (tf_hi - tf_lo + pa.strip - 1) / pa.strip;
+                    const dim3 grid(n_strips, groups);
+                    if (ntaps <= 12) {
+                        B200_LAUNCH(k_smooth_packed<3>, grid, dim3(kSmoothThreads), smoothp_smem_bytes<3>(), st, pa);
+                    } else if (ntaps <= 24) {
+                        B200_LAUNCH(k_smooth_packed<6>, grid, dim3(kSmoothThreads), smoothp_smem_bytes<6>(), st, pa);
+                    } else {
+                        B200_LAUNCH(k_smooth_packed<9>, grid, dim3(kSmoothThreads), smoothp_smem_bytes<9>(), st, pa);
+                    }
+                } else {
+                    const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                    B200_LAUNCH(k_smooth_generic, dim3(tiles, nu), dim3(256), smooth_smem_bytes(sa.TT, nf, nt), st, sa);
+                }
                 cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                 K2Args a2{};
                 a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.num = d_num;

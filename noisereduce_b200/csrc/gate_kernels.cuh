@@ -371,7 +371,7 @@ inline size_t smooth_smem_bytes(int TT, int nf, int nt) {
     return (size_t)smooth_rows(TT, nt) * kFW * 4 + (size_t)TT * smooth_cpitch(nf) * 2 + 16;
 }
 
-__global__ void __launch_bounds__(256) k_smooth(const SmoothArgs a) {
+__global__ void __launch_bounds__(256) k_smooth_generic(const SmoothArgs a) {
     B200_DYN_SMEM(unsigned, smem);
     const int nt = a.nt, nf = a.nf, aa = nt + 1;
     const int rows = smooth_rows(a.TT, nt);
@@ -420,6 +420,111 @@ __global__ void __launch_bounds__(256) k_smooth(const SmoothArgs a) {
             for (int d = -nf; d <= nf; ++d) acc += (nf + 1 - (d < 0 ? -d : d)) * (int)cr[nf + d];
         }
         a.num[((long long)ul * a.T + t0 + tt) * kFPad + f] = (unsigned short)acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed variant (the one that normally runs).  A thread owns 4 consecutive bins as byte lanes of
+// one register and streams over time: the time-direction recurrence costs ~4 ops/bin, and the
+// frequency-direction triangle is NTW dp4a dot products per output against byte windows of the
+// shared row.  Requirements: nt + 1 <= 14 (byte lanes: counts <= 196, biased first difference
+// <= 31) and 2 nf + 1 <= 4 NTW; otherwise the host falls back to k_smooth_generic.
+// CTA = 544 threads = 4 units x 136 bin-groups; one __syncthreads per frame.
+// ---------------------------------------------------------------------------------------------
+struct SmoothPArgs {
+    int n_units, T;
+    int nf, nt;
+    int tf_lo, tf_hi;
+    int strip;                 // output frames per CTA
+    const unsigned* bits;
+    const unsigned* rowflag;
+    unsigned short* num;
+    unsigned taps[9];          // triangle taps nf+1-|d|, d = -nf..nf, as packed bytes (zero padded)
+};
+constexpr int kSmoothGroups = kFPad / 4;          // 136 threads per unit
+constexpr int kSmoothUnits = 4;
+constexpr int kSmoothThreads = kSmoothGroups * kSmoothUnits;   // 544
+template <int NTW> __host__ __device__ constexpr int smoothp_rowbytes() { return kFPad + 4 * (NTW + 2) + 64; }
+template <int NTW> __host__ __device__ constexpr int smoothp_smem_bytes() { return 2 * kSmoothUnits * smoothp_rowbytes<NTW>(); }
+
+__device__ __forceinline__ unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
+#ifdef B200_CUSIM_BUILD
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xFFu) * ((b >> (8 * i)) & 0xFFu);
+    return c;
+#else
+    return __dp4a(a, b, c);
+#endif
+}
+
+template <int NTW>
+__global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPArgs a) {
+    constexpr int RB = smoothp_rowbytes<NTW>();
+    B200_DYN_SMEM(unsigned char, s_raw);                      // [2][4][RB]
+    const int tid = threadIdx.x;
+    const int ug = tid / kSmoothGroups, i = tid - ug * kSmoothGroups;
+    const int ul = blockIdx.y * kSmoothUnits + ug;
+    const bool active = ul < a.n_units;
+    const int t_begin = a.tf_lo + blockIdx.x * a.strip;
+    if (t_begin >= a.tf_hi) return;
+    const int t_end = min(t_begin + a.strip, a.tf_hi);
+    const int nt = a.nt, nf = a.nf, aa = nt + 1;
+    for (int k = tid; k < 2 * kSmoothUnits * RB / 4; k += kSmoothThreads) reinterpret_cast<unsigned*>(s_raw)[k] = 0u;
+    __syncthreads();
+
+    const int w = i >> 3, sh = (i & 7) * 4;
+    const unsigned fl = active ? ((a.rowflag[ul * kFW + w] >> sh) & 0xFu) : 0u;
+    const unsigned* bp = a.bits + (long long)(active ? ul : 0) * a.T * kFW + w;
+    unsigned short* outp = a.num + (long long)(active ? ul : 0) * a.T * kFPad + 4 * i;
+    unsigned taps[NTW];
+#pragma unroll
+    for (int m = 0; m < NTW; ++m) taps[m] = a.taps[m];
+
+    const int tau_s = t_begin - nt;                 // first frame fed into the recurrence
+    unsigned d1b = 0x10101010u, s2 = 0u;
+    int par = 0;
+    for (int tau = tau_s; tau <= t_end - 1 + nt; ++tau) {
+        unsigned na = 0u, nb = 0u, nc = 0u;
+        if (active) {
+            const int ta = tau, tb = tau - aa, tc = tau - 2 * aa;
+            if (ta >= 0 && ta < a.T) na = ((__ldg(bp + (long long)ta * kFW) >> sh) & 0xFu) | fl;
+            if (tb >= tau_s && tb >= 0 && tb < a.T) nb = ((__ldg(bp + (long long)tb * kFW) >> sh) & 0xFu) | fl;
+            if (tc >= tau_s && tc >= 0 && tc < a.T) nc = ((__ldg(bp + (long long)tc * kFW) >> sh) & 0xFu) | fl;
+        }
+        const unsigned ea = (na * 0x00204081u) & 0x01010101u;
+        const unsigned eb = (nb * 0x00204081u) & 0x01010101u;
+        const unsigned ec = (nc * 0x00204081u) & 0x01010101u;
+        d1b = d1b + ea + ec - 2u * eb;
+        s2 = s2 + d1b - 0x10101010u;
+        const int t_out = tau - nt;
+        if (t_out < t_begin) continue;              // CTA-uniform
+        unsigned char* row = s_raw + (par * kSmoothUnits + ug) * RB;
+        row[nf + 4 * i + 0] = (unsigned char)(s2 & 0xFFu);
+        row[nf + 4 * i + 1] = (unsigned char)((s2 >> 8) & 0xFFu);
+        row[nf + 4 * i + 2] = (unsigned char)((s2 >> 16) & 0xFFu);
+        row[nf + 4 * i + 3] = (unsigned char)(s2 >> 24);
+        __syncthreads();
+        const unsigned* rw = reinterpret_cast<const unsigned*>(row) + i;
+        unsigned wv[NTW + 1];
+#pragma unroll
+        for (int m = 0; m <= NTW; ++m) wv[m] = rw[m];
+        unsigned o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned acc = 0u;
+#pragma unroll
+            for (int m = 0; m < NTW; ++m) {
+                const unsigned win = (j == 0) ? wv[m] : __funnelshift_r(wv[m], wv[m + 1], 8 * j);
+                acc = dp4a_u(win, taps[m], acc);
+            }
+            o[j] = acc;
+        }
+        if (active) {
+            uint2 pk;
+            pk.x = o[0] | (o[1] << 16);
+            pk.y = o[2] | (o[3] << 16);
+            *reinterpret_cast<uint2*>(outp + (long long)t_out * kFPad) = pk;
+        }
+        par ^= 1;
     }
 }
 

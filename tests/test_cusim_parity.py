@@ -69,6 +69,16 @@ def test_stationary_no_smoothing_and_tiny_padding(lib):
     _assert_stationary(P.check_stationary(lib, y, cfg, tap_unit=(2, 0)))
 
 
+def test_smoothing_kernel_variants(lib):
+    """packed dp4a kernel with 3 / 6 / 9 tap words, and the generic fallback for long time extents."""
+    y = synth_small(C=1, n=7000)
+    for hz, ms in [(100, 50), (300, 100), (500, 200), (200, 250)]:    # nf = 3, 9, 16, 6; nt = 3, 6, 12, 15
+        cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=3000, padding=500, freq_mask_smooth_hz=hz,
+                           time_mask_smooth_ms=ms, prop_decrease=0.9)
+        res = P.check_stationary(lib, y, cfg, tap_unit=(1, 0))
+        _assert_stationary(res)
+
+
 def test_fp64_redecision_path_gives_same_bits(lib):
     y = synth_small(C=1, n=5000)
     cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=None, padding=300)
