@@ -536,16 +536,25 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
+    // carve the workspace into 256-byte aligned sub-buffers (vector stores need natural alignment)
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t off_bits = 0;
+    const size_t off_rowmax = off_bits + al((size_t)ub * g.T * kFW * 4);
+    const size_t off_rowflag = off_rowmax + al((size_t)ub * kFPad * 4);
+    const size_t off_num = off_rowflag + al((size_t)ub * kFW * 4);
+    const size_t end_stat = off_num + al((size_t)ub * g.T * kFPad * 2);
+    const size_t off_m0 = al((size_t)ub * g.T * kFPad * 4);
+    const size_t end_nonstat = off_m0 + al((size_t)ub * g.T * kFPad * 4);
     {
-        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, per_unit * (size_t)ub);
+        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, stat ? end_stat : end_nonstat);
         if (rc) return rc;
     }
-    unsigned* d_bits = (unsigned*)h->d_ws_buf;
-    unsigned* d_rowmax = d_bits + (size_t)ub * g.T * kFW;
-    unsigned* d_rowflag = d_rowmax + (size_t)ub * kFPad;
-    unsigned short* d_num = (unsigned short*)(d_rowflag + (size_t)ub * kFW);
+    unsigned* d_bits = (unsigned*)(h->d_ws_buf + off_bits);
+    unsigned* d_rowmax = (unsigned*)(h->d_ws_buf + off_rowmax);
+    unsigned* d_rowflag = (unsigned*)(h->d_ws_buf + off_rowflag);
+    unsigned short* d_num = (unsigned short*)(h->d_ws_buf + off_num);
     float* d_mag = (float*)h->d_ws_buf;                        // non-stationary: |X|, later the final mask
-    float* d_m0 = d_mag + (size_t)ub * g.T * kFPad;            //                 forward sweep / sigmoid mask
+    float* d_m0 = (float*)(h->d_ws_buf + off_m0);              //                 forward sweep / sigmoid mask
 
     CK(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), st));
     const long long dbg_u = (h->dbg_chunk >= 0 && h->dbg_chunk < g.n_chunks && h->dbg_channel >= 0 && h->dbg_channel < C)
