@@ -114,6 +114,10 @@ int b200gate_get_noise_mean_std(const b200gate_handle* h, double* mean_db, doubl
 /* Torch surface only: install the analysis/synthesis window the caller built with
  * torch.hann_window (float32, win_length values), so tables match the reference bit for bit. */
 int b200gate_set_window(b200gate_handle* h, const float* window, int32_t win_length);
+/* Torch surface only: thresholds from a noise clip xn [Bn][Ln] (float32; Bn == 1 or Bn == batch), as
+ * TorchGate.forward(x, xn) (torchgate.py:140-164).  xn == NULL returns to self-statistics. */
+int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int64_t Bn, int64_t Ln,
+                             int64_t stride, int is_device, void* cuda_stream);
 
 /* The operator.  in/out: [C][N] samples of `dtype` with row strides in elements; host or device
  * pointers (is_device).  out may not alias in.  For the torch surface out holds [C][(N/hop)*hop].

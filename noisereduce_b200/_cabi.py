@@ -24,6 +24,7 @@ EXPORTS = [
     "b200gate_create", "b200gate_destroy", "b200gate_last_error", "b200gate_noise_stats",
     "b200gate_noise_stats_collapsed", "b200gate_channel_sum", "b200gate_set_noise_threshold",
     "b200gate_get_noise_threshold", "b200gate_get_noise_mean_std", "b200gate_set_window",
+    "b200gate_torch_set_noise",
     "b200gate_run", "b200gate_get_stats", "b200gate_debug_select_unit", "b200gate_debug_dims",
     "b200gate_debug_read_bits", "b200gate_debug_read_mask", "b200gate_debug_read_spec",
 ]
@@ -87,6 +88,7 @@ class GateLibrary:
         d.b200gate_get_noise_threshold.argtypes = [vp, C.POINTER(dbl), i32]
         d.b200gate_get_noise_mean_std.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), i32]
         d.b200gate_set_window.argtypes = [vp, C.POINTER(C.c_float), i32]
+        d.b200gate_torch_set_noise.argtypes = [vp, vp, C.c_int, i64, i64, i64, C.c_int, vp]
         d.b200gate_run.argtypes = [vp, vp, vp, C.c_int, i64, i64, i64, i64, C.c_int, vp]
         d.b200gate_get_stats.argtypes = [vp, C.POINTER(Stats)]
         d.b200gate_debug_select_unit.argtypes = [vp, i64, i64]
@@ -162,6 +164,13 @@ class Gate:
 
     def noise_stats_collapsed_device(self, ptr, dtype, n, stream=None):
         self._check(self.lib.dll.b200gate_noise_stats_collapsed(self._h, ptr, dtype_code(dtype), n, 1, stream))
+
+    def set_window(self, window_f32):
+        w = np.ascontiguousarray(window_f32, dtype=np.float32)
+        self._check(self.lib.dll.b200gate_set_window(self._h, w.ctypes.data_as(C.POINTER(C.c_float)), w.shape[0]))
+
+    def torch_set_noise(self, ptr, Bn, Ln, stride, is_device=True, stream=None):
+        self._check(self.lib.dll.b200gate_torch_set_noise(self._h, ptr, F32, Bn, Ln, stride, 1 if is_device else 0, stream))
 
     def set_noise_threshold(self, thresh_db):
         t = np.ascontiguousarray(thresh_db, dtype=np.float64)

@@ -38,6 +38,10 @@ struct b200gate_handle {
     double *d_thr2_64 = nullptr, *d_wa64 = nullptr;
     double2* d_cs64 = nullptr;
     float ws_to_w = 0.f;
+    double sum_w = 0.0;
+    std::vector<float> user_window;                // torch surface: torch.hann_window values
+    float* d_tthr = nullptr;                       // torch surface: thresholds from xn, [tthr_units][FPad]
+    int tthr_units = 0;
     bool have_thresh = false;
     std::vector<double> thr, mean, sd;
     // workspace
@@ -103,9 +107,11 @@ int build_static_tables(b200gate_handle* h) {
     std::vector<double> w(N);
     double sw = 0.0;
     for (int n = 0; n < N; ++n) {
-        w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)N);    // periodic Hann (scipy 'hann', fftbins)
+        if ((int)h->user_window.size() == N) w[n] = (double)h->user_window[n];   // torch.hann_window (float32)
+        else w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)N);         // periodic Hann (scipy 'hann', fftbins)
         sw += w[n];
     }
+    h->sum_w = sw;
     std::vector<float> wa(N), ws(N), invn(H);
     std::vector<double> wa64(N);
     for (int n = 0; n < N; ++n) {
@@ -244,6 +250,20 @@ int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, 
     return B200GATE_OK;
 }
 
+void launch_k1n(const Geom& g, const Tables& tb, const float* x, float* mag, const DebugTap& dbg, int resident,
+                cudaStream_t st) {
+    K1nArgs a1{};
+    a1.g = g; a1.tb = tb; a1.x = x; a1.mag = mag; a1.dbg = dbg;
+    long long want = (long long)resident * kWarps * 4;
+    long long run = ((long long)g.n_units * g.T + want - 1) / want;
+    run = std::max(8LL, std::min(64LL, run));
+    run += run & 1;
+    a1.run = (int)run;
+    a1.n_runs = (g.T + a1.run - 1) / a1.run;
+    B200_LAUNCH(k1n_magnitude<8>, dim3(grid_1d((long long)g.n_units * a1.n_runs, kWarps, resident)), dim3(kThreads),
+                k1n_smem_floats() * 4, st, a1);
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -254,8 +274,8 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     *out = nullptr;
     if (p->abi_version != B200GATE_ABI_VERSION)
         return fail(nullptr, B200GATE_ERR_ARG, "ABI version %d, library is %d", p->abi_version, B200GATE_ABI_VERSION);
-    if (p->surface != B200GATE_SURFACE_NUMPY)
-        return fail(nullptr, B200GATE_ERR_ARG, "surface %d is not built into this library yet", p->surface);
+    if (p->surface != B200GATE_SURFACE_NUMPY && p->surface != B200GATE_SURFACE_TORCH)
+        return fail(nullptr, B200GATE_ERR_ARG, "unknown surface %d", p->surface);
     if (p->n_fft != kN || p->win_length != p->n_fft || p->hop_length * 4 != p->n_fft)
         return fail(nullptr, B200GATE_ERR_ARG,
                     "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d: this build runs "
@@ -308,7 +328,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
 void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
-                    h->d_wa64, h->d_cs64, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
+                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
                     h->d_dbg_mask, h->d_dbg_bits};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -342,8 +362,11 @@ int b200gate_get_noise_mean_std(const b200gate_handle* h, double* mean_db, doubl
     return B200GATE_OK;
 }
 
-int b200gate_set_window(b200gate_handle* h, const float*, int32_t) {
-    return fail(h, B200GATE_ERR_ARG, "b200gate_set_window: torch surface not built yet");
+int b200gate_set_window(b200gate_handle* h, const float* window, int32_t win_length) {
+    if (!h || !window) return B200GATE_ERR_ARG;
+    if (win_length != h->p.n_fft) return fail(h, B200GATE_ERR_ARG, "window length %d != n_fft %d", win_length, h->p.n_fft);
+    h->user_window.assign(window, window + win_length);
+    return build_static_tables(h);
 }
 
 int b200gate_channel_sum(b200gate_handle* h, const void* y, int dtype, int64_t C, int64_t n, int64_t stride,
@@ -441,11 +464,54 @@ int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out) {
     return B200GATE_OK;
 }
 
+int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int64_t Bn, int64_t Ln, int64_t stride,
+                             int is_device, void* stream) {
+    if (!h) return B200GATE_ERR_ARG;
+    if (h->p.surface != B200GATE_SURFACE_TORCH) return fail(h, B200GATE_ERR_STATE, "torch surface only");
+    if (!xn) { h->tthr_units = 0; return B200GATE_OK; }
+    if (Bn <= 0 || Ln <= 0 || dtype != B200GATE_F32) return fail(h, B200GATE_ERR_ARG, "xn must be float32 [Bn][Ln]");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* x = (const float*)xn;
+    float* tmp = nullptr;
+    long long xs = stride;
+    if (!is_device) {
+        CK(h, cudaMalloc((void**)&tmp, (size_t)Bn * Ln * 4));
+        CK(h, cudaMemcpy2DAsync(tmp, (size_t)Ln * 4, xn, (size_t)stride * 4, (size_t)Ln * 4, (size_t)Bn, cudaMemcpyHostToDevice, st));
+        x = tmp; xs = Ln;
+    }
+    Geom g{};
+    g.H = h->p.hop_length; g.C = (int)Bn; g.n_total = Ln; g.step = Ln; g.n_chunks = 1; g.pad = 0; g.Lp = Ln;
+    g.T = (int)(Ln / g.H) + 1; g.in_stride = xs; g.out_stride = xs; g.u0 = 0; g.n_units = (int)Bn;
+    float *mag = nullptr, *rowmax = nullptr;
+    CK(h, cudaMalloc((void**)&mag, (size_t)Bn * g.T * kFPad * 4));
+    CK(h, cudaMalloc((void**)&rowmax, (size_t)Bn * kFPad * 4));
+    if (h->d_tthr) cudaFree(h->d_tthr);
+    h->d_tthr = nullptr;
+    CK(h, cudaMalloc((void**)&h->d_tthr, (size_t)Bn * kFPad * 4));
+    DebugTap dbg{}; dbg.ul = -1;
+    launch_k1n(g, device_tables(h), x, mag, dbg, h->num_sm * 3, st);
+    TStatArgs ta{};
+    ta.n_units = (int)Bn; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64; ta.top_db = (float)h->p.top_db;
+    ta.n_std = (float)h->p.n_std_thresh; ta.ddof = h->p.std_ddof; ta.mag = mag; ta.rowmax = rowmax; ta.thr = h->d_tthr;
+    B200_LAUNCH(k_tgate_stats, dim3(grid_1d(Bn * kFPad, 128, 1 << 30)), dim3(128), 0, st, ta);
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(st));
+    cudaFree(mag); cudaFree(rowmax);
+    if (tmp) cudaFree(tmp);
+    h->tthr_units = (int)Bn;
+    return B200GATE_OK;
+}
+
 int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64_t C, int64_t N, int64_t in_stride,
                  int64_t out_stride, int is_device, void* stream) {
     if (!h || !in || !out || C <= 0 || N <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
-    if (in_stride < N || out_stride < N) return fail(h, B200GATE_ERR_ARG, "row strides must be >= N");
-    if (h->p.stationary && !h->have_thresh)
+    const bool torch_sem = h->p.surface == B200GATE_SURFACE_TORCH;
+    const int64_t No = torch_sem ? (N / h->p.hop_length) * h->p.hop_length : N;    // torchgate.py:255-262 length
+    if (in_stride < N || out_stride < No) return fail(h, B200GATE_ERR_ARG, "row strides too small");
+    if (torch_sem && N < 2 * h->p.win_length) return fail(h, B200GATE_ERR_ARG, "x must be bigger than %d", 2 * h->p.win_length);
+    if (torch_sem && h->tthr_units > 1 && h->tthr_units != C)
+        return fail(h, B200GATE_ERR_ARG, "xn has %d rows, x has %lld", h->tthr_units, (long long)C);
+    if (h->p.stationary && !torch_sem && !h->have_thresh)
         return fail(h, B200GATE_ERR_STATE, "stationary gate: call b200gate_noise_stats first");
     cudaStream_t st = (cudaStream_t)stream;
     const b200gate_params& p = h->p;
@@ -502,10 +568,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     g.H = p.hop_length;
     g.C = (int)C;
     g.n_total = N;
-    const bool chunked = p.chunk_size > 0 && N > p.chunk_size;
+    const bool chunked = !torch_sem && p.chunk_size > 0 && N > p.chunk_size;
     g.step = chunked ? p.chunk_size : N;
     g.n_chunks = chunked ? (int)((N - 1) / p.chunk_size) + 1 : 1;
-    g.pad = p.padding;
+    g.pad = torch_sem ? 0 : p.padding;                 // TorchGate filters the whole row, no chunk padding
     g.Lp = g.step + 2 * g.pad;
     g.T = (int)(g.Lp / g.H) + 1;
     g.in_stride = xs;
@@ -524,15 +590,16 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         tf_lo = std::max(0, h_lo - 3);
         tf_hi = std::min(h_hi, g.T);
     }
-    const bool tail_zeros = (g.pad + g.step > sig_len);     // stationary.py:126 leaves the tail zero
+    const bool tail_zeros = !torch_sem && (g.pad + g.step > sig_len);     // stationary.py:126 leaves the tail zero
     if (tail_zeros) {
         for (long long c = 0; c < C; ++c) CK(h, cudaMemsetAsync(y + c * ys, 0, (size_t)N * 4, st));
     }
 
     // ---- workspace / batching ---------------------------------------------------------------------
     const bool stat = p.stationary != 0;
-    const size_t per_unit = stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
-                                 : 2 * (size_t)g.T * kFPad * 4 + 64;
+    const size_t per_unit = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
+                                  : 2 * (size_t)g.T * kFPad * 4 + 64) +
+                            (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
@@ -545,10 +612,18 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t end_stat = off_num + al((size_t)ub * g.T * kFPad * 2);
     const size_t off_m0 = al((size_t)ub * g.T * kFPad * 4);
     const size_t end_nonstat = off_m0 + al((size_t)ub * g.T * kFPad * 4);
+    // torch surface, stationary: the stationary buffers follow the dB spectrogram
+    const size_t off_tdb = end_stat;
+    const size_t off_trow = off_tdb + al((size_t)ub * g.T * kFPad * 4);
+    const size_t off_tthr = off_trow + al((size_t)ub * kFPad * 4);
+    const size_t end_tstat = off_tthr + al((size_t)ub * kFPad * 4);
     {
-        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, stat ? end_stat : end_nonstat);
+        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
         if (rc) return rc;
     }
+    float* d_tdb = (float*)(h->d_ws_buf + off_tdb);
+    float* d_trow = (float*)(h->d_ws_buf + off_trow);
+    float* d_tthr_self = (float*)(h->d_ws_buf + off_tthr);
     unsigned* d_bits = (unsigned*)(h->d_ws_buf + off_bits);
     unsigned* d_rowmax = (unsigned*)(h->d_ws_buf + off_rowmax);
     unsigned* d_rowflag = (unsigned*)(h->d_ws_buf + off_rowflag);
@@ -599,23 +674,46 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         dbg.mask = h->d_dbg_mask;
 
         if (stat) {
-            CK(h, cudaMemsetAsync(d_rowmax, 0, (size_t)nu * kFPad * 4, st));
-            cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-            // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
-            K1Args a1{};
-            a1.g = g; a1.tb = tb; a1.x = x; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
-            {
-                long long want = (long long)resident * kWarps * 4;
-                long long run = ((long long)nu * g.T + want - 1) / want;
-                run = std::max(8LL, std::min(64LL, run));
-                run += run & 1;
-                a1.run = (int)run;
-                a1.n_runs = (g.T + a1.run - 1) / a1.run;
+            if (torch_sem) {
+                // TorchGate: |X| -> dB, per-row statistics over the row's own frames (or xn's), compare
+                cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+                launch_k1n(g, tb, x, d_tdb, dbg, resident, st);
+                TStatArgs ta{};
+                ta.n_units = nu; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64;
+                ta.top_db = (float)p.top_db; ta.n_std = (float)p.n_std_thresh; ta.ddof = p.std_ddof;
+                ta.mag = d_tdb; ta.rowmax = d_trow; ta.thr = d_tthr_self;
+                B200_LAUNCH(k_tgate_stats, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ta);
+                TBitsArgs ba{};
+                ba.n_units = nu; ba.T = g.T; ba.top_db = (float)p.top_db; ba.db = d_tdb; ba.rowmax = d_trow; ba.bits = d_bits;
+                if (h->tthr_units > 0) {
+                    ba.thr = h->tthr_units == 1 ? h->d_tthr : h->d_tthr + (size_t)u0 * kFPad;
+                    ba.thr_units = h->tthr_units == 1 ? 1 : nu;
+                } else {
+                    ba.thr = d_tthr_self;
+                    ba.thr_units = nu;
+                }
+                B200_LAUNCH(k_tgate_bits, dim3((unsigned)(((long long)nu * kFPad + 127) / 128)), dim3(128), 0, st, ba);
+                CK(h, cudaMemsetAsync(d_rowflag, 0, (size_t)nu * kFW * 4, st));
+                ++launches;
+            } else {
+                CK(h, cudaMemsetAsync(d_rowmax, 0, (size_t)nu * kFPad * 4, st));
+                cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+                // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
+                K1Args a1{};
+                a1.g = g; a1.tb = tb; a1.x = x; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
+                {
+                    long long want = (long long)resident * kWarps * 4;
+                    long long run = ((long long)nu * g.T + want - 1) / want;
+                    run = std::max(8LL, std::min(64LL, run));
+                    run += run & 1;
+                    a1.run = (int)run;
+                    a1.n_runs = (g.T + a1.run - 1) / a1.run;
+                }
+                const long long items1 = (long long)nu * a1.n_runs;
+                B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, resident)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
+                B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
+                            (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
             }
-            const long long items1 = (long long)nu * a1.n_runs;
-            B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, resident)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
-            B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
-                        (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
             launches += 2;
             cudaEventRecord(h->stage_ev[4 * bi + 1], st);
             cudaEventRecord(h->stage_ev[4 * bi + 2], st);
@@ -674,35 +772,32 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             }
         } else {
             cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-            K1nArgs a1{};
-            a1.g = g; a1.tb = tb; a1.x = x; a1.mag = d_mag; a1.dbg = dbg;
-            {
-                long long want = (long long)resident * kWarps * 4;
-                long long run = ((long long)nu * g.T + want - 1) / want;
-                run = std::max(8LL, std::min(64LL, run));
-                run += run & 1;
-                a1.run = (int)run;
-                a1.n_runs = (g.T + a1.run - 1) / a1.run;
-            }
-            B200_LAUNCH(k1n_magnitude<8>, dim3(grid_1d((long long)nu * a1.n_runs, kWarps, resident)), dim3(kThreads),
-                        k1n_smem_floats() * 4, st, a1);
+            launch_k1n(g, tb, x, d_mag, dbg, resident, st);
             cudaEventRecord(h->stage_ev[4 * bi + 1], st);
-            IirArgs ia{};
-            ia.n_units = nu; ia.T = g.T;
-            {
-                const double tfr = p.time_constant_s * p.sr / (double)g.H;        // nonstationary.py:109-114
-                ia.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
+            if (torch_sem) {
+                TMovArgs ma{};
+                ma.n_units = nu; ma.T = g.T; ma.n_movemean = p.n_movemean; ma.n_thresh = (float)p.thresh_n_mult;
+                ma.inv_temp = (float)p.sigmoid_slope; ma.p = (float)p.prop_decrease; ma.mag = d_mag; ma.m0 = d_m0;
+                B200_LAUNCH(k_tgate_movmean, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ma);
+            } else {
+                IirArgs ia{};
+                ia.n_units = nu; ia.T = g.T;
+                {
+                    const double tfr = p.time_constant_s * p.sr / (double)g.H;        // nonstationary.py:109-114
+                    ia.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
+                }
+                ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
+                ia.mag = d_mag; ia.m0 = d_m0;
+                B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
             }
-            ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
-            ia.mag = d_mag; ia.m0 = d_m0;
-            B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
             launches += 2;
             cudaEventRecord(h->stage_ev[4 * bi + 2], st);
             cudaEventRecord(h->stage_ev[4 * bi + 3], st);
             if (tf_hi > tf_lo) {
                 SmoothFArgs sa{};
                 sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
-                sa.p = (float)p.prop_decrease; sa.one_minus_p = (float)(1.0 - p.prop_decrease);
+                sa.p = torch_sem ? 1.0f : (float)p.prop_decrease;
+                sa.one_minus_p = torch_sem ? 0.0f : (float)(1.0 - p.prop_decrease);
                 sa.m0 = d_m0; sa.m2 = d_mag;
                 const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
                 B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, nf), st, sa);
@@ -749,19 +844,19 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * N * es))) return rc;
             const int gr = grid_1d((long long)C * N, 256, h->num_sm * 16);
             void* dst = is_device ? out : h->d_raw;
-            const long long ds = is_device ? out_stride : N;
+            const long long ds = is_device ? out_stride : No;
             if (dtype == B200GATE_I16)
-                { auto kern_ = k_from_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (short*)dst, (long long)C, (long long)N, ys, ds); }
+                { auto kern_ = k_from_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (short*)dst, (long long)C, (long long)No, ys, ds); }
             else
-                { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (double*)dst, (long long)C, (long long)N, ys, ds); }
+                { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (double*)dst, (long long)C, (long long)No, ys, ds); }
             ++launches;
             res = h->d_raw;
         } else if (is_device) {
-            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * 4, y, (size_t)ys * 4, (size_t)N * 4, (size_t)C,
+            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * 4, y, (size_t)ys * 4, (size_t)No * 4, (size_t)C,
                                     cudaMemcpyDeviceToDevice, st));
         }
         if (!is_device)
-            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, res, (size_t)N * es, (size_t)N * es, (size_t)C,
+            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, res, (size_t)(dtype != B200GATE_F32 ? No : ys) * es, (size_t)No * es, (size_t)C,
                                     cudaMemcpyDeviceToHost, st));
     }
     CK(h, cudaGetLastError());

@@ -917,6 +917,116 @@ __global__ void __launch_bounds__(256) k_smooth_f(const SmoothFArgs a) {
 }
 
 // =============================================================================================
+// TorchGate surface (noisereduce/torchgate/torchgate.py:200-264).  Same analysis / synthesis kernels;
+// what differs is the mask: statistics per (row, bin) over the row's own frames (or over xn's),
+// top_db = 40, unbiased std (torchgate.py:127-165, torchgate/utils.py:6-23), and for the
+// non-stationary variant a moving mean instead of the IIR (torchgate.py:168-198).
+// =============================================================================================
+struct TStatArgs {
+    int n_units, T;
+    float in_scale;            // sum(window): TorchGate's STFT is not normalised
+    float eps;                 // torch.finfo(float64).eps added in float32
+    float top_db;
+    float n_std;
+    int ddof;
+    float* mag;                // in: |X| / sum(w);  out: dB (float32), unclamped
+    float* rowmax;             // [n_units][FPad] max_t dB
+    float* thr;                // [n_units][FPad] mean + n_std * std of the clamped dB
+};
+
+__global__ void __launch_bounds__(128) k_tgate_stats(const TStatArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.n_units * kFPad) return;
+    const int ul = (int)(idx / kFPad), f = (int)(idx - (long long)ul * kFPad);
+    float* D = a.mag + (long long)ul * a.T * kFPad + f;
+    if (f >= kF) {
+        a.rowmax[idx] = -INFINITY;
+        a.thr[idx] = INFINITY;
+        return;
+    }
+    float mx = -INFINITY;
+#pragma unroll 4
+    for (int t = 0; t < a.T; ++t) {
+        const float db = 20.0f * log10f(D[(long long)t * kFPad] * a.in_scale + a.eps);
+        D[(long long)t * kFPad] = db;
+        mx = fmaxf(mx, db);
+    }
+    const float fl = mx - a.top_db;
+    double sum = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < a.T; ++t) sum += (double)fmaxf(D[(long long)t * kFPad], fl);
+    const double mean = sum / a.T;
+    double ss = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < a.T; ++t) {
+        const double d = (double)fmaxf(D[(long long)t * kFPad], fl) - mean;
+        ss += d * d;
+    }
+    const double sd = sqrt(ss / (double)(a.T - a.ddof));
+    a.rowmax[idx] = mx;
+    a.thr[idx] = (float)(mean + sd * (double)a.n_std);
+}
+
+struct TBitsArgs {
+    int n_units, T;
+    int thr_units;             // rows of thr: n_units (self / per-row xn) or 1 (broadcast)
+    float top_db;
+    const float* db;           // [n_units][T][FPad]
+    const float* rowmax;       // [n_units][FPad]  (of x itself)
+    const float* thr;          // [thr_units][FPad]
+    unsigned* bits;            // [n_units][T][FW]
+};
+
+__global__ void __launch_bounds__(128) k_tgate_bits(const TBitsArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // grid covers n_units*FPad exactly
+    const int ul = (int)(idx / kFPad), f = (int)(idx - (long long)ul * kFPad);
+    const bool ok = ul < a.n_units;
+    const float* D = a.db + (long long)(ok ? ul : 0) * a.T * kFPad + f;
+    const float fl = ok ? a.rowmax[(long long)ul * kFPad + f] - a.top_db : 0.f;
+    const float th = ok ? a.thr[(long long)(a.thr_units == 1 ? 0 : ul) * kFPad + f] : INFINITY;
+    const int w = f >> 5, lane = threadIdx.x & 31;
+    for (int t = 0; t < a.T; ++t) {
+        const bool on = ok && (f < kF) && (fmaxf(D[(long long)t * kFPad], fl) > th);
+        const unsigned word = __ballot_sync(0xffffffffu, on);
+        if (ok && lane == 0) a.bits[((long long)ul * a.T + t) * kFW + w] = word;
+    }
+}
+
+struct TMovArgs {
+    int n_units, T;
+    int n_movemean;
+    float n_thresh, inv_temp, p;
+    const float* mag;
+    float* m0;                 // blended sigmoid mask, prop_decrease * (m - 1) + 1 (torchgate.py:241)
+};
+
+__global__ void __launch_bounds__(128) k_tgate_movmean(const TMovArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.n_units * kFPad) return;
+    const int ul = (int)(idx / kFPad), f = (int)(idx - (long long)ul * kFPad);
+    const float* A = a.mag + (long long)ul * a.T * kFPad + f;
+    float* M = a.m0 + (long long)ul * a.T * kFPad + f;
+    if (f >= kF) {
+        for (int t = 0; t < a.T; ++t) M[(long long)t * kFPad] = 0.f;
+        return;
+    }
+    // conv1d(ones(n), padding="same"): window [t - left, t + right], zero padded, left = (n-1)/2
+    const int n = a.n_movemean, left = (n - 1) / 2, right = n - 1 - left;
+    double run = 0.0;
+    for (int t = 0; t <= right && t < a.T; ++t) run += (double)A[(long long)t * kFPad];
+    for (int t = 0; t < a.T; ++t) {
+        const float Av = A[(long long)t * kFPad];
+        const float S = (float)(run / (double)n);
+        const float r = (Av - S) / S;
+        const float m = 1.0f / (1.0f + expf(-(r - a.n_thresh) * a.inv_temp));
+        M[(long long)t * kFPad] = a.p * (m - 1.0f) + 1.0f;
+        const int tin = t + 1 + right, tout = t - left;
+        if (tin < a.T) run += (double)A[(long long)tin * kFPad];
+        if (tout >= 0) run -= (double)A[(long long)tout * kFPad];
+    }
+}
+
+// =============================================================================================
 // dtype conversion at the edges (base.py:140 promotes every chunk to float64; :218-226 casts back)
 // =============================================================================================
 template <typename Tin>

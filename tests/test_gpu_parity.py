@@ -130,3 +130,37 @@ def test_device_pointer_path_and_properties(lib):
     # idempotent launch: same input -> bit-identical output (no races in the overlap-add seams)
     y2 = dg.run(x)
     assert torch.equal(y, y2)
+
+
+def test_torchgate_surface(lib, golden_dir):
+    """Config 4 surface: CUDA tensors through TorchGate.forward, vs the reference's own outputs
+    (tests/golden/torchgate_small.npz) and the float64 oracle."""
+    import torch
+    from noisereduce_b200.torchgate import TorchGate
+    from oracle import torchgate_oracle as TO
+    g = np.load(os.path.join(golden_dir, "torchgate_small.npz"))
+    x = torch.from_numpy(g["x"]).cuda()
+    sr = int(g["sr"])
+    tol = 2e-5          # FP32 path vs the reference's float32 / float64 runs (its own f32-vs-f64 gap is 2.5e-7)
+    y = TorchGate(sr=sr).to("cuda")(x)
+    assert y.is_cuda and y.dtype == torch.float32 and tuple(y.shape) == tuple(g["out_stat_f32"].shape)
+    assert P.relinf(y.cpu().numpy(), g["out_stat_f64"]) < tol
+    assert P.relinf(y.cpu().numpy(), g["out_stat_f32"]) < tol
+    y = TorchGate(sr=sr, nonstationary=True)(x)
+    assert P.relinf(y.cpu().numpy(), g["out_nonstat_f64"]) < tol
+    y = TorchGate(sr=sr, prop_decrease=0.7)(x.double(), x[:1, :6000].double())
+    assert y.dtype == torch.float64
+    assert P.relinf(y.cpu().numpy(), g["out_stat_xn_p07_f64"]) < tol
+    # config-4 shaped batch (subset of rows checked against the oracle)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    xb = 0.05 * torch.randn((32, 160000), device="cuda", generator=gen)
+    t = torch.arange(160000, device="cuda") / 16000
+    xb += 0.2 * torch.sin(2 * torch.pi * 700 * t) * ((t % 1.0) < 0.3)
+    tg = TorchGate(sr=16000)
+    yb = tg(xb)
+    torch.cuda.synchronize()
+    assert tuple(yb.shape) == (32, 160000)
+    for r in (0, 31):
+        ref = TO.torchgate_forward(xb[r:r + 1].cpu().numpy().astype(np.float64), 16000,
+                                   window=torch.hann_window(1024).numpy())
+        assert P.relinf(yb[r:r + 1].cpu().numpy(), ref) < 1e-4
