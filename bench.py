@@ -120,15 +120,16 @@ def cpu_reference_run(steps, warmup, quiet=False):
     from oracle import ref_port
     from oracle import spectral_gate_oracle as O
     cores = os.cpu_count() or 1
-    n_chunks = max(2, min(24, cores))          # bounded sample: <= 24 of config 2's 48 chunks
+    n_chunks = max(2, min(32, cores))          # bounded sample: <= 32 of config 2's 48 chunks (one per worker)
     C = 64
     n = n_chunks * 600000
     rng = np.random.default_rng(1000)
-    y = rng.standard_normal((C, n), dtype=np.float32)
-    y *= np.float32(0.05)
+    base = rng.standard_normal(n + 64 * 997, dtype=np.float32) * np.float32(0.05)
     t = np.arange(n, dtype=np.float64) / SR
     gate = 0.25 * ((t % 2.0) < 0.5)
-    for c in range(C):
+    y = np.empty((C, n), dtype=np.float32)
+    for c in range(C):                         # same distribution as the device workload; shifted noise per channel
+        y[c] = base[c * 997: c * 997 + n]
         y[c] += (gate * np.sin(2 * np.pi * 440.0 * 2 ** ((c % 24) / 12) * t)).astype(np.float32)
     cfg = O.GateConfig(sr=SR, stationary=True, n_fft=1024, hop_length=256)
     jobs = min(cores, n_chunks)

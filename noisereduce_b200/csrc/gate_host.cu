@@ -53,7 +53,12 @@ struct b200gate_handle {
     size_t raw_bytes = 0;
     Counters* d_cnt = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> stage_ev;             // 4 per batch: k1 start, k1 end(+rowfloor), smooth end, k2 end
+    std::vector<cudaEvent_t> stage_ev;
+    std::vector<cudaEvent_t> pipe_ev;              // 3 per batch (input landed, compute done, output landed)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined host path
+    float* d_slab_in[2] = {nullptr, nullptr};
+    float* d_slab_out[2] = {nullptr, nullptr};
+    size_t slab_in_bytes[2] = {0, 0}, slab_out_bytes[2] = {0, 0};             // 4 per batch: k1 start, k1 end(+rowfloor), smooth end, k2 end
     b200gate_stats stats{};
     // debug taps
     long long dbg_chunk = -1, dbg_channel = -1;
@@ -307,6 +312,8 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     if (rc == B200GATE_OK) {
         cudaEventCreate(&h->ev0);
         cudaEventCreate(&h->ev1);
+        cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
 #ifndef B200_CUSIM_BUILD
         cudaFuncSetAttribute(k1_analyze<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats() * 4);
         cudaFuncSetAttribute(k2_synthesize<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
@@ -335,6 +342,13 @@ void b200gate_destroy(b200gate_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    for (int i = 0; i < 2; ++i) {
+        if (h->d_slab_in[i]) cudaFree(h->d_slab_in[i]);
+        if (h->d_slab_out[i]) cudaFree(h->d_slab_out[i]);
+    }
     delete h;
 }
 
@@ -524,7 +538,12 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     float* y = nullptr;
     long long xs = in_stride, ys = out_stride;
     const bool direct = is_device && dtype == B200GATE_F32;
-    if (direct) {
+    // Host float32 input that the reference would chunk: stream it through the GPU slab by slab
+    // (H2D of slab k+1, kernels of slab k and D2H of slab k-1 overlap on three streams) instead of
+    // staging the whole recording -- the role of _read_chunk + the memmap write-back (base.py:130-187).
+    const bool pipelined = !is_device && dtype == B200GATE_F32 && !torch_sem && h->p.chunk_size > 0 &&
+                           N > h->p.chunk_size && h->p.padding >= h->p.hop_length;
+    if (direct || pipelined) {
         x = (const float*)in;
         y = (float*)out;
     } else {
@@ -603,6 +622,21 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
+    long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
+    if (pipelined) {
+        // ~512 MB of input per slab, whole chunks, within the workspace limit
+        slab_chunks = std::max(1LL, std::min<long long>(g.n_chunks, (512LL << 20) / std::max<long long>(1, C * g.step * 4)));
+        slab_chunks = std::max(1LL, std::min(slab_chunks, ub / C));
+        if (ub < C) return fail(h, B200GATE_ERR_NOMEM, "workspace limit too small for one chunk of all channels");
+        ub = slab_chunks * C;
+        slab_w = slab_chunks * g.step + 2 * g.pad;
+        slab_ow = slab_chunks * g.step;
+        for (int i = 0; i < 2; ++i) {
+            int rc;
+            if ((rc = ensure(h, (void**)&h->d_slab_in[i], &h->slab_in_bytes[i], (size_t)C * slab_w * 4))) return rc;
+            if ((rc = ensure(h, (void**)&h->d_slab_out[i], &h->slab_out_bytes[i], (size_t)C * slab_ow * 4))) return rc;
+        }
+    }
     // carve the workspace into 256-byte aligned sub-buffers (vector stores need natural alignment)
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t off_bits = 0;
@@ -662,12 +696,38 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         CK(h, cudaEventCreate(&e));
         h->stage_ev.push_back(e);
     }
+    while (pipelined && h->pipe_ev.size() < 3 * n_batches) {
+        cudaEvent_t e;
+        CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pipe_ev.push_back(e);
+    }
     size_t bi = 0;
     cudaEventRecord(evk0, st);
     for (long long u0 = 0; u0 < U; u0 += ub, ++bi) {
         const int nu = (int)std::min(ub, U - u0);
         g.u0 = (int)u0;
         g.n_units = nu;
+        const float* xb = x;
+        float* yb = y;
+        if (pipelined) {
+            // slab = chunks [c0, c1): input window [w0, w1) of every channel, output [c0*step, o1)
+            const long long c0 = u0 / C, c1 = c0 + nu / C;
+            const long long w0 = std::max(0LL, c0 * g.step - g.pad), w1 = std::min<long long>(N, c1 * g.step + g.pad);
+            const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
+            const int ib = (int)(bi & 1);
+            if (bi >= 2) CK(h, cudaStreamWaitEvent(h->s_h2d, h->pipe_ev[3 * (bi - 2) + 1], 0));   // slab buffer free
+            CK(h, cudaMemcpy2DAsync(h->d_slab_in[ib], (size_t)slab_w * 4, (const float*)in + w0, (size_t)in_stride * 4,
+                                    (size_t)(w1 - w0) * 4, (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 0], h->s_h2d));
+            CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * bi + 0], 0));
+            if (bi >= 2) CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * (bi - 2) + 2], 0));         // output buffer drained
+            // virtual row bases so the kernels keep absolute sample indices
+            xb = h->d_slab_in[ib] - w0;
+            yb = h->d_slab_out[ib] - o0;
+            g.in_stride = slab_w;
+            g.out_stride = slab_ow;
+            (void)o1;
+        }
         DebugTap dbg{};
         dbg.ul = (dbg_u >= u0 && dbg_u < u0 + nu) ? (int)(dbg_u - u0) : -1;
         dbg.spec = h->d_dbg_spec;
@@ -677,7 +737,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (torch_sem) {
                 // TorchGate: |X| -> dB, per-row statistics over the row's own frames (or xn's), compare
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, x, d_tdb, dbg, resident, st);
+                launch_k1n(g, tb, xb, d_tdb, dbg, resident, st);
                 TStatArgs ta{};
                 ta.n_units = nu; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64;
                 ta.top_db = (float)p.top_db; ta.n_std = (float)p.n_std_thresh; ta.ddof = p.std_ddof;
@@ -700,7 +760,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
                 // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
                 K1Args a1{};
-                a1.g = g; a1.tb = tb; a1.x = x; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
+                a1.g = g; a1.tb = tb; a1.x = xb; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
                 {
                     long long want = (long long)resident * kWarps * 4;
                     long long run = ((long long)nu * g.T + want - 1) / want;
@@ -749,7 +809,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
                 cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                 K2Args a2{};
-                a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.num = d_num;
+                a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.num = d_num;
                 a2.pD = (float)(p.prop_decrease / D);
                 a2.one_minus_p = (float)(1.0 - p.prop_decrease);
                 a2.nt = nt;
@@ -772,7 +832,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             }
         } else {
             cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-            launch_k1n(g, tb, x, d_mag, dbg, resident, st);
+            launch_k1n(g, tb, xb, d_mag, dbg, resident, st);
             cudaEventRecord(h->stage_ev[4 * bi + 1], st);
             if (torch_sem) {
                 TMovArgs ma{};
@@ -803,7 +863,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, nf), st, sa);
                 cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                 K2Args a2{};
-                a2.g = g; a2.tb = tb; a2.x = x; a2.y = y; a2.fmask = d_mag;
+                a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.fmask = d_mag;
                 a2.nt = nt;
                 a2.dbg = dbg;
                 {
@@ -833,11 +893,25 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             CK(h, cudaMemcpy(h->d_dbg_bits, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice));
         }
         CK(h, cudaGetLastError());
+        if (pipelined) {
+            const long long c0 = u0 / C, c1 = c0 + nu / C;
+            const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
+            const int ib = (int)(bi & 1);
+            CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 1], st));
+            CK(h, cudaStreamWaitEvent(h->s_d2h, h->pipe_ev[3 * bi + 1], 0));
+            CK(h, cudaMemcpy2DAsync((float*)out + o0, (size_t)out_stride * 4, h->d_slab_out[ib], (size_t)slab_ow * 4,
+                                    (size_t)(o1 - o0) * 4, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
+            CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 2], h->s_d2h));
+        }
     }
     cudaEventRecord(evk1, st);
+    if (pipelined) {
+        CK(h, cudaStreamSynchronize(h->s_d2h));
+        CK(h, cudaStreamSynchronize(h->s_h2d));
+    }
 
     // ---- results back -------------------------------------------------------------------------------
-    if (!direct) {
+    if (!direct && !pipelined) {
         const void* res = y;
         if (dtype != B200GATE_F32) {
             int rc;

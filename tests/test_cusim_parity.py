@@ -43,6 +43,19 @@ def test_stationary_chunked_two_channels(lib):
     _assert_stationary(P.check_stationary(lib, y, cfg, tap_unit=(0, 1)))
 
 
+def test_pipelined_host_path_one_chunk_per_slab(lib):
+    """Host float32 input is streamed slab by slab (H2D / kernels / D2H on three streams); a tiny
+    workspace limit forces one chunk per slab so slab seams and buffer recycling are exercised."""
+    y = synth_small(C=2, n=23000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=4000, padding=600)
+    res = P.check_stationary(lib, y, cfg, tap_unit=(3, 1), workspace_limit_bytes=70000.0)
+    _assert_stationary(res)
+    assert res["stats"]["units"] == 12 and res["stats"]["kernel_launches"] >= 6 * 4
+    cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=4000, padding=600, time_constant_s=0.3)
+    res = P.check_nonstationary(lib, y, cfg, tap_unit=(5, 0), workspace_limit_bytes=250000.0)
+    assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5
+
+
 def test_stationary_own_thresholds_end_to_end(lib):
     y = synth_small(C=2, n=9000)
     cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=4000, padding=500)
