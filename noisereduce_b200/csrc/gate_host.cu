@@ -4,7 +4,7 @@
 // table of independent (chunk, channel) units, sizes the device workspace, and launches
 // k1_analyze -> k_rowfloor -> k_smooth -> k2_synthesize per batch of units on the caller's stream.
 #include "../../include/b200gate.h"
-#include "gate_kernels.cuh"
+#include "gate_kernels_2k.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -38,6 +38,7 @@ struct b200gate_handle {
     double *d_thr2_64 = nullptr, *d_wa64 = nullptr;
     double2* d_cs64 = nullptr;
     float ws_to_w = 0.f;
+    float2 *d_wa2 = nullptr, *d_ws2 = nullptr, *d_w2k = nullptr, *d_invn2 = nullptr;   // n_fft = 2048 family
     double sum_w = 0.0;
     std::vector<float> user_window;                // torch surface: torch.hann_window values
     float* d_tthr = nullptr;                       // torch surface: thresholds from xn, [tthr_units][FPad]
@@ -107,7 +108,47 @@ int ensure(b200gate_handle* h, void** p, size_t* have, size_t need) {
 }
 
 // Tables that depend only on the geometry: windows, twiddles, overlap-add norm, edge factors.
+int build_static_tables_2k(b200gate_handle* h) {
+    const int N = kN2, H = h->p.hop_length;
+    std::vector<double> w(N);
+    double sw = 0.0;
+    for (int n = 0; n < N; ++n) {
+        w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)N);
+        sw += w[n];
+    }
+    h->sum_w = sw;
+    h->ws_to_w = (float)(1024.0 / sw);
+    std::vector<float2> wa2(1024), ws2(1024), w2k(kF2), invn2(256), tw(32 * 32);
+    for (int m = 0; m < 1024; ++m) {
+        wa2[m] = make_float2((float)(w[2 * m] / sw), (float)(w[2 * m + 1] / sw));
+        ws2[m] = make_float2((float)(w[2 * m] * sw / 1024.0), (float)(w[2 * m + 1] * sw / 1024.0));
+    }
+    for (int k = 0; k < kF2; ++k) {
+        const long double th = M_PIl * (long double)k / 1024.0L;
+        w2k[k] = make_float2((float)cosl(th), (float)(-sinl(th)));
+    }
+    for (int r = 0; r < H; ++r) {
+        double sacc = 0.0;
+        for (int i = 0; i * H + r < N; ++i) sacc += w[i * H + r] * w[i * H + r];
+        const float v = (float)(sacc > 1e-10 ? 1.0 / sacc : 1.0);
+        if (r & 1) invn2[r >> 1].y = v; else invn2[r >> 1].x = v;
+    }
+    for (int q = 0; q < 32; ++q)
+        for (int l = 0; l < 32; ++l) {
+            const long double th = 2.0L * M_PIl * (long double)(l * q) / 1024.0L;
+            tw[q * 32 + l] = make_float2((float)cosl(th), (float)(-sinl(th)));
+        }
+    int rc;
+    if ((rc = upload(h, &h->d_wa2, wa2))) return rc;
+    if ((rc = upload(h, &h->d_ws2, ws2))) return rc;
+    if ((rc = upload(h, &h->d_w2k, w2k))) return rc;
+    if ((rc = upload(h, &h->d_invn2, invn2))) return rc;
+    if ((rc = upload(h, &h->d_tw, tw))) return rc;
+    return B200GATE_OK;
+}
+
 int build_static_tables(b200gate_handle* h) {
+    if (h->p.n_fft == kN2) return build_static_tables_2k(h);
     const int N = h->p.n_fft, H = h->p.hop_length;
     std::vector<double> w(N);
     double sw = 0.0;
@@ -281,11 +322,15 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         return fail(nullptr, B200GATE_ERR_ARG, "ABI version %d, library is %d", p->abi_version, B200GATE_ABI_VERSION);
     if (p->surface != B200GATE_SURFACE_NUMPY && p->surface != B200GATE_SURFACE_TORCH)
         return fail(nullptr, B200GATE_ERR_ARG, "unknown surface %d", p->surface);
-    if (p->n_fft != kN || p->win_length != p->n_fft || p->hop_length * 4 != p->n_fft)
+    const bool geo1k = p->n_fft == kN && p->win_length == kN && p->hop_length == kN / 4;
+    const bool geo2k = p->n_fft == kN2 && p->win_length == kN2 && p->hop_length == kN2 / 4 &&
+                       p->surface == B200GATE_SURFACE_NUMPY && !p->stationary;
+    if (!geo1k && !geo2k)
         return fail(nullptr, B200GATE_ERR_ARG,
-                    "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d: this build runs "
-                    "n_fft=1024, win_length=n_fft, hop_length=n_fft/4",
-                    p->n_fft, p->win_length, p->hop_length);
+                    "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d (%s gate): this build runs "
+                    "n_fft=1024 (both gates, both surfaces) and n_fft=2048 (non-stationary gate), each with "
+                    "win_length=n_fft, hop_length=n_fft/4",
+                    p->n_fft, p->win_length, p->hop_length, p->stationary ? "stationary" : "non-stationary");
     if (p->n_grad_freq < 0 || p->n_grad_time < 0 || p->n_grad_freq > 64 || p->n_grad_time > 64)
         return fail(nullptr, B200GATE_ERR_ARG, "smoothing extents out of range (%d, %d)", p->n_grad_freq, p->n_grad_time);
     if ((long long)(p->n_grad_freq + 1) * (p->n_grad_freq + 1) * (p->n_grad_time + 1) * (p->n_grad_time + 1) > 65535)
@@ -319,7 +364,9 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaFuncSetAttribute(k2_synthesize<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
         cudaFuncSetAttribute(k2_synthesize<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
         cudaFuncSetAttribute(k1n_magnitude<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
-        cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k1n_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n2_smem_floats() * 4);
+        cudaFuncSetAttribute(k2_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k22_smem_floats() * 4);
         cudaFuncSetAttribute(k_smooth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 #endif
     }
@@ -335,7 +382,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
 void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
-                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
+                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
                     h->d_dbg_mask, h->d_dbg_bits};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -448,13 +495,14 @@ int b200gate_debug_select_unit(b200gate_handle* h, int64_t chunk, int64_t channe
 int b200gate_debug_dims(const b200gate_handle* h, int64_t* T, int32_t* F, int32_t* words) {
     if (!h) return B200GATE_ERR_ARG;
     if (T) *T = h->dbg_T;
-    if (F) *F = kF;
-    if (words) *words = kFW;
+    if (F) *F = h->p.n_fft == kN2 ? kF2 : kF;
+    if (words) *words = h->p.n_fft == kN2 ? kFW2 : kFW;
     return B200GATE_OK;
 }
 
 int b200gate_debug_read_bits(b200gate_handle* h, uint32_t* bits) {
     if (!h || !bits || !h->d_dbg_bits || h->dbg_T <= 0) return B200GATE_ERR_STATE;
+    if (h->p.n_fft == kN2) { memset(bits, 0, (size_t)h->dbg_T * kFW2 * 4); return B200GATE_OK; }   // no binary mask in this family
     CK(h, cudaDeviceSynchronize());
     CK(h, cudaMemcpy(bits, h->d_dbg_bits, (size_t)h->dbg_T * kFW * 4, cudaMemcpyDeviceToHost));
     return B200GATE_OK;
@@ -462,13 +510,13 @@ int b200gate_debug_read_bits(b200gate_handle* h, uint32_t* bits) {
 int b200gate_debug_read_mask(b200gate_handle* h, float* mask) {
     if (!h || !mask || !h->d_dbg_mask || h->dbg_T <= 0) return B200GATE_ERR_STATE;
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(mask, h->d_dbg_mask, (size_t)h->dbg_T * kF * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(mask, h->d_dbg_mask, (size_t)h->dbg_T * (h->p.n_fft == kN2 ? kF2 : kF) * 4, cudaMemcpyDeviceToHost));
     return B200GATE_OK;
 }
 int b200gate_debug_read_spec(b200gate_handle* h, float* spec) {
     if (!h || !spec || !h->d_dbg_spec || h->dbg_T <= 0) return B200GATE_ERR_STATE;
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(spec, h->d_dbg_spec, (size_t)h->dbg_T * kF * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(spec, h->d_dbg_spec, (size_t)h->dbg_T * (h->p.n_fft == kN2 ? kF2 : kF) * 8, cudaMemcpyDeviceToHost));
     return B200GATE_OK;
 }
 
@@ -598,14 +646,17 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const long long U = (long long)g.n_chunks * C;
     if (U > 0x7fffffffLL || g.Lp / g.H > 0x3fffffffLL) return fail(h, B200GATE_ERR_ARG, "problem too large");
 
+    const int NFFT = p.n_fft;
+    const bool two_k = NFFT == kN2;
+    const int FP = two_k ? kFPad2 : kFPad, FF = two_k ? kF2 : kF;
     // frames whose masks k2 needs (same for every full chunk)
     const long long sig_len = (long long)(g.T - 1) * g.H;
     long long jp_hi = std::min(g.pad + g.step, sig_len);
     int tf_lo = 0, tf_hi = 0;
     int h_lo = 0, h_hi = 0;
     if (jp_hi > g.pad) {
-        h_lo = (int)((g.pad + kN / 2) / g.H);
-        h_hi = (int)((jp_hi + kN / 2 + g.H - 1) / g.H);
+        h_lo = (int)((g.pad + NFFT / 2) / g.H);
+        h_hi = (int)((jp_hi + NFFT / 2 + g.H - 1) / g.H);
         tf_lo = std::max(0, h_lo - 3);
         tf_hi = std::min(h_hi, g.T);
     }
@@ -617,7 +668,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // ---- workspace / batching ---------------------------------------------------------------------
     const bool stat = p.stationary != 0;
     const size_t per_unit = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
-                                  : 2 * (size_t)g.T * kFPad * 4 + 64) +
+                                  : 2 * (size_t)g.T * FP * 4 + 64) +
                             (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
@@ -644,8 +695,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t off_rowflag = off_rowmax + al((size_t)ub * kFPad * 4);
     const size_t off_num = off_rowflag + al((size_t)ub * kFW * 4);
     const size_t end_stat = off_num + al((size_t)ub * g.T * kFPad * 2);
-    const size_t off_m0 = al((size_t)ub * g.T * kFPad * 4);
-    const size_t end_nonstat = off_m0 + al((size_t)ub * g.T * kFPad * 4);
+    const size_t off_m0 = al((size_t)ub * g.T * FP * 4);
+    const size_t end_nonstat = off_m0 + al((size_t)ub * g.T * FP * 4);
     // torch surface, stationary: the stationary buffers follow the dB spectrogram
     const size_t off_tdb = end_stat;
     const size_t off_trow = off_tdb + al((size_t)ub * g.T * kFPad * 4);
@@ -673,13 +724,13 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (h->d_dbg_spec) cudaFree(h->d_dbg_spec);
             if (h->d_dbg_mask) cudaFree(h->d_dbg_mask);
             if (h->d_dbg_bits) cudaFree(h->d_dbg_bits);
-            CK(h, cudaMalloc((void**)&h->d_dbg_spec, (size_t)g.T * kF * 8));
-            CK(h, cudaMalloc((void**)&h->d_dbg_mask, (size_t)g.T * kF * 4));
+            CK(h, cudaMalloc((void**)&h->d_dbg_spec, (size_t)g.T * kF2 * 8));
+            CK(h, cudaMalloc((void**)&h->d_dbg_mask, (size_t)g.T * kF2 * 4));
             CK(h, cudaMalloc((void**)&h->d_dbg_bits, (size_t)g.T * kFW * 4));
             h->dbg_T_alloc = g.T;
         }
-        CK(h, cudaMemsetAsync(h->d_dbg_spec, 0, (size_t)g.T * kF * 8, st));
-        CK(h, cudaMemsetAsync(h->d_dbg_mask, 0, (size_t)g.T * kF * 4, st));
+        CK(h, cudaMemsetAsync(h->d_dbg_spec, 0, (size_t)g.T * FF * 8, st));
+        CK(h, cudaMemsetAsync(h->d_dbg_mask, 0, (size_t)g.T * FF * 4, st));
         h->dbg_T = g.T;
     } else {
         h->dbg_T = 0;
@@ -831,55 +882,110 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 launches += 2;
             }
         } else {
-            cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-            launch_k1n(g, tb, xb, d_mag, dbg, resident, st);
-            cudaEventRecord(h->stage_ev[4 * bi + 1], st);
-            if (torch_sem) {
-                TMovArgs ma{};
-                ma.n_units = nu; ma.T = g.T; ma.n_movemean = p.n_movemean; ma.n_thresh = (float)p.thresh_n_mult;
-                ma.inv_temp = (float)p.sigmoid_slope; ma.p = (float)p.prop_decrease; ma.mag = d_mag; ma.m0 = d_m0;
-                B200_LAUNCH(k_tgate_movmean, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ma);
-            } else {
-                IirArgs ia{};
-                ia.n_units = nu; ia.T = g.T;
+            if (two_k) {
+                Tables2 t2{};
+                t2.wa2 = h->d_wa2; t2.ws2 = h->d_ws2; t2.tw = h->d_tw; t2.w2k = h->d_w2k; t2.invn2 = h->d_invn2;
+                t2.ws_to_w = h->ws_to_w;
+                const int res2 = h->num_sm * 2;
+                cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+                K1n2Args a1{};
+                a1.g = g; a1.tb = t2; a1.x = xb; a1.mag = d_mag; a1.dbg = dbg;
                 {
-                    const double tfr = p.time_constant_s * p.sr / (double)g.H;        // nonstationary.py:109-114
+                    long long want = (long long)resident * kWarps * 4;
+                    long long run = ((long long)nu * g.T + want - 1) / want;
+                    a1.run = (int)std::max(4LL, std::min(64LL, run));
+                    a1.n_runs = (g.T + a1.run - 1) / a1.run;
+                }
+                B200_LAUNCH(k1n_magnitude_2k, dim3(grid_1d((long long)nu * a1.n_runs, kWarps, resident)), dim3(kThreads),
+                            k1n2_smem_floats() * 4, st, a1);
+                cudaEventRecord(h->stage_ev[4 * bi + 1], st);
+                IirArgs ia{};
+                ia.n_units = nu; ia.T = g.T; ia.F = kF2; ia.FPad = kFPad2;
+                {
+                    const double tfr = p.time_constant_s * p.sr / (double)g.H;
                     ia.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
                 }
                 ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
                 ia.mag = d_mag; ia.m0 = d_m0;
-                B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
-            }
-            launches += 2;
-            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
-            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
-            if (tf_hi > tf_lo) {
-                SmoothFArgs sa{};
-                sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
-                sa.p = torch_sem ? 1.0f : (float)p.prop_decrease;
-                sa.one_minus_p = torch_sem ? 0.0f : (float)(1.0 - p.prop_decrease);
-                sa.m0 = d_m0; sa.m2 = d_mag;
-                const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, nf), st, sa);
-                cudaEventRecord(h->stage_ev[4 * bi + 2], st);
-                K2Args a2{};
-                a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.fmask = d_mag;
-                a2.nt = nt;
-                a2.dbg = dbg;
-                {
-                    const long long hops = h_hi - h_lo;
-                    long long want = (long long)resident * kWarps * 4;
-                    long long run = ((long long)nu * hops + want - 1) / want;
-                    run = std::max(16LL, std::min(128LL, run));
-                    run += run & 1;
-                    a2.run = (int)run;
-                    a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
-                }
-                auto kern2 = k2_synthesize<8, true>;
-                B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
-                            k2_smem_floats(g.H) * 4, st, a2);
-                cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+                B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad2, 128, 1 << 30)), dim3(128), 0, st, ia);
                 launches += 2;
+                cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+                cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+                if (tf_hi > tf_lo) {
+                    SmoothFArgs sa{};
+                    sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 16;
+                    sa.F = kF2; sa.FPad = kFPad2;
+                    sa.p = (float)p.prop_decrease; sa.one_minus_p = (float)(1.0 - p.prop_decrease);
+                    sa.m0 = d_m0; sa.m2 = d_mag;
+                    const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                    B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+                    cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+                    K22Args a2{};
+                    a2.g = g; a2.tb = t2; a2.x = xb; a2.y = yb; a2.fmask = d_mag; a2.dbg = dbg;
+                    {
+                        const long long hops = h_hi - h_lo;
+                        long long want = (long long)res2 * kWarps * 4;
+                        long long run = ((long long)nu * hops + want - 1) / want;
+                        a2.run = (int)std::max(16LL, std::min(128LL, run));
+                        a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
+                    }
+                    B200_LAUNCH(k2_synthesize_2k, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, res2)), dim3(kThreads),
+                                k22_smem_floats() * 4, st, a2);
+                    cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+                    launches += 2;
+                }
+            } else {
+                cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+                launch_k1n(g, tb, xb, d_mag, dbg, resident, st);
+                cudaEventRecord(h->stage_ev[4 * bi + 1], st);
+                if (torch_sem) {
+                    TMovArgs ma{};
+                    ma.n_units = nu; ma.T = g.T; ma.n_movemean = p.n_movemean; ma.n_thresh = (float)p.thresh_n_mult;
+                    ma.inv_temp = (float)p.sigmoid_slope; ma.p = (float)p.prop_decrease; ma.mag = d_mag; ma.m0 = d_m0;
+                    B200_LAUNCH(k_tgate_movmean, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ma);
+                } else {
+                    IirArgs ia{};
+                    ia.n_units = nu; ia.T = g.T; ia.F = kF; ia.FPad = kFPad;
+                    {
+                        const double tfr = p.time_constant_s * p.sr / (double)g.H;        // nonstationary.py:109-114
+                        ia.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
+                    }
+                    ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
+                    ia.mag = d_mag; ia.m0 = d_m0;
+                    B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
+                }
+                launches += 2;
+                cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+                cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+                if (tf_hi > tf_lo) {
+                    SmoothFArgs sa{};
+                    sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
+                    sa.F = kF; sa.FPad = kFPad;
+                    sa.p = torch_sem ? 1.0f : (float)p.prop_decrease;
+                    sa.one_minus_p = torch_sem ? 0.0f : (float)(1.0 - p.prop_decrease);
+                    sa.m0 = d_m0; sa.m2 = d_mag;
+                    const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                    B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+                    cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+                    K2Args a2{};
+                    a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.fmask = d_mag;
+                    a2.nt = nt;
+                    a2.dbg = dbg;
+                    {
+                        const long long hops = h_hi - h_lo;
+                        long long want = (long long)resident * kWarps * 4;
+                        long long run = ((long long)nu * hops + want - 1) / want;
+                        run = std::max(16LL, std::min(128LL, run));
+                        run += run & 1;
+                        a2.run = (int)run;
+                        a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
+                    }
+                    auto kern2 = k2_synthesize<8, true>;
+                    B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
+                                k2_smem_floats(g.H) * 4, st, a2);
+                    cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+                    launches += 2;
+                }
             }
         }
         if (dbg.ul >= 0 && stat) {

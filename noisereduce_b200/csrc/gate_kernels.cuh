@@ -836,6 +836,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
 
 struct IirArgs {
     int n_units, T;
+    int F, FPad;               // bins and padded row pitch (513/544 for n_fft 1024, 1025/1056 for 2048)
     double b;                  // nonstationary.py:114
     float n_mult, slope;       // thresh_n_mult_nonstationary, sigmoid_slope_nonstationary
     const float* mag;          // [n_units][T][FPad]
@@ -843,76 +844,79 @@ struct IirArgs {
 };
 
 __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
+    const int FP = a.FPad, FF = a.F;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)a.n_units * kFPad) return;
-    const int ul = (int)(idx / kFPad), f = (int)(idx - (long long)ul * kFPad);
-    const float* A = a.mag + (long long)ul * a.T * kFPad + f;
-    float* M = a.m0 + (long long)ul * a.T * kFPad + f;
-    if (f >= kF) {
-        for (int t = 0; t < a.T; ++t) M[(long long)t * kFPad] = 0.f;
+    if (idx >= (long long)a.n_units * FP) return;
+    const int ul = (int)(idx / FP), f = (int)(idx - (long long)ul * FP);
+    const float* A = a.mag + (long long)ul * a.T * FP + f;
+    float* M = a.m0 + (long long)ul * a.T * FP + f;
+    if (f >= FF) {
+        for (int t = 0; t < a.T; ++t) M[(long long)t * FP] = 0.f;
         return;
     }
     const double b = a.b, omb = 1.0 - a.b;
     double s = (double)A[0];
 #pragma unroll 8
     for (int t = 0; t < a.T; ++t) {
-        s = b * (double)A[(long long)t * kFPad] + omb * s;
-        M[(long long)t * kFPad] = (float)s;
+        s = b * (double)A[(long long)t * FP] + omb * s;
+        M[(long long)t * FP] = (float)s;
     }
-    s = (double)M[(long long)(a.T - 1) * kFPad];
+    s = (double)M[(long long)(a.T - 1) * FP];
 #pragma unroll 8
     for (int t = a.T - 1; t >= 0; --t) {
-        s = b * (double)M[(long long)t * kFPad] + omb * s;
-        const double r = ((double)A[(long long)t * kFPad] - s) / s;
-        M[(long long)t * kFPad] = (float)(1.0 / (1.0 + exp(-(r - (double)a.n_mult) * (double)a.slope)));
+        s = b * (double)M[(long long)t * FP] + omb * s;
+        const double r = ((double)A[(long long)t * FP] - s) / s;
+        M[(long long)t * FP] = (float)(1.0 / (1.0 + exp(-(r - (double)a.n_mult) * (double)a.slope)));
     }
 }
 
 struct SmoothFArgs {
     int n_units, T;
+    int F, FPad;
     int nf, nt;
     int tf_lo, tf_hi, TT;
     float p, one_minus_p;
     const float* m0;           // [n_units][T][FPad]
     float* m2;                 // [n_units][T][FPad]
 };
-__host__ __device__ inline int smoothf_cpitch(int nf) { return kFPad + 2 * nf + 1; }
-inline size_t smoothf_smem_bytes(int TT, int nf) { return (size_t)TT * smoothf_cpitch(nf) * 4; }
+__host__ __device__ inline int smoothf_cpitch(int FPad, int nf) { return FPad + 2 * nf + 1; }
+inline size_t smoothf_smem_bytes(int TT, int FPad, int nf) { return (size_t)TT * smoothf_cpitch(FPad, nf) * 4; }
 
 __global__ void __launch_bounds__(256) k_smooth_f(const SmoothFArgs a) {
     B200_DYN_SMEM(float, s_c);                         // [TT][cp]
-    const int nt = a.nt, nf = a.nf, cp = smoothf_cpitch(nf);
+    const int FP = a.FPad, FF = a.F;
+    const int nt = a.nt, nf = a.nf, cp = smoothf_cpitch(a.FPad, nf);
     const int ul = blockIdx.y;
     const int t0 = a.tf_lo + blockIdx.x * a.TT;
     if (t0 >= a.tf_hi) return;
     const int tt_n = min(a.TT, a.tf_hi - t0);
     for (int i = threadIdx.x; i < a.TT * cp; i += blockDim.x) s_c[i] = 0.f;
     __syncthreads();
-    const float* src = a.m0 + (long long)ul * a.T * kFPad;
-    for (int i = threadIdx.x; i < tt_n * kFPad; i += blockDim.x) {
-        const int tt = i / kFPad, f = i - tt * kFPad;
-        if (f >= kF) continue;
+    const float* src = a.m0 + (long long)ul * a.T * FP;
+    for (int i = threadIdx.x; i < tt_n * FP; i += blockDim.x) {
+        const int tt = i / FP, f = i - tt * FP;
+        if (f >= FF) continue;
         const int t = t0 + tt;
         float acc = 0.f;
         for (int bb = -nt; bb <= nt; ++bb) {
             const int tq = t - bb;
-            if (tq >= 0 && tq < a.T) acc = fmaf((float)(nt + 1 - (bb < 0 ? -bb : bb)), src[(long long)tq * kFPad + f], acc);
+            if (tq >= 0 && tq < a.T) acc = fmaf((float)(nt + 1 - (bb < 0 ? -bb : bb)), src[(long long)tq * FP + f], acc);
         }
         s_c[tt * cp + nf + f] = acc;
     }
     __syncthreads();
     const float invD = 1.0f / ((float)((nf + 1) * (nf + 1)) * (float)((nt + 1) * (nt + 1)));
-    float* dst = a.m2 + (long long)ul * a.T * kFPad;
-    for (int i = threadIdx.x; i < tt_n * kFPad; i += blockDim.x) {
-        const int tt = i / kFPad, f = i - tt * kFPad;
+    float* dst = a.m2 + (long long)ul * a.T * FP;
+    for (int i = threadIdx.x; i < tt_n * FP; i += blockDim.x) {
+        const int tt = i / FP, f = i - tt * FP;
         float v = 0.f;
-        if (f < kF) {
+        if (f < FF) {
             const float* cr = s_c + tt * cp + f;
             float acc = 0.f;
             for (int d = -nf; d <= nf; ++d) acc = fmaf((float)(nf + 1 - (d < 0 ? -d : d)), cr[nf + d], acc);
             v = fmaf(acc * invD, a.p, a.one_minus_p);           // nonstationary.py:82-84
         }
-        dst[(long long)(t0 + tt) * kFPad + f] = v;
+        dst[(long long)(t0 + tt) * FP + f] = v;
     }
 }
 

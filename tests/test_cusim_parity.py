@@ -140,6 +140,22 @@ def test_nonstationary_chunked(lib):
     assert res["mask_err"] < P.MASK_TOL_NONSTAT and res["out_relinf"] < P.OUT_TOL_TIGHT * 5
 
 
+def test_nonstationary_n_fft_2048(lib):
+    """config-3 family: one real 2048-sample frame per complex-1024 warp FFT (half-length trick)."""
+    y = synth_small(C=2, n=20000)
+    cases = [(dict(chunk_size=8000, padding=1200, time_constant_s=0.3), [(1, 1), (0, 0), (2, 0)]),
+             (dict(prop_decrease=0.8), [(0, 1)]),
+             (dict(chunk_size=7000, padding=100), [(2, 0)])]
+    for kw, units in cases:
+        cfg = O.GateConfig(sr=SR, stationary=False, n_fft=2048, **kw)
+        for unit in units:
+            res = P.check_nonstationary(lib, y, cfg, tap_unit=unit)
+            assert res["spec_err"] < P.SPEC_TOL and res["mask_err"] < P.MASK_TOL_NONSTAT
+            assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5
+    with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
+        P.check_stationary(lib, y, O.GateConfig(sr=SR, stationary=True, n_fft=2048))
+
+
 def test_python_surface_on_simulator(lib, monkeypatch):
     """reduce_noise() host logic (shapes, dtypes, defaults, errors) with the simulator library."""
     monkeypatch.setattr(_cabi, "_LIB", lib)

@@ -93,6 +93,26 @@ def test_nonstationary(lib, golden_dir):
     assert np.abs(out.astype(np.int32) - f["out_nonstationary"].astype(np.int32)).max() <= 1
 
 
+def test_nonstationary_n_fft_2048_config3(lib, golden_dir):
+    """Config 3 geometry: 48 kHz, n_fft=2048 (hop 512, F=1025, T=1290 per chunk, filter 21 x 9)."""
+    import noisereduce_b200 as nr
+    sr = 48000
+    rng = np.random.default_rng(1002)
+    n = 1_300_000
+    t = np.arange(n) / sr
+    y = (0.05 * rng.standard_normal((2, n)) + 0.25 * ((t % 2.0) < 0.5) * np.sin(2 * np.pi * 523.25 * t)).astype(np.float32)
+    cfg = O.GateConfig(sr=sr, stationary=False, n_fft=2048)
+    for unit in [(0, 0), (1, 1), (2, 0)]:
+        res = P.check_nonstationary(lib, y, cfg, tap_unit=unit)
+        assert res["T"] == 1290
+        assert res["spec_err"] < P.SPEC_TOL and res["mask_err"] < P.MASK_TOL_NONSTAT, res
+        assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5, res
+    s = np.load(os.path.join(golden_dir, "synth_small.npz"))
+    out = nr.reduce_noise(y=s["y"].astype(np.float64), sr=int(s["sr"]), stationary=False, n_fft=2048,
+                          time_constant_s=0.5, prop_decrease=0.9)
+    assert out.dtype == np.float64 and P.relinf(out, s["out_nonstat_2048_f64"]) < P.OUT_TOL
+
+
 def test_golden_fish_and_small(lib, golden_dir):
     import noisereduce_b200 as nr
     f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
