@@ -92,21 +92,45 @@ __device__ __forceinline__ float chunk_sample(const float* __restrict__ xrow, lo
     return (j >= 0 && j < Lp && g >= 0 && g < n_total) ? __ldg(xrow + g) : 0.0f;
 }
 
-// Load the rows of a frame pair (frame t in rows 0..31, frame t+1 in rows HR..31+HR), window them
-// and pack them as one complex signal.  Returns the L2 norm^2 contribution of this lane.
+// Rows of a frame pair: frame t is rows 0..31, frame t+1 rows HR..31+HR of the same 32+HR row window
+// (row = 32 consecutive samples = one coalesced 128-byte access of the warp).
+template <int HR>
+__device__ __forceinline__ bool pair_window_interior(long long base, long long i1, long long Lp, long long n_total) {
+    const long long g0 = i1 + base;
+    const int span = 32 * (32 + HR);
+    return base >= 0 && base + span <= Lp && g0 >= 0 && g0 + span <= n_total;
+}
+
+// Software pipelining of the HBM latency: the 2*HR rows of the NEXT pair that this pair has not
+// touched are requested before this pair's FFT and sit in registers until the next iteration; the
+// other 32-HR rows were read by this pair and come back from L1.
+template <int HR>
+__device__ __forceinline__ void load_new_rows(float (&nx)[2 * HR], const float* __restrict__ xrow, long long base_next,
+                                              long long i1, int lane) {
+    const float* p = xrow + i1 + base_next + 32 * (32 - HR) + lane;
+#pragma unroll
+    for (int r = 0; r < 2 * HR; ++r) nx[r] = __ldg(p + 32 * r);
+}
+
+// Load (or assemble from the pre-loaded rows) the raw samples of the pair, window them and pack the
+// two frames as one complex signal.  Returns this lane's contribution to ||frame pair||^2.
 template <int HR>
 __device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32], const float* __restrict__ xrow,
                                                  long long base, long long i1, long long Lp, long long n_total,
-                                                 const float* __restrict__ s_wa, int lane, bool va, bool vb) {
+                                                 const float* __restrict__ s_wa, int lane, bool vb,
+                                                 const float (&nx)[2 * HR], bool have_nx) {
     float xr[32 + HR];
-    const long long g0 = i1 + base;
-    const int span = 32 * (32 + HR);
-    if (base >= 0 && base + span <= Lp && g0 >= 0 && g0 + span <= n_total) {
-        // interior of the chunk and of the recording (all but the edge frames): plain coalesced rows
-        const float* p = xrow + g0 + lane;
+    if (have_nx) {                                   // interior pair whose new rows were pre-loaded
+        const float* p = xrow + i1 + base + lane;
+#pragma unroll
+        for (int r = 0; r < 32 - HR; ++r) xr[r] = __ldg(p + 32 * r);
+#pragma unroll
+        for (int r = 0; r < 2 * HR; ++r) xr[32 - HR + r] = nx[r];
+    } else if (pair_window_interior<HR>(base, i1, Lp, n_total)) {
+        const float* p = xrow + i1 + base + lane;
 #pragma unroll
         for (int r = 0; r < 32 + HR; ++r) xr[r] = __ldg(p + 32 * r);
-    } else {
+    } else {                                         // chunk / recording edges: zero-extended samples
 #pragma unroll
         for (int r = 0; r < 32 + HR; ++r) xr[r] = chunk_sample(xrow, base + lane + 32 * r, i1, Lp, n_total);
     }
@@ -114,10 +138,16 @@ __device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
         const float w = s_wa[lane + 32 * r];
-        re[r] = va ? xr[r] * w : 0.f;
-        im[r] = vb ? xr[r + HR] * w : 0.f;
+        re[r] = xr[r] * w;
+        im[r] = xr[r + HR] * w;
         e = fmaf(re[r], re[r], e);
-        e = fmaf(im[r], im[r], e);
+    }
+    if (vb) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) e = fmaf(im[r], im[r], e);
+    } else {                                         // odd frame count: the pair's second frame does not exist
+#pragma unroll
+        for (int r = 0; r < 32; ++r) im[r] = 0.f;
     }
     return e;
 }
@@ -225,12 +255,16 @@ __global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
 #pragma unroll
         for (int q = 0; q < kFW; ++q) mx[q] = 0.f;
 
+        float nx[2 * HR];
+        bool have_nx = false;
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
-            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, true, vb);
-            if (t + 2 < t1) prefetch_next_pair<HR>(xrow, base + 2LL * H, i1, g.Lp, g.n_total, lane);
+            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, have_nx);
+            have_nx = (t + 2 < t1) && pair_window_interior<HR>(base, i1, g.Lp, g.n_total) &&
+                      pair_window_interior<HR>(base + 2LL * H, i1, g.Lp, g.n_total);
+            if (have_nx) load_new_rows<HR>(nx, xrow, base + 2LL * H, i1, lane);
             const float S = sqrtf(warp_sum(e));
             warp_fft1024(re, im, tile, s_tw, lane);
 
@@ -612,15 +646,31 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         float acc[32 + HR];
 #pragma unroll
         for (int r = 0; r < 32 + HR; ++r) acc[r] = 0.f;
+        float nx[2 * HR];
+#pragma unroll
+        for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
 
         for (int t = t_start; t < he; t += 2) {
             const bool va = (t <= t_last), vb = (t + 1 <= t_last);
             if (va) {                                   // vb implies va
                 const long long base = (long long)t * H - kN / 2;
                 float re[32], im[32];
-                load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, va, vb);
-                if (t + 2 <= t_last) prefetch_next_pair<HR>(xrow, base + 2LL * H, i1, g.Lp, g.n_total, lane);
+                // (no register pre-load of the next pair's rows here: k2 is at its register budget; the
+                //  mask loads below were the dominant exposed latency)
+                load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
                 const long long offA = (long long)t * kFPad, offB = (long long)(vb ? t + 1 : t) * kFPad;
+                // the masks of this pair are requested now, a whole FFT before the apply step needs them
+                float mka[kFW], mkb[FMASK ? kFW : 1];         // uint16 numerators travel packed two per register
+#pragma unroll
+                for (int q = 0; q < kFW; ++q) {
+                    const int k = lane + 32 * q;                         // < FPad, rows are padded
+                    if (FMASK) {
+                        mka[q] = frow[offA + k];
+                        mkb[FMASK ? q : 0] = frow[offB + k];
+                    } else {
+                        mka[q] = __uint_as_float((unsigned)mrow[offA + k] | ((unsigned)mrow[offB + k] << 16));
+                    }
+                }
                 float eta = 0.f, etb = 0.f;
                 if (!FMASK && blend) {
                     eta = a.one_minus_p * time_edge(t, g.T, a.nt);
@@ -651,14 +701,15 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
 #pragma unroll
                         for (int q = 0; q < kFW; ++q) {
                             const int sA = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
-                            const int k = lane + 32 * q;                 // < FPad, rows are padded
+                            const int k = lane + 32 * q;
                             float ma, mb;
                             if (FMASK) {
-                                ma = frow[offA + k];
-                                mb = frow[offB + k];
+                                ma = mka[q];
+                                mb = mkb[FMASK ? q : 0];
                             } else {
-                                ma = fmaf((float)mrow[offA + k], a.pD, eta * s_ef[k]);
-                                mb = fmaf((float)mrow[offB + k], a.pD, etb * s_ef[k]);
+                                const unsigned pk = __float_as_uint(mka[q]);
+                                ma = fmaf((float)(pk & 0xFFFFu), a.pD, eta * s_ef[k]);
+                                mb = fmaf((float)(pk >> 16), a.pD, etb * s_ef[k]);
                             }
                             if (!vb) mb = 0.f;
                             const float s = 0.5f * (ma + mb), d = 0.5f * (ma - mb);
@@ -801,12 +852,16 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
         const float* xrow = a.x + (long long)c * g.in_stride;
         const int t0 = run * a.run;
         const int t1 = min(t0 + a.run, g.T);
+        float nx[2 * HR];
+        bool have_nx = false;
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
-            load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, true, vb);
-            if (t + 2 < t1) prefetch_next_pair<HR>(xrow, base + 2LL * H, i1, g.Lp, g.n_total, lane);
+            load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, have_nx);
+            have_nx = (t + 2 < t1) && pair_window_interior<HR>(base, i1, g.Lp, g.n_total) &&
+                      pair_window_interior<HR>(base + 2LL * H, i1, g.Lp, g.n_total);
+            if (have_nx) load_new_rows<HR>(nx, xrow, base + 2LL * H, i1, lane);
             warp_fft1024(re, im, tile, s_tw, lane);
             float* dstA = a.mag + ((long long)ul * g.T + t) * kFPad;
 #pragma unroll
