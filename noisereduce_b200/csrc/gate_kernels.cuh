@@ -256,15 +256,14 @@ __global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
         for (int q = 0; q < kFW; ++q) mx[q] = 0.f;
 
         float nx[2 * HR];
-        bool have_nx = false;
+#pragma unroll
+        for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
-            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, have_nx);
-            have_nx = (t + 2 < t1) && pair_window_interior<HR>(base, i1, g.Lp, g.n_total) &&
-                      pair_window_interior<HR>(base + 2LL * H, i1, g.Lp, g.n_total);
-            if (have_nx) load_new_rows<HR>(nx, xrow, base + 2LL * H, i1, lane);
+            // (measured: pre-loading the next pair's rows costs k1 more bookkeeping than it hides)
+            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
             const float S = sqrtf(warp_sum(e));
             warp_fft1024(re, im, tile, s_tw, lane);
 
@@ -853,15 +852,13 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
         const int t0 = run * a.run;
         const int t1 = min(t0 + a.run, g.T);
         float nx[2 * HR];
-        bool have_nx = false;
+#pragma unroll
+        for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
-            load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, have_nx);
-            have_nx = (t + 2 < t1) && pair_window_interior<HR>(base, i1, g.Lp, g.n_total) &&
-                      pair_window_interior<HR>(base + 2LL * H, i1, g.Lp, g.n_total);
-            if (have_nx) load_new_rows<HR>(nx, xrow, base + 2LL * H, i1, lane);
+            load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
             warp_fft1024(re, im, tile, s_tw, lane);
             float* dstA = a.mag + ((long long)ul * g.T + t) * kFPad;
 #pragma unroll

@@ -48,3 +48,25 @@ def sharded_reduce_noise(dg, x_local: torch.Tensor, rank: int, world: int, gathe
     full = torch.empty((world * x_local.shape[0], x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
     dist.all_gather_into_tensor(full, y_local, group=group)
     return full
+
+
+def sharded_run_overlapped(dg, x_local: torch.Tensor, out_local: torch.Tensor, gathered: torch.Tensor, world: int,
+                           comm_stream, groups: int = 8, group=None):
+    """Denoise this rank's channels group by group and all-gather each finished group on `comm_stream`
+    while the next group is being computed.  `gathered` is the final [world*C, N] waveform in channel
+    order; each group's all-gather writes rank r's rows straight into gathered[r*C + g0 : r*C + g1].
+    Thresholds must already be set (chained_noise_stats)."""
+    C, N = x_local.shape
+    g3 = gathered.view(world, C, N)
+    gs = (C + groups - 1) // groups
+    cur = torch.cuda.current_stream()
+    for g0 in range(0, C, gs):
+        g1 = min(C, g0 + gs)
+        dg.run(x_local[g0:g1], out_local[g0:g1])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        comm_stream.wait_event(ev)
+        with torch.cuda.stream(comm_stream):
+            dist.all_gather([g3[r, g0:g1] for r in range(world)], out_local[g0:g1], group=group)
+    cur.wait_stream(comm_stream)
+    return gathered
