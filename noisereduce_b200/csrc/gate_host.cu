@@ -813,7 +813,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 K1Args a1{};
                 a1.g = g; a1.tb = tb; a1.x = xb; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
                 {
-                    long long want = (long long)resident * kWarps * 4;
+                    long long want = (long long)h->num_sm * B200_K1_MINBLOCKS * kWarps * 4;
                     long long run = ((long long)nu * g.T + want - 1) / want;
                     run = std::max(8LL, std::min(64LL, run));
                     run += run & 1;
@@ -821,7 +821,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a1.n_runs = (g.T + a1.run - 1) / a1.run;
                 }
                 const long long items1 = (long long)nu * a1.n_runs;
-                B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, resident)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
+                B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, h->num_sm * B200_K1_MINBLOCKS)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
                 B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
                             (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
             }

@@ -33,6 +33,9 @@ constexpr int kFW = (kF + 31) / 32; // 17 mask words per frame
 constexpr int kFPad = kFW * 32;     // 544: padded bin count (tables, mask row pitch)
 constexpr int kWarps = 4;           // warps per CTA for k1/k2 (each warp is independent)
 constexpr int kThreads = kWarps * 32;
+#ifndef B200_K1_MINBLOCKS
+#define B200_K1_MINBLOCKS 4          // k1 fits 128 registers: 16 warps per SM
+#endif
 
 struct Geom {
     int H;                  // hop
@@ -215,7 +218,7 @@ struct K1Args {
 constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats + kWarps * 2 * kFW + 8; }
 
 template <int HR>
-__global__ void __launch_bounds__(kThreads, 3) k1_analyze(const K1Args a) {
+__global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const K1Args a) {
     B200_DYN_SMEM(float, smem);
     float* s_wa = smem;
     float2* s_tw = reinterpret_cast<float2*>(smem + kN);
@@ -477,8 +480,11 @@ struct SmoothPArgs {
 constexpr int kSmoothGroups = kFPad / 4;          // 136 threads per unit
 constexpr int kSmoothUnits = 4;
 constexpr int kSmoothThreads = kSmoothGroups * kSmoothUnits;   // 544
+constexpr int kSmoothBatch = 4;                    // frames per barrier
 template <int NTW> __host__ __device__ constexpr int smoothp_rowbytes() { return kFPad + 4 * (NTW + 2) + 64; }
-template <int NTW> __host__ __device__ constexpr int smoothp_smem_bytes() { return 2 * kSmoothUnits * smoothp_rowbytes<NTW>(); }
+template <int NTW> __host__ __device__ constexpr int smoothp_smem_bytes() {
+    return 2 * kSmoothBatch * kSmoothUnits * smoothp_rowbytes<NTW>();
+}
 
 __device__ __forceinline__ unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
 #ifdef B200_CUSIM_BUILD
@@ -492,7 +498,8 @@ __device__ __forceinline__ unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
 template <int NTW>
 __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPArgs a) {
     constexpr int RB = smoothp_rowbytes<NTW>();
-    B200_DYN_SMEM(unsigned char, s_raw);                      // [2][4][RB]
+    constexpr int NB = kSmoothBatch;
+    B200_DYN_SMEM(unsigned char, s_raw);                      // [2][NB][4 units][RB]
     const int tid = threadIdx.x;
     const int ug = tid / kSmoothGroups, i = tid - ug * kSmoothGroups;
     const int ul = blockIdx.y * kSmoothUnits + ug;
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPA
     if (t_begin >= a.tf_hi) return;
     const int t_end = min(t_begin + a.strip, a.tf_hi);
     const int nt = a.nt, nf = a.nf, aa = nt + 1;
-    for (int k = tid; k < 2 * kSmoothUnits * RB / 4; k += kSmoothThreads) reinterpret_cast<unsigned*>(s_raw)[k] = 0u;
+    for (int k = tid; k < 2 * NB * kSmoothUnits * RB / 4; k += kSmoothThreads) reinterpret_cast<unsigned*>(s_raw)[k] = 0u;
     __syncthreads();
 
     const int w = i >> 3, sh = (i & 7) * 4;
@@ -513,49 +520,69 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPA
     for (int m = 0; m < NTW; ++m) taps[m] = a.taps[m];
 
     const int tau_s = t_begin - nt;                 // first frame fed into the recurrence
+    const int tau_e = t_end - 1 + nt;               // last one
     unsigned d1b = 0x10101010u, s2 = 0u;
     int par = 0;
-    for (int tau = tau_s; tau <= t_end - 1 + nt; ++tau) {
-        unsigned na = 0u, nb = 0u, nc = 0u;
-        if (active) {
-            const int ta = tau, tb = tau - aa, tc = tau - 2 * aa;
-            if (ta >= 0 && ta < a.T) na = ((__ldg(bp + (long long)ta * kFW) >> sh) & 0xFu) | fl;
-            if (tb >= tau_s && tb >= 0 && tb < a.T) nb = ((__ldg(bp + (long long)tb * kFW) >> sh) & 0xFu) | fl;
-            if (tc >= tau_s && tc >= 0 && tc < a.T) nc = ((__ldg(bp + (long long)tc * kFW) >> sh) & 0xFu) | fl;
-        }
+    // warm-up: the first 2 nt frames only feed the recurrence (no output yet)
+    auto nib = [&](int t) -> unsigned {
+        return (active && t >= tau_s && t >= 0 && t < a.T) ? (((__ldg(bp + (long long)t * kFW) >> sh) & 0xFu) | fl) : 0u;
+    };
+    auto advance = [&](unsigned na, unsigned nb, unsigned nc) {
         const unsigned ea = (na * 0x00204081u) & 0x01010101u;
         const unsigned eb = (nb * 0x00204081u) & 0x01010101u;
         const unsigned ec = (nc * 0x00204081u) & 0x01010101u;
         d1b = d1b + ea + ec - 2u * eb;
         s2 = s2 + d1b - 0x10101010u;
-        const int t_out = tau - nt;
-        if (t_out < t_begin) continue;              // CTA-uniform
-        unsigned char* row = s_raw + (par * kSmoothUnits + ug) * RB;
-        row[nf + 4 * i + 0] = (unsigned char)(s2 & 0xFFu);
-        row[nf + 4 * i + 1] = (unsigned char)((s2 >> 8) & 0xFFu);
-        row[nf + 4 * i + 2] = (unsigned char)((s2 >> 16) & 0xFFu);
-        row[nf + 4 * i + 3] = (unsigned char)(s2 >> 24);
-        __syncthreads();
-        const unsigned* rw = reinterpret_cast<const unsigned*>(row) + i;
-        unsigned wv[NTW + 1];
+    };
+    int tau = tau_s;
+    for (; tau < t_begin + nt; ++tau) advance(nib(tau), nib(tau - aa), nib(tau - 2 * aa));
+    // steady state: NB output frames per barrier; all bit loads of a batch are issued up front
+    for (; tau <= tau_e; tau += NB) {
+        unsigned na[NB], nb[NB], nc[NB];
 #pragma unroll
-        for (int m = 0; m <= NTW; ++m) wv[m] = rw[m];
-        unsigned o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned acc = 0u;
-#pragma unroll
-            for (int m = 0; m < NTW; ++m) {
-                const unsigned win = (j == 0) ? wv[m] : __funnelshift_r(wv[m], wv[m + 1], 8 * j);
-                acc = dp4a_u(win, taps[m], acc);
-            }
-            o[j] = acc;
+        for (int j = 0; j < NB; ++j) {
+            const int tj = tau + j;
+            const bool live = tj <= tau_e;
+            na[j] = live ? nib(tj) : 0u;
+            nb[j] = live ? nib(tj - aa) : 0u;
+            nc[j] = live ? nib(tj - 2 * aa) : 0u;
         }
-        if (active) {
-            uint2 pk;
-            pk.x = o[0] | (o[1] << 16);
-            pk.y = o[2] | (o[3] << 16);
-            *reinterpret_cast<uint2*>(outp + (long long)t_out * kFPad) = pk;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            advance(na[j], nb[j], nc[j]);
+            unsigned char* row = s_raw + ((par * NB + j) * kSmoothUnits + ug) * RB;
+            row[nf + 4 * i + 0] = (unsigned char)(s2 & 0xFFu);
+            row[nf + 4 * i + 1] = (unsigned char)((s2 >> 8) & 0xFFu);
+            row[nf + 4 * i + 2] = (unsigned char)((s2 >> 16) & 0xFFu);
+            row[nf + 4 * i + 3] = (unsigned char)(s2 >> 24);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int t_out = tau + j - nt;
+            if (tau + j > tau_e) break;
+            const unsigned char* row = s_raw + ((par * NB + j) * kSmoothUnits + ug) * RB;
+            const unsigned* rw = reinterpret_cast<const unsigned*>(row) + i;
+            unsigned wv[NTW + 1];
+#pragma unroll
+            for (int m = 0; m <= NTW; ++m) wv[m] = rw[m];
+            unsigned o[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                unsigned acc = 0u;
+#pragma unroll
+                for (int m = 0; m < NTW; ++m) {
+                    const unsigned win = (jj == 0) ? wv[m] : __funnelshift_r(wv[m], wv[m + 1], 8 * jj);
+                    acc = dp4a_u(win, taps[m], acc);
+                }
+                o[jj] = acc;
+            }
+            if (active) {
+                uint2 pk;
+                pk.x = o[0] | (o[1] << 16);
+                pk.y = o[2] | (o[3] << 16);
+                *reinterpret_cast<uint2*>(outp + (long long)t_out * kFPad) = pk;
+            }
         }
         par ^= 1;
     }
