@@ -166,6 +166,10 @@ def main():
                           + (f", x{n_gpus} GPUs: 64 channels per GPU" if n_gpus > 1 else ""),
               "channels_per_gpu": C_PER_GPU, "samples_per_channel": int(args.minutes * 60 * SR),
               "chunk_size": 600000, "padding": 30000, "l2_policy": "inputs (7.4 GB) larger than L2"}
+    if n_gpus > 1:
+        config["collective"] = ("one all-gather of the final [64*N, 28.8M] float32 waveform, issued per 8-channel group so "
+                                "NVLink traffic overlaps the next group's kernels; 16 SMs reserved for NCCL")
+        config["all_gather_bytes_received_per_rank"] = (n_gpus - 1) * C_PER_GPU * int(args.minutes * 60 * SR) * 4
 
     if args.impl == "reference":
         if rank != 0:
@@ -197,7 +201,8 @@ def main():
 
     x = synth_device(torch, C, n, rank * C, device)
     out = torch.empty_like(x)
-    dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256)
+    # multi-GPU: the persistent grids leave 16 SMs free so the NCCL all-gather kernels run concurrently
+    dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256, reserve_sms=16 if world > 1 else 0)
     # noise statistics once (stationary.py:61-81): the reference's sequential channel mean, chained over ranks
     if world == 1:
         dg.noise_stats(x)

@@ -60,6 +60,8 @@ typedef struct b200gate_params {
     int32_t n_movemean;         /* torch surface, non-stationary                                 */
     int32_t debug_guard_scale;  /* tests only: multiplies the FP32 guard band (0 = 1x), forcing more
                                  * bins through the FP64 re-decision path                          */
+    int32_t reserve_sms;        /* SMs the persistent grids leave free (for a concurrent NCCL collective) */
+    int32_t reserved1;
     int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
     int64_t padding;
     double sr;

@@ -349,6 +349,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     cudaGetDevice(&dev);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->num_sm = prop.multiProcessorCount;
+    if (p->reserve_sms > 0 && p->reserve_sms < h->num_sm) h->num_sm -= p->reserve_sms;   // leave room for NCCL
     int rc = build_static_tables(h);
     if (rc == B200GATE_OK) {
         e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));

@@ -39,7 +39,7 @@ def test_params_struct_layout_matches_header():
     body = src[src.index("typedef struct b200gate_params {"): src.index("} b200gate_params;")]
     c_names = re.findall(r"^\s*(?:int32_t|int64_t|double)\s+([a-z0-9_]+);", body, flags=re.M)
     assert names == c_names
-    assert ctypes.sizeof(_cabi.Params) == 12 * 4 + 2 * 8 + 8 * 8
+    assert ctypes.sizeof(_cabi.Params) == 14 * 4 + 2 * 8 + 8 * 8
     names = [f for f, _ in _cabi.Stats._fields_]
     body = src[src.index("typedef struct b200gate_stats {"): src.index("} b200gate_stats;")]
     c_names = []
