@@ -70,3 +70,42 @@ def sharded_run_overlapped(dg, x_local: torch.Tensor, out_local: torch.Tensor, g
             dist.all_gather([g3[r, g0:g1] for r in range(world)], out_local[g0:g1], group=group)
     cur.wait_stream(comm_stream)
     return gathered
+
+
+# ---- interleaved channel ownership: zero-copy, overlappable gathers --------------------------------
+def gathered_noise_stats(dg, x_local: torch.Tensor, rank: int, world: int, group=None):
+    """Ownership: global channel c * world + rank.  Every rank gathers the (small) noise clip of all
+    channels, orders it globally and runs the ordinary single-process noise statistics on it, so the
+    thresholds are exactly those of one process holding all channels (stationary.py:61-81)."""
+    p = dg.gate.params
+    C, N = x_local.shape
+    n = N
+    if p.clip_noise and p.chunk_size > 0 and n > p.chunk_size:
+        n = int(p.chunk_size)
+    clip = x_local[:, :n].contiguous()
+    allc = torch.empty((world, C, n), dtype=clip.dtype, device=clip.device)
+    dist.all_gather_into_tensor(allc.view(-1), clip.view(-1), group=group)
+    ordered = allc.permute(1, 0, 2).reshape(C * world, n).contiguous()      # row c*world + r
+    dg.noise_stats(ordered)
+    return ordered
+
+
+def interleaved_run_overlapped(dg, x_local: torch.Tensor, out_local: torch.Tensor, gathered: torch.Tensor, world: int,
+                               comm_stream, groups: int = 8, group=None):
+    """gathered: [C, world, N] == the final [C*world, N] waveform with global channel c*world + rank.
+    Each finished local channel is all-gathered straight into gathered[c] (contiguous, zero-copy) on
+    `comm_stream` while the next channel group is being computed."""
+    C, N = x_local.shape
+    gs = (C + groups - 1) // groups
+    cur = torch.cuda.current_stream()
+    for g0 in range(0, C, gs):
+        g1 = min(C, g0 + gs)
+        dg.run(x_local[g0:g1], out_local[g0:g1])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        comm_stream.wait_event(ev)
+        with torch.cuda.stream(comm_stream):
+            for c in range(g0, g1):
+                dist.all_gather_into_tensor(gathered[c].view(-1), out_local[c], group=group)
+    cur.wait_stream(comm_stream)
+    return gathered

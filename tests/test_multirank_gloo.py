@@ -27,6 +27,26 @@ def _free_port():
     return p
 
 
+def _worker_interleaved(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    from noisereduce_b200.device import DeviceGate
+    from noisereduce_b200.parallel import gathered_noise_stats
+    from tests.cusim_util import cusim_library
+    from tests.synth_host import synth_small
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    y = torch.from_numpy(synth_small(C=4, n=6000))
+    x_local = y[rank::world].contiguous()                 # global channel c * world + rank
+    dg = DeviceGate(sr=SR, stationary=True, lib=cusim_library(), **KW)
+    gathered_noise_stats(dg, x_local, rank, world)
+    out = dg.run(x_local)
+    full = torch.empty((x_local.shape[0], world, x_local.shape[1]))
+    for c in range(x_local.shape[0]):
+        dist.all_gather_into_tensor(full[c].view(-1), out[c])
+    if rank == 0:
+        np.savez(result_path, full=full.reshape(-1, x_local.shape[1]).numpy(), thr=dg.gate.noise_threshold())
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, result_path):
     sys.path.insert(0, ROOT)
     from noisereduce_b200.device import DeviceGate
@@ -62,3 +82,18 @@ def test_two_ranks_equal_one_process(tmp_path):
     thr = dg.gate.noise_threshold()
     assert np.array_equal(r["thr0"], thr) and np.array_equal(r["thr1"], thr)     # bit-equal thresholds
     assert np.array_equal(r["full"], single)                                    # identical waveform
+
+
+def test_interleaved_ownership_equals_one_process(tmp_path):
+    from noisereduce_b200.device import DeviceGate
+    from tests.cusim_util import cusim_library
+    from tests.synth_host import synth_small
+    cusim_library()
+    result = str(tmp_path / "res2.npz")
+    mp.spawn(_worker_interleaved, args=(2, _free_port(), result), nprocs=2, join=True)
+    r = np.load(result)
+    y = torch.from_numpy(synth_small(C=4, n=6000))
+    dg = DeviceGate(sr=SR, stationary=True, lib=cusim_library(), **KW)
+    dg.noise_stats(y)
+    assert np.array_equal(r["thr"], dg.gate.noise_threshold())
+    assert np.array_equal(r["full"], dg.run(y).numpy())
