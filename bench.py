@@ -167,9 +167,8 @@ def main():
               "channels_per_gpu": C_PER_GPU, "samples_per_channel": int(args.minutes * 60 * SR),
               "chunk_size": 600000, "padding": 30000, "l2_policy": "inputs (7.4 GB) larger than L2"}
     if n_gpus > 1:
-        config["collective"] = ("all-gather of the final [64*N, 28.8M] float32 waveform (interleaved channel ownership, "
-                                "zero-copy per channel), issued as each 8-channel group finishes so NVLink traffic "
-                                "overlaps the next group's kernels; 16 SMs reserved for NCCL")
+        config["collective"] = ("all-gather of the final [64*N, 28.8M] float32 waveform, issued as each 8-channel group "
+                                "finishes so NVLink traffic overlaps the next group's kernels; 16 SMs reserved for NCCL")
         config["all_gather_bytes_received_per_rank"] = (n_gpus - 1) * C_PER_GPU * int(args.minutes * 60 * SR) * 4
 
     if args.impl == "reference":
@@ -208,10 +207,9 @@ def main():
     if world == 1:
         dg.noise_stats(x)
     else:
-        from noisereduce_b200.parallel import gathered_noise_stats
-        gathered_noise_stats(dg, x, rank, world)
-    # channel ownership is interleaved (global channel c*world + rank): [C, world, n] IS the final waveform
-    gathered = torch.empty((C, world, n), dtype=torch.float32, device=device) if world > 1 else None
+        from noisereduce_b200.parallel import chained_noise_stats
+        chained_noise_stats(dg, x, rank, world)
+    gathered = torch.empty((world * C, n), dtype=torch.float32, device=device) if world > 1 else None
     comm_stream = torch.cuda.Stream() if world > 1 else None
     acc_stats = {"k1_ms": 0.0, "smooth_ms": 0.0, "k2_ms": 0.0, "kernel_launches": 0}
 
@@ -224,8 +222,10 @@ def main():
         else:
             # the path's single collective -- the all-gather of the final waveform -- is issued per
             # channel group so NVLink traffic overlaps the kernels of the next group
-            from noisereduce_b200.parallel import interleaved_run_overlapped
-            interleaved_run_overlapped(dg, x, out, gathered, world, comm_stream, groups=8)
+            # (measured on 2 and 4 B200s: this beats both one monolithic all-gather after the kernels and
+            #  64 per-channel zero-copy gathers -- profiles/r01_scaling_notes.md)
+            from noisereduce_b200.parallel import sharded_run_overlapped
+            sharded_run_overlapped(dg, x, out, gathered, world, comm_stream, groups=8)
 
     def barrier():
         if world > 1:
