@@ -52,11 +52,37 @@ __host__ __device__ __forceinline__ constexpr float sin32(int m) {
          : 0.19509032201612826785f;
 }
 
+// ---- packed FP32 pairs (Blackwell add/sub/mul/fma .f32x2: one instruction, two lanes of a 64-bit register) ----
+// The FP32 pipe already runs scalar FADD/FFMA at ~124 of 128 lanes/clk/SM (profiles/r01_g_f32x2_microbench.txt),
+// so packing does not raise FLOP/s; it halves the ISSUE slots (and instruction bytes) of the butterfly network,
+// which is what these instruction-issue / instruction-fetch bound kernels are short of.
+#ifdef B200_CUSIM_BUILD
+struct f2 { float lo, hi; };
+__device__ __forceinline__ f2 f2_pack(float a, float b) { return f2{a, b}; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& a, float& b) { a = v.lo; b = v.hi; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { return f2{a.lo + b.lo, a.hi + b.hi}; }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { return f2{a.lo - b.lo, a.hi - b.hi}; }
+__device__ __forceinline__ f2 f2_mul_s(f2 a, float c) { return f2{a.lo * c, a.hi * c}; }
+__device__ __forceinline__ f2 f2_fma_s(f2 a, float c, f2 acc) { return f2{fmaf(a.lo, c, acc.lo), fmaf(a.hi, c, acc.hi)}; }
+#else
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_pack(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_mul_s(f2 a, float c) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(f2_pack(c, c))); return r; }
+__device__ __forceinline__ f2 f2_fma_s(f2 a, float c, f2 acc) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(f2_pack(c, c)), "l"(acc)); return r; }
+#endif
+
+#ifndef B200_PACKED_DFT
+#define B200_PACKED_DFT 1
+#endif
+
 // 32-point DFT over the register slots of one thread (radix-2 decimation in frequency).
 //   BREV_IN == false: logical input i in slot i          -> frequency q in slot brev5(q)
 //   BREV_IN == true : logical input i in slot brev5(i)   -> frequency q in slot q
 template <bool BREV_IN>
-__device__ __forceinline__ void dft32(float (&re)[32], float (&im)[32]) {
+__device__ __forceinline__ void dft32_scalar(float (&re)[32], float (&im)[32]) {
 #pragma unroll
     for (int len = 32; len >= 2; len >>= 1) {
         const int half = len >> 1;
@@ -92,6 +118,74 @@ __device__ __forceinline__ void dft32(float (&re)[32], float (&im)[32]) {
             }
         }
     }
+}
+
+// Same network, natural slots in -> brev5 slots out.  Stage 1 (partners i, i+16) is scalar; its outputs are
+// paired (slot i, slot i+16) so that stages 2..5, which treat both halves identically (same partner offsets, same
+// twiddles), run on packed registers: 4 x 8 packed butterflies instead of 4 x 16 scalar ones.
+__device__ __forceinline__ void dft32_packed(float (&re)[32], float (&im)[32]) {
+    constexpr float kH = 0.70710678118654752440f;
+    f2 Pr[16], Pi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float ar = re[i], ai = im[i], br = re[i + 16], bi = im[i + 16];
+        const float sr = ar + br, si = ai + bi, dr = ar - br, di = ai - bi;
+        float tr, ti;
+        if (i == 0) { tr = dr; ti = di; }
+        else if (i == 8) { tr = di; ti = -dr; }
+        else if (i == 4) { tr = (dr + di) * kH; ti = (di - dr) * kH; }
+        else if (i == 12) { tr = (di - dr) * kH; ti = -(dr + di) * kH; }
+        else { const float c = cos32(i), s = sin32(i); tr = fmaf(di, s, dr * c); ti = fmaf(-dr, s, di * c); }
+        Pr[i] = f2_pack(sr, tr);
+        Pi[i] = f2_pack(si, ti);
+    }
+#pragma unroll
+    for (int len = 16; len >= 2; len >>= 1) {
+        const int half = len >> 1, step = 32 / len;
+#pragma unroll
+        for (int blk = 0; blk < 16; blk += len) {
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const int ia = blk + i, ib = blk + i + half, m = i * step;
+                const f2 ar = Pr[ia], ai = Pi[ia], br = Pr[ib], bi = Pi[ib];
+                Pr[ia] = f2_add(ar, br);
+                Pi[ia] = f2_add(ai, bi);
+                if (m == 0) {
+                    Pr[ib] = f2_sub(ar, br);
+                    Pi[ib] = f2_sub(ai, bi);
+                } else if (m == 8) {                           // * (-i): (di, -dr)
+                    Pr[ib] = f2_sub(ai, bi);
+                    Pi[ib] = f2_sub(br, ar);
+                } else if (m == 4) {
+                    const f2 dr = f2_sub(ar, br), di = f2_sub(ai, bi);
+                    Pr[ib] = f2_mul_s(f2_add(dr, di), kH);
+                    Pi[ib] = f2_mul_s(f2_sub(di, dr), kH);
+                } else if (m == 12) {
+                    const f2 dr = f2_sub(ar, br), di = f2_sub(ai, bi);
+                    Pr[ib] = f2_mul_s(f2_sub(di, dr), kH);
+                    Pi[ib] = f2_mul_s(f2_add(dr, di), -kH);
+                } else {
+                    const f2 dr = f2_sub(ar, br), di = f2_sub(ai, bi);
+                    const float c = cos32(m), s = sin32(m);
+                    Pr[ib] = f2_fma_s(di, s, f2_mul_s(dr, c));
+                    Pi[ib] = f2_fma_s(dr, -s, f2_mul_s(di, c));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        f2_unpack(Pr[i], re[i], re[i + 16]);
+        f2_unpack(Pi[i], im[i], im[i + 16]);
+    }
+}
+
+template <bool BREV_IN>
+__device__ __forceinline__ void dft32(float (&re)[32], float (&im)[32]) {
+#if B200_PACKED_DFT
+    if (!BREV_IN) { dft32_packed(re, im); return; }
+#endif
+    dft32_scalar<BREV_IN>(re, im);
 }
 
 // Twiddle by exp(-2 pi i lane q / 1024) and transpose lanes <-> slots through shared memory.
