@@ -89,27 +89,6 @@ int fail(b200gate_handle* h, int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                           \
     } while (0)
 
-// Inter-pass twiddles exp(-2 pi i lane q / 1024) of the 32 x 32 warp FFT, in the layout warp_fft1024 reads.
-void fill_twiddles(std::vector<float2>& tw) {
-    tw.resize(32 * 32);
-    auto cw = [](int l, int q) {
-        const long double th = 2.0L * M_PIl * (long double)(l * q) / 1024.0L;
-        return make_float2((float)cosl(th), (float)(-sinl(th)));
-    };
-#if B200_PACKED_DFT
-    // float4 entry (i, lane) = (cos q0, cos q1, -sin q0, -sin q1), q0 = brev5(i), q1 = q0 + 1
-    for (int i = 0; i < 16; ++i)
-        for (int l = 0; l < 32; ++l) {
-            const float2 a = cw(l, brev5(i)), b = cw(l, brev5(i) + 1);
-            tw[(i * 32 + l) * 2 + 0] = make_float2(a.x, b.x);
-            tw[(i * 32 + l) * 2 + 1] = make_float2(a.y, b.y);
-        }
-#else
-    for (int q = 0; q < 32; ++q)
-        for (int l = 0; l < 32; ++l) tw[q * 32 + l] = cw(l, q);
-#endif
-}
-
 template <class T>
 int upload(b200gate_handle* h, T** dptr, const std::vector<T>& v) {
     if (!*dptr) CK(h, cudaMalloc((void**)dptr, v.size() * sizeof(T)));
@@ -154,7 +133,11 @@ int build_static_tables_2k(b200gate_handle* h) {
         const float v = (float)(sacc > 1e-10 ? 1.0 / sacc : 1.0);
         if (r & 1) invn2[r >> 1].y = v; else invn2[r >> 1].x = v;
     }
-    fill_twiddles(tw);
+    for (int q = 0; q < 32; ++q)
+        for (int l = 0; l < 32; ++l) {
+            const long double th = 2.0L * M_PIl * (long double)(l * q) / 1024.0L;
+            tw[q * 32 + l] = make_float2((float)cosl(th), (float)(-sinl(th)));
+        }
     int rc;
     if ((rc = upload(h, &h->d_wa2, wa2))) return rc;
     if ((rc = upload(h, &h->d_ws2, ws2))) return rc;
@@ -189,7 +172,11 @@ int build_static_tables(b200gate_handle* h) {
         invn[r] = (float)(s > 1e-10 ? 1.0 / s : 1.0);
     }
     std::vector<float2> tw(32 * 32);
-    fill_twiddles(tw);
+    for (int q = 0; q < 32; ++q)
+        for (int l = 0; l < 32; ++l) {
+            const long double th = 2.0L * M_PIl * (long double)(l * q) / 1024.0L;
+            tw[q * 32 + l] = make_float2((float)cosl(th), (float)(-sinl(th)));
+        }
     std::vector<double2> cs(N);
     for (int m = 0; m < N; ++m) {
         const long double th = 2.0L * M_PIl * (long double)m / (long double)N;

@@ -63,8 +63,6 @@ __device__ __forceinline__ void f2_unpack(f2 v, float& a, float& b) { a = v.lo; 
 __device__ __forceinline__ f2 f2_add(f2 a, f2 b) { return f2{a.lo + b.lo, a.hi + b.hi}; }
 __device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { return f2{a.lo - b.lo, a.hi - b.hi}; }
 __device__ __forceinline__ f2 f2_mul_s(f2 a, float c) { return f2{a.lo * c, a.hi * c}; }
-__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
-__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { return f2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
 __device__ __forceinline__ f2 f2_fma_s(f2 a, float c, f2 acc) { return f2{fmaf(a.lo, c, acc.lo), fmaf(a.hi, c, acc.hi)}; }
 #else
 typedef unsigned long long f2;
@@ -73,8 +71,6 @@ __device__ __forceinline__ void f2_unpack(f2 v, float& a, float& b) { asm("mov.b
 __device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 f2_mul_s(f2 a, float c) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(f2_pack(c, c))); return r; }
-__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f2 f2_fma_s(f2 a, float c, f2 acc) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(f2_pack(c, c)), "l"(acc)); return r; }
 #endif
 
@@ -127,8 +123,9 @@ __device__ __forceinline__ void dft32_scalar(float (&re)[32], float (&im)[32]) {
 // Same network, natural slots in -> brev5 slots out.  Stage 1 (partners i, i+16) is scalar; its outputs are
 // paired (slot i, slot i+16) so that stages 2..5, which treat both halves identically (same partner offsets, same
 // twiddles), run on packed registers: 4 x 8 packed butterflies instead of 4 x 16 scalar ones.
-__device__ __forceinline__ void dft32_packed_core(const float (&re)[32], const float (&im)[32], f2 (&Pr)[16], f2 (&Pi)[16]) {
+__device__ __forceinline__ void dft32_packed(float (&re)[32], float (&im)[32]) {
     constexpr float kH = 0.70710678118654752440f;
+    f2 Pr[16], Pi[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const float ar = re[i], ai = im[i], br = re[i + 16], bi = im[i + 16];
@@ -176,11 +173,6 @@ __device__ __forceinline__ void dft32_packed_core(const float (&re)[32], const f
             }
         }
     }
-}
-// pack i holds slots (i, i+16) = frequencies (brev5(i), brev5(i) + 1)
-__device__ __forceinline__ void dft32_packed(float (&re)[32], float (&im)[32]) {
-    f2 Pr[16], Pi[16];
-    dft32_packed_core(re, im, Pr, Pi);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         f2_unpack(Pr[i], re[i], re[i + 16]);
@@ -227,64 +219,17 @@ __device__ __forceinline__ void twiddle_transpose(float (&re)[32], float (&im)[3
     __syncwarp();
 }
 
-// Packed twiddle + transpose (pass 1 -> pass 2).  tw4: [16][32] float4, entry (i, lane) =
-// (cos a0, cos a1, -sin a0, -sin a1) with a_j = 2 pi lane (brev5(i) + j) / 1024 -- the twiddles of the two
-// frequencies pack i carries.  Shares the table's 8 KB with the scalar layout (same bytes, other order).
-__device__ __forceinline__ void twiddle_transpose_packed(const f2 (&Pr)[16], const f2 (&Pi)[16], float (&re)[32],
-                                                         float (&im)[32], float* __restrict__ tile,
-                                                         const float4* __restrict__ tw4, int lane) {
-    f2 Tr[16], Ti[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float4 w = tw4[i * 32 + lane];
-        const f2 wr = f2_pack(w.x, w.y), wi = f2_pack(w.z, w.w);
-        Tr[i] = f2_sub(f2_mul(Pr[i], wr), f2_mul(Pi[i], wi));          // a wr - b wi
-        Ti[i] = f2_fma(Pr[i], wi, f2_mul(Pi[i], wr));                  // a wi + b wr
-    }
-    float* row = tile + lane * 33;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { float lo, hi; f2_unpack(Tr[i], lo, hi); row[brev5(i)] = lo; row[brev5(i) + 1] = hi; }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; ++r) re[r] = tile[r * 33 + lane];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { float lo, hi; f2_unpack(Ti[i], lo, hi); row[brev5(i)] = lo; row[brev5(i) + 1] = hi; }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; ++r) im[r] = tile[r * 33 + lane];
-    __syncwarp();
-}
-
 // Forward 1024-point FFT: input point lane+32r in slot r, output X[lane + 32 q] in slot brev5(q).
 // Both radix-32 passes run through ONE copy of the butterfly network (a 2-trip runtime loop): the
 // kernels are instruction-fetch sensitive (each warp walks its own instruction stream), so code
 // size matters more than the two saved branches.
-// `tw` is the inter-pass twiddle table in the layout of B200_PACKED_DFT (see gate_host.cu).
 __device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], float* __restrict__ tile,
                                              const float2* __restrict__ tw, int lane) {
-#if B200_PACKED_DFT
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        f2 Pr[16], Pi[16];
-        dft32_packed_core(re, im, Pr, Pi);                            // natural slots -> packed (brev order)
-        if (pass == 0) {
-            twiddle_transpose_packed(Pr, Pi, re, im, tile, reinterpret_cast<const float4*>(tw), lane);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                f2_unpack(Pr[i], re[i], re[i + 16]);
-                f2_unpack(Pi[i], im[i], im[i + 16]);
-            }
-        }
-    }
-#else
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         dft32<false>(re, im);                                         // natural slots -> brev slots
         if (pass == 0) twiddle_transpose<true>(re, im, tile, tw, lane);   // brev slots -> natural slots
     }
-#endif
 }
 
 }  // namespace b200
