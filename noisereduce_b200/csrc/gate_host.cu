@@ -59,7 +59,10 @@ struct b200gate_handle {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined host path
     float* d_slab_in[2] = {nullptr, nullptr};
     float* d_slab_out[2] = {nullptr, nullptr};
-    size_t slab_in_bytes[2] = {0, 0}, slab_out_bytes[2] = {0, 0};             // 4 per batch: k1 start, k1 end(+rowfloor), smooth end, k2 end
+    size_t slab_in_bytes[2] = {0, 0}, slab_out_bytes[2] = {0, 0};
+    void* d_slab_raw_in[2] = {nullptr, nullptr};   // int16 / float64 host callers: raw-dtype slabs, converted on device
+    void* d_slab_raw_out[2] = {nullptr, nullptr};
+    size_t slab_raw_in_bytes[2] = {0, 0}, slab_raw_out_bytes[2] = {0, 0};             // 4 per batch: k1 start, k1 end(+rowfloor), smooth end, k2 end
     b200gate_stats stats{};
     // debug taps
     long long dbg_chunk = -1, dbg_channel = -1;
@@ -396,6 +399,8 @@ void b200gate_destroy(b200gate_handle* h) {
     for (int i = 0; i < 2; ++i) {
         if (h->d_slab_in[i]) cudaFree(h->d_slab_in[i]);
         if (h->d_slab_out[i]) cudaFree(h->d_slab_out[i]);
+        if (h->d_slab_raw_in[i]) cudaFree(h->d_slab_raw_in[i]);
+        if (h->d_slab_raw_out[i]) cudaFree(h->d_slab_raw_out[i]);
     }
     delete h;
 }
@@ -590,7 +595,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // Host float32 input that the reference would chunk: stream it through the GPU slab by slab
     // (H2D of slab k+1, kernels of slab k and D2H of slab k-1 overlap on three streams) instead of
     // staging the whole recording -- the role of _read_chunk + the memmap write-back (base.py:130-187).
-    const bool pipelined = !is_device && dtype == B200GATE_F32 && !torch_sem && h->p.chunk_size > 0 &&
+    const bool pipelined = !is_device && !torch_sem && h->p.chunk_size > 0 &&
                            N > h->p.chunk_size && h->p.padding >= h->p.hop_length;
     if (direct || pipelined) {
         x = (const float*)in;
@@ -687,6 +692,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             int rc;
             if ((rc = ensure(h, (void**)&h->d_slab_in[i], &h->slab_in_bytes[i], (size_t)C * slab_w * 4))) return rc;
             if ((rc = ensure(h, (void**)&h->d_slab_out[i], &h->slab_out_bytes[i], (size_t)C * slab_ow * 4))) return rc;
+            if (dtype != B200GATE_F32) {
+                if ((rc = ensure(h, &h->d_slab_raw_in[i], &h->slab_raw_in_bytes[i], (size_t)C * slab_w * es))) return rc;
+                if ((rc = ensure(h, &h->d_slab_raw_out[i], &h->slab_raw_out_bytes[i], (size_t)C * slab_ow * es))) return rc;
+            }
         }
     }
     // carve the workspace into 256-byte aligned sub-buffers (vector stores need natural alignment)
@@ -768,11 +777,20 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
             if (bi >= 2) CK(h, cudaStreamWaitEvent(h->s_h2d, h->pipe_ev[3 * (bi - 2) + 1], 0));   // slab buffer free
-            CK(h, cudaMemcpy2DAsync(h->d_slab_in[ib], (size_t)slab_w * 4, (const float*)in + w0, (size_t)in_stride * 4,
-                                    (size_t)(w1 - w0) * 4, (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
+            void* h2d_dst = dtype == B200GATE_F32 ? (void*)h->d_slab_in[ib] : h->d_slab_raw_in[ib];
+            CK(h, cudaMemcpy2DAsync(h2d_dst, (size_t)slab_w * es, (const char*)in + (size_t)w0 * es, (size_t)in_stride * es,
+                                    (size_t)(w1 - w0) * es, (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
             CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 0], h->s_h2d));
             CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * bi + 0], 0));
             if (bi >= 2) CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * (bi - 2) + 2], 0));         // output buffer drained
+            if (dtype != B200GATE_F32) {                                                           // base.py:140 promotion
+                const int gr = grid_1d((long long)C * (w1 - w0), 256, h->num_sm * 16);
+                if (dtype == B200GATE_I16)
+                    { auto kern_ = k_to_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const short*)h->d_slab_raw_in[ib], h->d_slab_in[ib], (long long)C, (long long)(w1 - w0), (long long)slab_w, (long long)slab_w); }
+                else
+                    { auto kern_ = k_to_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const double*)h->d_slab_raw_in[ib], h->d_slab_in[ib], (long long)C, (long long)(w1 - w0), (long long)slab_w, (long long)slab_w); }
+                ++launches;
+            }
             // virtual row bases so the kernels keep absolute sample indices
             xb = h->d_slab_in[ib] - w0;
             yb = h->d_slab_out[ib] - o0;
@@ -1004,10 +1022,20 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const long long c0 = u0 / C, c1 = c0 + nu / C;
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
+            const void* d2h_src = h->d_slab_out[ib];
+            if (dtype != B200GATE_F32) {                                                           // base.py:218-226 cast back
+                const int gr = grid_1d((long long)C * (o1 - o0), 256, h->num_sm * 16);
+                if (dtype == B200GATE_I16)
+                    { auto kern_ = k_from_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)h->d_slab_out[ib], (short*)h->d_slab_raw_out[ib], (long long)C, (long long)(o1 - o0), (long long)slab_ow, (long long)slab_ow); }
+                else
+                    { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)h->d_slab_out[ib], (double*)h->d_slab_raw_out[ib], (long long)C, (long long)(o1 - o0), (long long)slab_ow, (long long)slab_ow); }
+                ++launches;
+                d2h_src = h->d_slab_raw_out[ib];
+            }
             CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 1], st));
             CK(h, cudaStreamWaitEvent(h->s_d2h, h->pipe_ev[3 * bi + 1], 0));
-            CK(h, cudaMemcpy2DAsync((float*)out + o0, (size_t)out_stride * 4, h->d_slab_out[ib], (size_t)slab_ow * 4,
-                                    (size_t)(o1 - o0) * 4, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
+            CK(h, cudaMemcpy2DAsync((char*)out + (size_t)o0 * es, (size_t)out_stride * es, d2h_src, (size_t)slab_ow * es,
+                                    (size_t)(o1 - o0) * es, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
             CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 2], h->s_d2h));
         }
     }

@@ -184,3 +184,31 @@ def test_torchgate_surface(lib, golden_dir):
         ref = TO.torchgate_forward(xb[r:r + 1].cpu().numpy().astype(np.float64), 16000,
                                    window=torch.hann_window(1024).numpy())
         assert P.relinf(yb[r:r + 1].cpu().numpy(), ref) < 1e-4
+
+
+def test_batching_slabs_and_config5_geometry(lib):
+    """Workspace batching / host slab streaming at realistic sizes, and config-5 chunking (60 s chunks,
+    T = 11485): results must not depend on how units are batched, and must match the oracle."""
+    import noisereduce_b200 as nr
+    sr = 48000
+    rng = np.random.default_rng(1003)
+    n = 6_500_000                                      # > 2 chunks of 2.88 M samples
+    t = np.arange(n) / sr
+    y = (0.05 * rng.standard_normal((2, n)) + 0.25 * ((t % 2.0) < 0.5) * np.sin(2 * np.pi * 660 * t)).astype(np.float32)
+    kw = dict(chunk_size=2_880_000, padding=30000)
+    cfg = O.GateConfig(sr=sr, stationary=True, **kw)
+    res = P.check_stationary(lib, y, cfg, tap_unit=(1, 1))
+    assert res["T"] == 11485
+    _assert_stationary(res)
+    # default chunking, tiny workspace -> many batches / slabs; identical to the one-batch result
+    cfg = O.GateConfig(sr=sr, stationary=True)
+    a = P.check_stationary(lib, y[:, :3_000_000], cfg, tap_unit=(2, 1))
+    b = P.check_stationary(lib, y[:, :3_000_000], cfg, tap_unit=(2, 1), workspace_limit_bytes=8.0e6)
+    _assert_stationary(a)
+    assert b["stats"]["kernel_launches"] > a["stats"]["kernel_launches"]
+    assert np.array_equal(a["out"], b["out"])
+    # int16 host input streams through the raw-dtype slab pipeline
+    yi = (y[:, :2_000_000] * 20000).astype(np.int16)
+    out = nr.reduce_noise(y=yi, sr=sr, stationary=True)
+    ref = O.reduce_noise(yi, sr, cfg=O.GateConfig(sr=sr, stationary=True))
+    assert out.dtype == np.int16 and np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1
