@@ -13,9 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# B200GATE_LIB lets kernel-tuning experiments (scripts/) point at an alternative nvcc build of the same sources;
-# it must still be a CUDA build of libb200gate -- there is no non-CUDA implementation to point it at.
-DEFAULT_LIB = os.environ.get("B200GATE_LIB", os.path.join(_HERE, "libb200gate.so"))
+DEFAULT_LIB = os.path.join(_HERE, "libb200gate.so")
 
 ABI_VERSION = 1
 F32, I16, F64 = 0, 1, 2

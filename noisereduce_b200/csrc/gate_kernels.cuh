@@ -33,9 +33,6 @@ constexpr int kFW = (kF + 31) / 32; // 17 mask words per frame
 constexpr int kFPad = kFW * 32;     // 544: padded bin count (tables, mask row pitch)
 constexpr int kWarps = 4;           // warps per CTA for k1/k2 (each warp is independent)
 constexpr int kThreads = kWarps * 32;
-#ifndef B200_K2_LOCKSTEP
-#define B200_K2_LOCKSTEP 0
-#endif
 #ifndef B200_K1_MINBLOCKS
 #define B200_K1_MINBLOCKS 4          // k1 fits 128 registers: 16 warps per SM
 #endif
@@ -609,7 +606,7 @@ struct K2Args {
     DebugTap dbg;
 };
 
-constexpr int k2_smem_floats(int H) { return 2 * kN + 2 * kN + H + kFPad + kWarps * kExchFloats + 8; }
+constexpr int k2_smem_floats(int H) { return 2 * kN + 2 * kN + H + kFPad + kWarps * kExchFloats; }
 
 // time edge factor of the zero-padded smoothing: sum of the triangle taps that stay inside [0, T)
 __device__ __forceinline__ float time_edge(int t, int T, int nt) {
@@ -646,22 +643,10 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
     const long long n_items = (long long)g.n_units * a.n_runs;
     const bool blend = (a.one_minus_p != 0.f);
 
-#if B200_K2_LOCKSTEP
-    // Lock-step variant: the 4 warps of the CTA walk the pair loop together (one barrier per pair), so
-    // they fetch the same instruction lines at the same time.
-    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_tiles + kWarps * kExchFloats);
-    for (long long item0 = (long long)blockIdx.x * kWarps; item0 < n_items; item0 += (long long)gridDim.x * kWarps) {
-        const long long item = item0 + warp;
-        const bool has_item = item < n_items;
-        const int ul = has_item ? (int)(item / a.n_runs) : 0;
-        const int run = has_item ? (int)(item - (long long)ul * a.n_runs) : 0;
-#else
     for (long long item = (long long)blockIdx.x * kWarps + warp; item < n_items;
          item += (long long)gridDim.x * kWarps) {
-        const bool has_item = true;
         const int ul = (int)(item / a.n_runs);
         const int run = (int)(item - (long long)ul * a.n_runs);
-#endif
         const int u = g.u0 + ul;
         const int ic = u / g.C, c = u - ic * g.C;
         const long long i1 = (long long)ic * g.step - g.pad;
@@ -671,28 +656,18 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         long long jp_hi = g.pad + out_len;
         const long long sig_len = (long long)(g.T - 1) * H;          // istft output length
         if (jp_hi > sig_len) jp_hi = sig_len;                        // beyond it the reference leaves zeros
+        if (jp_hi <= g.pad) continue;
         const long long jlo = g.pad + kN / 2, jhi = jp_hi + kN / 2;
         const int h_lo = (int)(jlo / H), h_hi = (int)((jhi + H - 1) / H);
         const int hs = h_lo + run * a.run;
         const int he = min(hs + a.run, h_hi);
-        const bool work = has_item && jp_hi > g.pad && hs < he;
+        if (hs >= he) continue;
         const int t_start = max(0, hs - (NH - 1));
         const int t_last = min(he - 1, g.T - 1);
         const float* xrow = a.x + (long long)c * g.in_stride;
         float* yrow = a.y + (long long)c * g.out_stride;
         const unsigned short* mrow = FMASK ? nullptr : a.num + (long long)ul * g.T * kFPad;
         const float* frow = FMASK ? a.fmask + (long long)ul * g.T * kFPad : nullptr;
-        const int n_iter = work ? (he - t_start + 1) / 2 : 0;
-#if B200_K2_LOCKSTEP
-        __syncthreads();
-        if (lane == 0) s_cnt[warp] = (unsigned)n_iter;
-        __syncthreads();
-        int n_max = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) n_max = max(n_max, (int)s_cnt[w]);
-#else
-        const int n_max = n_iter;
-#endif
 
         float acc[32 + HR];
 #pragma unroll
@@ -701,12 +676,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
 #pragma unroll
         for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
 
-        for (int it = 0; it < n_max; ++it) {
-#if B200_K2_LOCKSTEP
-            __syncthreads();
-            if (it >= n_iter) continue;
-#endif
-            const int t = t_start + 2 * it;
+        for (int t = t_start; t < he; t += 2) {
             const bool va = (t <= t_last), vb = (t + 1 <= t_last);
             if (va) {                                   // vb implies va
                 const long long base = (long long)t * H - kN / 2;
