@@ -48,7 +48,7 @@ struct b200gate_handle {
     // workspace
     char* d_ws_buf = nullptr;
     size_t ws_bytes = 0;
-    float *d_in = nullptr, *d_out = nullptr;       // staging for host / non-f32 callers
+    void *d_in = nullptr, *d_out = nullptr;        // staging for host callers (kernel dtype)
     size_t in_bytes = 0, out_bytes = 0;
     void* d_raw = nullptr;                         // raw-dtype staging
     size_t raw_bytes = 0;
@@ -57,8 +57,8 @@ struct b200gate_handle {
     std::vector<cudaEvent_t> stage_ev;
     std::vector<cudaEvent_t> pipe_ev;              // 3 per batch (input landed, compute done, output landed)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined host path
-    float* d_slab_in[2] = {nullptr, nullptr};
-    float* d_slab_out[2] = {nullptr, nullptr};
+    void* d_slab_in[2] = {nullptr, nullptr};       // caller-dtype slabs
+    void* d_slab_out[2] = {nullptr, nullptr};
     size_t slab_in_bytes[2] = {0, 0}, slab_out_bytes[2] = {0, 0};
     void* d_slab_raw_in[2] = {nullptr, nullptr};   // int16 / float64 host callers: raw-dtype slabs, converted on device
     void* d_slab_raw_out[2] = {nullptr, nullptr};
@@ -299,7 +299,15 @@ int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, 
     return B200GATE_OK;
 }
 
-void launch_k1n(const Geom& g, const Tables& tb, const float* x, float* mag, const DebugTap& dbg, int resident,
+// run `stmt` with T bound to the kernels' sample type
+#define B200_WITH_DTYPE(dt, ...)                                           \
+    do {                                                                   \
+        if ((dt) == B200GATE_I16) { using T = short; __VA_ARGS__; }        \
+        else if ((dt) == B200GATE_F64) { using T = double; __VA_ARGS__; }  \
+        else { using T = float; __VA_ARGS__; }                             \
+    } while (0)
+
+void launch_k1n(const Geom& g, const Tables& tb, const void* x, int kdt, float* mag, const DebugTap& dbg, int resident,
                 cudaStream_t st) {
     K1nArgs a1{};
     a1.g = g; a1.tb = tb; a1.x = x; a1.mag = mag; a1.dbg = dbg;
@@ -309,8 +317,9 @@ void launch_k1n(const Geom& g, const Tables& tb, const float* x, float* mag, con
     run += run & 1;
     a1.run = (int)run;
     a1.n_runs = (g.T + a1.run - 1) / a1.run;
-    B200_LAUNCH(k1n_magnitude<8>, dim3(grid_1d((long long)g.n_units * a1.n_runs, kWarps, resident)), dim3(kThreads),
-                k1n_smem_floats() * 4, st, a1);
+    B200_WITH_DTYPE(kdt, { auto kern_ = k1n_magnitude<8, T>;
+        B200_LAUNCH(kern_, dim3(grid_1d((long long)g.n_units * a1.n_runs, kWarps, resident)), dim3(kThreads),
+                    k1n_smem_floats() * 4, st, a1); });
 }
 
 }  // namespace
@@ -364,10 +373,13 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
         cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
 #ifndef B200_CUSIM_BUILD
-        cudaFuncSetAttribute(k1_analyze<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats() * 4);
-        cudaFuncSetAttribute(k2_synthesize<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
-        cudaFuncSetAttribute(k2_synthesize<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
-        cudaFuncSetAttribute(k1n_magnitude<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
+        for (int dt = 0; dt < 3; ++dt)
+            B200_WITH_DTYPE(dt, {
+                cudaFuncSetAttribute(k1_analyze<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats() * 4);
+                cudaFuncSetAttribute(k2_synthesize<8, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
+                cudaFuncSetAttribute(k2_synthesize<8, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
+                cudaFuncSetAttribute(k1n_magnitude<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
+            });
         cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k1n_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n2_smem_floats() * 4);
         cudaFuncSetAttribute(k2_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k22_smem_floats() * 4);
@@ -399,8 +411,6 @@ void b200gate_destroy(b200gate_handle* h) {
     for (int i = 0; i < 2; ++i) {
         if (h->d_slab_in[i]) cudaFree(h->d_slab_in[i]);
         if (h->d_slab_out[i]) cudaFree(h->d_slab_out[i]);
-        if (h->d_slab_raw_in[i]) cudaFree(h->d_slab_raw_in[i]);
-        if (h->d_slab_raw_out[i]) cudaFree(h->d_slab_raw_out[i]);
     }
     delete h;
 }
@@ -557,7 +567,7 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
     h->d_tthr = nullptr;
     CK(h, cudaMalloc((void**)&h->d_tthr, (size_t)Bn * kFPad * 4));
     DebugTap dbg{}; dbg.ul = -1;
-    launch_k1n(g, device_tables(h), x, mag, dbg, h->num_sm * 3, st);
+    launch_k1n(g, device_tables(h), x, B200GATE_F32, mag, dbg, h->num_sm * 3, st);
     TStatArgs ta{};
     ta.n_units = (int)Bn; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64; ta.top_db = (float)h->p.top_db;
     ta.n_std = (float)h->p.n_std_thresh; ta.ddof = h->p.std_ddof; ta.mag = mag; ta.rowmax = rowmax; ta.thr = h->d_tthr;
@@ -587,49 +597,50 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     h->stats = b200gate_stats{};
     long long launches = 0;
 
-    // ---- stage to float32 device rows ------------------------------------------------------
-    const float* x = nullptr;
-    float* y = nullptr;
+    // ---- where the kernels read / write ---------------------------------------------------------------
+    // The n_fft = 1024 numpy-surface kernels are templated on the sample dtype: they read the caller's
+    // float32 / int16 / float64 rows directly and cast on store (base.py:140, :218-226).  The 2048 family and
+    // the torch surface run on float32 rows (other dtypes are converted at the edge).
+    const bool native = !torch_sem && p.n_fft == kN;
+    const int kdt = native ? dtype : B200GATE_F32;            // dtype the kernels see
+    const size_t kes = dtype_size(kdt);
+    const void* x = nullptr;
+    void* y = nullptr;
     long long xs = in_stride, ys = out_stride;
-    const bool direct = is_device && dtype == B200GATE_F32;
-    // Host float32 input that the reference would chunk: stream it through the GPU slab by slab
-    // (H2D of slab k+1, kernels of slab k and D2H of slab k-1 overlap on three streams) instead of
-    // staging the whole recording -- the role of _read_chunk + the memmap write-back (base.py:130-187).
-    const bool pipelined = !is_device && !torch_sem && h->p.chunk_size > 0 &&
+    const bool direct = is_device && kdt == dtype;
+    // Host input that the reference would chunk: stream it through the GPU slab by slab (H2D of slab k+1,
+    // kernels of slab k and D2H of slab k-1 overlap on three streams) instead of staging the whole
+    // recording -- the role of _read_chunk + the memmap write-back (base.py:130-187).
+    const bool pipelined = !is_device && kdt == dtype && !torch_sem && h->p.chunk_size > 0 &&
                            N > h->p.chunk_size && h->p.padding >= h->p.hop_length;
     if (direct || pipelined) {
-        x = (const float*)in;
-        y = (float*)out;
+        x = in;
+        y = out;
     } else {
         int rc;
-        if ((rc = ensure(h, (void**)&h->d_in, &h->in_bytes, (size_t)C * N * 4))) return rc;
-        if ((rc = ensure(h, (void**)&h->d_out, &h->out_bytes, (size_t)C * N * 4))) return rc;
+        if ((rc = ensure(h, (void**)&h->d_in, &h->in_bytes, (size_t)C * N * kes))) return rc;
+        if ((rc = ensure(h, (void**)&h->d_out, &h->out_bytes, (size_t)C * N * kes))) return rc;
         x = h->d_in;
         y = h->d_out;
         xs = ys = N;
-        const void* raw = in;
-        long long rs = in_stride;
-        if (!is_device) {
-            if (dtype == B200GATE_F32) {
-                CK(h, cudaMemcpy2DAsync(h->d_in, (size_t)N * 4, in, (size_t)in_stride * 4, (size_t)N * 4, (size_t)C,
-                                        cudaMemcpyHostToDevice, st));
-                raw = nullptr;
-            } else {
+        if (kdt == dtype) {                                   // host rows, whole recording at once
+            CK(h, cudaMemcpy2DAsync(h->d_in, (size_t)N * es, in, (size_t)in_stride * es, (size_t)N * es, (size_t)C,
+                                    cudaMemcpyHostToDevice, st));
+        } else {                                              // float32-only kernel family: convert at the edge
+            const void* raw = in;
+            long long rs = in_stride;
+            if (!is_device) {
                 if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * N * es))) return rc;
                 CK(h, cudaMemcpy2DAsync(h->d_raw, (size_t)N * es, in, (size_t)in_stride * es, (size_t)N * es, (size_t)C,
                                         cudaMemcpyHostToDevice, st));
                 raw = h->d_raw;
                 rs = N;
             }
-        }
-        if (raw) {
             const int gr = grid_1d((long long)C * N, 256, h->num_sm * 16);
             if (dtype == B200GATE_I16)
-                { auto kern_ = k_to_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const short*)raw, h->d_in, (long long)C, (long long)N, rs, (long long)N); }
-            else if (dtype == B200GATE_F64)
-                { auto kern_ = k_to_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const double*)raw, h->d_in, (long long)C, (long long)N, rs, (long long)N); }
-            else   // f32 on device with a stride we cannot use directly never happens (direct path)
-                { auto kern_ = k_to_f32<float>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)raw, h->d_in, (long long)C, (long long)N, rs, (long long)N); }
+                { auto kern_ = k_to_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const short*)raw, (float*)h->d_in, (long long)C, (long long)N, rs, (long long)N); }
+            else
+                { auto kern_ = k_to_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const double*)raw, (float*)h->d_in, (long long)C, (long long)N, rs, (long long)N); }
             ++launches;
         }
     }
@@ -668,7 +679,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     }
     const bool tail_zeros = !torch_sem && (g.pad + g.step > sig_len);     // stationary.py:126 leaves the tail zero
     if (tail_zeros) {
-        for (long long c = 0; c < C; ++c) CK(h, cudaMemsetAsync(y + c * ys, 0, (size_t)N * 4, st));
+        for (long long c = 0; c < C; ++c) CK(h, cudaMemsetAsync((char*)y + (size_t)c * ys * kes, 0, (size_t)N * kes, st));
     }
 
     // ---- workspace / batching ---------------------------------------------------------------------
@@ -682,7 +693,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
     if (pipelined) {
         // ~512 MB of input per slab, whole chunks, within the workspace limit
-        slab_chunks = std::max(1LL, std::min<long long>(g.n_chunks, (512LL << 20) / std::max<long long>(1, C * g.step * 4)));
+        slab_chunks = std::max(1LL, std::min<long long>(g.n_chunks, (512LL << 20) / std::max<long long>(1, C * g.step * (long long)es)));
         slab_chunks = std::max(1LL, std::min(slab_chunks, ub / C));
         if (ub < C) return fail(h, B200GATE_ERR_NOMEM, "workspace limit too small for one chunk of all channels");
         ub = slab_chunks * C;
@@ -690,12 +701,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         slab_ow = slab_chunks * g.step;
         for (int i = 0; i < 2; ++i) {
             int rc;
-            if ((rc = ensure(h, (void**)&h->d_slab_in[i], &h->slab_in_bytes[i], (size_t)C * slab_w * 4))) return rc;
-            if ((rc = ensure(h, (void**)&h->d_slab_out[i], &h->slab_out_bytes[i], (size_t)C * slab_ow * 4))) return rc;
-            if (dtype != B200GATE_F32) {
-                if ((rc = ensure(h, &h->d_slab_raw_in[i], &h->slab_raw_in_bytes[i], (size_t)C * slab_w * es))) return rc;
-                if ((rc = ensure(h, &h->d_slab_raw_out[i], &h->slab_raw_out_bytes[i], (size_t)C * slab_ow * es))) return rc;
-            }
+            if ((rc = ensure(h, (void**)&h->d_slab_in[i], &h->slab_in_bytes[i], (size_t)C * slab_w * es))) return rc;
+            if ((rc = ensure(h, (void**)&h->d_slab_out[i], &h->slab_out_bytes[i], (size_t)C * slab_ow * es))) return rc;
         }
     }
     // carve the workspace into 256-byte aligned sub-buffers (vector stores need natural alignment)
@@ -768,8 +775,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         const int nu = (int)std::min(ub, U - u0);
         g.u0 = (int)u0;
         g.n_units = nu;
-        const float* xb = x;
-        float* yb = y;
+        const void* xb = x;
+        void* yb = y;
         if (pipelined) {
             // slab = chunks [c0, c1): input window [w0, w1) of every channel, output [c0*step, o1)
             const long long c0 = u0 / C, c1 = c0 + nu / C;
@@ -777,23 +784,14 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
             if (bi >= 2) CK(h, cudaStreamWaitEvent(h->s_h2d, h->pipe_ev[3 * (bi - 2) + 1], 0));   // slab buffer free
-            void* h2d_dst = dtype == B200GATE_F32 ? (void*)h->d_slab_in[ib] : h->d_slab_raw_in[ib];
-            CK(h, cudaMemcpy2DAsync(h2d_dst, (size_t)slab_w * es, (const char*)in + (size_t)w0 * es, (size_t)in_stride * es,
-                                    (size_t)(w1 - w0) * es, (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaMemcpy2DAsync(h->d_slab_in[ib], (size_t)slab_w * es, (const char*)in + (size_t)w0 * es,
+                                    (size_t)in_stride * es, (size_t)(w1 - w0) * es, (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
             CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 0], h->s_h2d));
             CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * bi + 0], 0));
             if (bi >= 2) CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * (bi - 2) + 2], 0));         // output buffer drained
-            if (dtype != B200GATE_F32) {                                                           // base.py:140 promotion
-                const int gr = grid_1d((long long)C * (w1 - w0), 256, h->num_sm * 16);
-                if (dtype == B200GATE_I16)
-                    { auto kern_ = k_to_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const short*)h->d_slab_raw_in[ib], h->d_slab_in[ib], (long long)C, (long long)(w1 - w0), (long long)slab_w, (long long)slab_w); }
-                else
-                    { auto kern_ = k_to_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const double*)h->d_slab_raw_in[ib], h->d_slab_in[ib], (long long)C, (long long)(w1 - w0), (long long)slab_w, (long long)slab_w); }
-                ++launches;
-            }
             // virtual row bases so the kernels keep absolute sample indices
-            xb = h->d_slab_in[ib] - w0;
-            yb = h->d_slab_out[ib] - o0;
+            xb = (const char*)h->d_slab_in[ib] - (size_t)w0 * es;
+            yb = (char*)h->d_slab_out[ib] - (size_t)o0 * es;
             g.in_stride = slab_w;
             g.out_stride = slab_ow;
             (void)o1;
@@ -807,7 +805,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (torch_sem) {
                 // TorchGate: |X| -> dB, per-row statistics over the row's own frames (or xn's), compare
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, d_tdb, dbg, resident, st);
+                launch_k1n(g, tb, xb, kdt, d_tdb, dbg, resident, st);
                 TStatArgs ta{};
                 ta.n_units = nu; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64;
                 ta.top_db = (float)p.top_db; ta.n_std = (float)p.n_std_thresh; ta.ddof = p.std_ddof;
@@ -840,7 +838,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a1.n_runs = (g.T + a1.run - 1) / a1.run;
                 }
                 const long long items1 = (long long)nu * a1.n_runs;
-                B200_LAUNCH(k1_analyze<8>, dim3(grid_1d(items1, kWarps, h->num_sm * B200_K1_MINBLOCKS)), dim3(kThreads), k1_smem_floats() * 4, st, a1);
+                B200_WITH_DTYPE(kdt, { auto kern_ = k1_analyze<8, T>;
+                    B200_LAUNCH(kern_, dim3(grid_1d(items1, kWarps, h->num_sm * B200_K1_MINBLOCKS)), dim3(kThreads), k1_smem_floats() * 4, st, a1); });
                 B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
                             (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
             }
@@ -894,9 +893,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
                 }
                 const long long items2 = (long long)nu * a2.n_runs;
-                auto kern2 = k2_synthesize<8, false>;
-                B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
-                            k2_smem_floats(g.H) * 4, st, a2);
+                B200_WITH_DTYPE(kdt, { auto kern2 = k2_synthesize<8, false, T>;
+                    B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
+                                k2_smem_floats(g.H) * 4, st, a2); });
                 cudaEventRecord(h->stage_ev[4 * bi + 3], st);
                 launches += 2;
             }
@@ -908,7 +907,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 const int res2 = h->num_sm * 2;
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
                 K1n2Args a1{};
-                a1.g = g; a1.tb = t2; a1.x = xb; a1.mag = d_mag; a1.dbg = dbg;
+                a1.g = g; a1.tb = t2; a1.x = (const float*)xb; a1.mag = d_mag; a1.dbg = dbg;
                 {
                     long long want = (long long)resident * kWarps * 4;
                     long long run = ((long long)nu * g.T + want - 1) / want;
@@ -940,7 +939,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
                     cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                     K22Args a2{};
-                    a2.g = g; a2.tb = t2; a2.x = xb; a2.y = yb; a2.fmask = d_mag; a2.dbg = dbg;
+                    a2.g = g; a2.tb = t2; a2.x = (const float*)xb; a2.y = (float*)yb; a2.fmask = d_mag; a2.dbg = dbg;
                     {
                         const long long hops = h_hi - h_lo;
                         long long want = (long long)res2 * kWarps * 4;
@@ -955,7 +954,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
             } else {
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, d_mag, dbg, resident, st);
+                launch_k1n(g, tb, xb, kdt, d_mag, dbg, resident, st);
                 cudaEventRecord(h->stage_ev[4 * bi + 1], st);
                 if (torch_sem) {
                     TMovArgs ma{};
@@ -999,9 +998,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                         a2.run = (int)run;
                         a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
                     }
-                    auto kern2 = k2_synthesize<8, true>;
-                    B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
-                                k2_smem_floats(g.H) * 4, st, a2);
+                    B200_WITH_DTYPE(kdt, { auto kern2 = k2_synthesize<8, true, T>;
+                        B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
+                                    k2_smem_floats(g.H) * 4, st, a2); });
                     cudaEventRecord(h->stage_ev[4 * bi + 3], st);
                     launches += 2;
                 }
@@ -1023,15 +1022,6 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
             const void* d2h_src = h->d_slab_out[ib];
-            if (dtype != B200GATE_F32) {                                                           // base.py:218-226 cast back
-                const int gr = grid_1d((long long)C * (o1 - o0), 256, h->num_sm * 16);
-                if (dtype == B200GATE_I16)
-                    { auto kern_ = k_from_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)h->d_slab_out[ib], (short*)h->d_slab_raw_out[ib], (long long)C, (long long)(o1 - o0), (long long)slab_ow, (long long)slab_ow); }
-                else
-                    { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)h->d_slab_out[ib], (double*)h->d_slab_raw_out[ib], (long long)C, (long long)(o1 - o0), (long long)slab_ow, (long long)slab_ow); }
-                ++launches;
-                d2h_src = h->d_slab_raw_out[ib];
-            }
             CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 1], st));
             CK(h, cudaStreamWaitEvent(h->s_d2h, h->pipe_ev[3 * bi + 1], 0));
             CK(h, cudaMemcpy2DAsync((char*)out + (size_t)o0 * es, (size_t)out_stride * es, d2h_src, (size_t)slab_ow * es,
@@ -1047,11 +1037,13 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
 
     // ---- results back -------------------------------------------------------------------------------
     if (!direct && !pipelined) {
-        const void* res = y;
-        if (dtype != B200GATE_F32) {
+        if (kdt == dtype) {
+            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, y, (size_t)ys * es, (size_t)No * es, (size_t)C,
+                                    cudaMemcpyDeviceToHost, st));
+        } else {
             int rc;
             if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * N * es))) return rc;
-            const int gr = grid_1d((long long)C * N, 256, h->num_sm * 16);
+            const int gr = grid_1d((long long)C * No, 256, h->num_sm * 16);
             void* dst = is_device ? out : h->d_raw;
             const long long ds = is_device ? out_stride : No;
             if (dtype == B200GATE_I16)
@@ -1059,14 +1051,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             else
                 { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (double*)dst, (long long)C, (long long)No, ys, ds); }
             ++launches;
-            res = h->d_raw;
-        } else if (is_device) {
-            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * 4, y, (size_t)ys * 4, (size_t)No * 4, (size_t)C,
-                                    cudaMemcpyDeviceToDevice, st));
+            if (!is_device)
+                CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, h->d_raw, (size_t)No * es, (size_t)No * es, (size_t)C,
+                                        cudaMemcpyDeviceToHost, st));
         }
-        if (!is_device)
-            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, res, (size_t)(dtype != B200GATE_F32 ? No : ys) * es, (size_t)No * es, (size_t)C,
-                                    cudaMemcpyDeviceToHost, st));
     }
     CK(h, cudaGetLastError());
 

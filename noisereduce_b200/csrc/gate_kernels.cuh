@@ -89,10 +89,29 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // One sample of the zero-extended padded chunk (base.py:130-142 zeros outside [0, n_total);
 // scipy boundary='zeros' outside [0, Lp)).  j: chunk-local index, i1: global index of j = 0.
-__device__ __forceinline__ float chunk_sample(const float* __restrict__ xrow, long long j, long long i1,
+// The kernels read the caller's samples in their own dtype (float32 / int16 / float64) and convert on
+// load -- the device-side form of base.py:140's promotion -- and k2 casts on store (base.py:218-226).
+template <typename T>
+__device__ __forceinline__ float ld_sample(const T* p) { return (float)__ldg(p); }
+template <typename T>
+__device__ __forceinline__ double ld_sample_f64(const T* p) { return (double)__ldg(p); }
+template <typename T>
+__device__ __forceinline__ T st_cast(float v);
+template <> __device__ __forceinline__ float st_cast<float>(float v) { return v; }
+template <> __device__ __forceinline__ double st_cast<double>(float v) { return (double)v; }
+template <> __device__ __forceinline__ short st_cast<short>(float v) { return (short)(int)v; }   // numpy astype: truncate, wrap
+
+template <typename T>
+__device__ __forceinline__ float chunk_sample(const T* __restrict__ xrow, long long j, long long i1,
                                               long long Lp, long long n_total) {
     const long long g = i1 + j;
-    return (j >= 0 && j < Lp && g >= 0 && g < n_total) ? __ldg(xrow + g) : 0.0f;
+    return (j >= 0 && j < Lp && g >= 0 && g < n_total) ? ld_sample(xrow + g) : 0.0f;
+}
+template <typename T>
+__device__ __forceinline__ double chunk_sample_f64(const T* __restrict__ xrow, long long j, long long i1,
+                                                   long long Lp, long long n_total) {
+    const long long g = i1 + j;
+    return (j >= 0 && j < Lp && g >= 0 && g < n_total) ? ld_sample_f64(xrow + g) : 0.0;
 }
 
 // Rows of a frame pair: frame t is rows 0..31, frame t+1 rows HR..31+HR of the same 32+HR row window
@@ -107,32 +126,32 @@ __device__ __forceinline__ bool pair_window_interior(long long base, long long i
 // Software pipelining of the HBM latency: the 2*HR rows of the NEXT pair that this pair has not
 // touched are requested before this pair's FFT and sit in registers until the next iteration; the
 // other 32-HR rows were read by this pair and come back from L1.
-template <int HR>
-__device__ __forceinline__ void load_new_rows(float (&nx)[2 * HR], const float* __restrict__ xrow, long long base_next,
+template <int HR, typename T>
+__device__ __forceinline__ void load_new_rows(float (&nx)[2 * HR], const T* __restrict__ xrow, long long base_next,
                                               long long i1, int lane) {
-    const float* p = xrow + i1 + base_next + 32 * (32 - HR) + lane;
+    const T* p = xrow + i1 + base_next + 32 * (32 - HR) + lane;
 #pragma unroll
-    for (int r = 0; r < 2 * HR; ++r) nx[r] = __ldg(p + 32 * r);
+    for (int r = 0; r < 2 * HR; ++r) nx[r] = ld_sample(p + 32 * r);
 }
 
 // Load (or assemble from the pre-loaded rows) the raw samples of the pair, window them and pack the
 // two frames as one complex signal.  Returns this lane's contribution to ||frame pair||^2.
-template <int HR>
-__device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32], const float* __restrict__ xrow,
+template <int HR, typename T>
+__device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32], const T* __restrict__ xrow,
                                                  long long base, long long i1, long long Lp, long long n_total,
                                                  const float* __restrict__ s_wa, int lane, bool vb,
                                                  const float (&nx)[2 * HR], bool have_nx) {
     float xr[32 + HR];
     if (have_nx) {                                   // interior pair whose new rows were pre-loaded
-        const float* p = xrow + i1 + base + lane;
+        const T* p = xrow + i1 + base + lane;
 #pragma unroll
-        for (int r = 0; r < 32 - HR; ++r) xr[r] = __ldg(p + 32 * r);
+        for (int r = 0; r < 32 - HR; ++r) xr[r] = ld_sample(p + 32 * r);
 #pragma unroll
         for (int r = 0; r < 2 * HR; ++r) xr[32 - HR + r] = nx[r];
     } else if (pair_window_interior<HR>(base, i1, Lp, n_total)) {
-        const float* p = xrow + i1 + base + lane;
+        const T* p = xrow + i1 + base + lane;
 #pragma unroll
-        for (int r = 0; r < 32 + HR; ++r) xr[r] = __ldg(p + 32 * r);
+        for (int r = 0; r < 32 + HR; ++r) xr[r] = ld_sample(p + 32 * r);
     } else {                                         // chunk / recording edges: zero-extended samples
 #pragma unroll
         for (int r = 0; r < 32 + HR; ++r) xr[r] = chunk_sample(xrow, base + lane + 32 * r, i1, Lp, n_total);
@@ -163,8 +182,8 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
     (void)p;
 #endif
 }
-template <int HR>
-__device__ __forceinline__ void prefetch_next_pair(const float* __restrict__ xrow, long long base_next, long long i1,
+template <int HR, typename T>
+__device__ __forceinline__ void prefetch_next_pair(const T* __restrict__ xrow, long long base_next, long long i1,
                                                    long long Lp, long long n_total, int lane) {
     // rows 32-HR .. 31+HR of the next pair are the ones this pair has not touched: 2*HR rows of 128 B
     if (lane < 2 * HR) {
@@ -183,11 +202,12 @@ __device__ __forceinline__ void prefetch_next_pair(const float* __restrict__ xro
 // Exact (float64) re-decision of one bin of one frame: direct DFT of the windowed samples.
 // Warp-cooperative; every lane returns the same value.  2 = above threshold, 1 = not above,
 // 0 = unresolved even in float64 (|P - T^2| <= 1e-12 T^2).
-__device__ B200_NOINLINE int recheck_bin_fp64(const float* __restrict__ xrow, long long base, long long i1,
+template <typename T>
+__device__ B200_NOINLINE int recheck_bin_fp64(const T* __restrict__ xrow, long long base, long long i1,
                                               long long Lp, long long n_total, int k, const Tables& tb, int lane) {
     double sr = 0.0, si = 0.0;
     for (int n = lane; n < kN; n += 32) {
-        const double x = (double)chunk_sample(xrow, base + n, i1, Lp, n_total) * tb.wa64[n];
+        const double x = chunk_sample_f64(xrow, base + n, i1, Lp, n_total) * tb.wa64[n];   // the caller's exact samples
         const double2 cs = tb.cs64[(k * n) & (kN - 1)];
         sr = fma(x, cs.x, sr);
         si = fma(-x, cs.y, si);
@@ -206,7 +226,7 @@ __device__ B200_NOINLINE int recheck_bin_fp64(const float* __restrict__ xrow, lo
 struct K1Args {
     Geom g;
     Tables tb;
-    const float* x;            // [C][in_stride] float32 samples
+    const void* x;             // [C][in_stride] samples in the caller's dtype (kernel template T)
     unsigned* bits;            // [n_units][T][FW]
     unsigned* rowmax;          // [n_units][FPad]  max_t 4|X|^2 as float bits (>= 0 so uint order works)
     Counters* cnt;
@@ -217,7 +237,7 @@ struct K1Args {
 
 constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats + kWarps * 2 * kFW + 8; }
 
-template <int HR>
+template <int HR, typename T>
 __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const K1Args a) {
     B200_DYN_SMEM(float, smem);
     float* s_wa = smem;
@@ -251,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const 
         const int u = g.u0 + ul;
         const int ic = u / g.C, c = u - ic * g.C;
         const long long i1 = (long long)ic * g.step - g.pad;
-        const float* xrow = a.x + (long long)c * g.in_stride;
+        const T* xrow = static_cast<const T*>(a.x) + (long long)c * g.in_stride;
         const int t0 = run * a.run;
         const int t1 = min(t0 + a.run, g.T);
         float mx[kFW];
@@ -594,8 +614,8 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPA
 struct K2Args {
     Geom g;
     Tables tb;
-    const float* x;
-    float* y;                      // [C][out_stride] float32
+    const void* x;                 // caller dtype (kernel template T)
+    void* y;                       // [C][out_stride], caller dtype
     const unsigned short* num;     // [n_units][T][FPad] integer mask numerators (stationary)
     const float* fmask;            // [n_units][T][FPad] final float masks (non-stationary)
     float pD;                      // prop_decrease / D
@@ -616,7 +636,7 @@ __device__ __forceinline__ float time_edge(int t, int T, int nt) {
     return (float)s / (float)((nt + 1) * (nt + 1));
 }
 
-template <int HR, bool FMASK>
+template <int HR, bool FMASK, typename T>
 __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
     constexpr int NH = 32 / HR;             // frames overlapping one hop (win / hop)
     B200_DYN_SMEM(float, smem);
@@ -664,8 +684,8 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         if (hs >= he) continue;
         const int t_start = max(0, hs - (NH - 1));
         const int t_last = min(he - 1, g.T - 1);
-        const float* xrow = a.x + (long long)c * g.in_stride;
-        float* yrow = a.y + (long long)c * g.out_stride;
+        const T* xrow = static_cast<const T*>(a.x) + (long long)c * g.in_stride;
+        T* yrow = static_cast<T*>(a.y) + (long long)c * g.out_stride;
         const unsigned short* mrow = FMASK ? nullptr : a.num + (long long)ul * g.T * kFPad;
         const float* frow = FMASK ? a.fmask + (long long)ul * g.T * kFPad : nullptr;
 
@@ -790,9 +810,9 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                 if (t >= hs && t + 1 < he && t >= NH - 1 && t + 1 <= g.T - 1 && jp0 >= g.pad &&
                     jp0 + 2 * H <= jp_hi) {
                     // both hops interior and fully inside the chunk centre: 2*HR coalesced row stores
-                    float* dst = yrow + i1 + jp0 + lane;
+                    T* dst = yrow + i1 + jp0 + lane;
 #pragma unroll
-                    for (int r = 0; r < 2 * HR; ++r) dst[32 * r] = acc[r] * s_invn[(r % HR) * 32 + lane];
+                    for (int r = 0; r < 2 * HR; ++r) dst[32 * r] = st_cast<T>(acc[r] * s_invn[(r % HR) * 32 + lane]);
                 } else {
 #pragma unroll 1
                     for (int r = 0; r < 2 * HR; ++r) {
@@ -819,7 +839,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                             }
                             inv = nrm > 1e-10f ? 1.0f / nrm : 1.0f;
                         }
-                        yrow[i1 + jp] = v * inv;
+                        yrow[i1 + jp] = st_cast<T>(v * inv);
                     }
                 }
             }
@@ -843,7 +863,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
 struct K1nArgs {
     Geom g;
     Tables tb;
-    const float* x;
+    const void* x;
     float* mag;                // [n_units][T][FPad]
     DebugTap dbg;
     int run, n_runs;
@@ -851,7 +871,7 @@ struct K1nArgs {
 
 constexpr int k1n_smem_floats() { return kN + 2 * kN + kWarps * kExchFloats; }
 
-template <int HR>
+template <int HR, typename T>
 __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
     B200_DYN_SMEM(float, smem);
     float* s_wa = smem;
@@ -875,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
         const int u = g.u0 + ul;
         const int ic = u / g.C, c = u - ic * g.C;
         const long long i1 = (long long)ic * g.step - g.pad;
-        const float* xrow = a.x + (long long)c * g.in_stride;
+        const T* xrow = static_cast<const T*>(a.x) + (long long)c * g.in_stride;
         const int t0 = run * a.run;
         const int t1 = min(t0 + a.run, g.T);
         float nx[2 * HR];

@@ -12,7 +12,8 @@ from .spectralgate.base import SpectralGate
 
 
 class DeviceGate:
-    """A gate bound to the current CUDA device, taking [C, N] float32 CUDA tensors.  (With the CPU
+    """A gate bound to the current CUDA device, taking [C, N] float32 / int16 / float64 CUDA tensors
+    (read and written by the kernels in that dtype).  (With the CPU
     simulator library that tests inject via `lib=`, "device" pointers are host pointers.)"""
 
     def __init__(self, sr, stationary=True, prop_decrease=1.0, time_constant_s=2.0, freq_mask_smooth_hz=500,
@@ -30,15 +31,17 @@ class DeviceGate:
         self.gate = _cabi.Gate(lib=lib, **p)
         self.stationary = stationary
 
-    @staticmethod
-    def _check(x: torch.Tensor):
-        if not (x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1):
-            raise ValueError("expected a [C, N] float32 tensor with contiguous rows")
+    _NP = {torch.float32: np.float32, torch.int16: np.int16, torch.float64: np.float64}
+
+    @classmethod
+    def _check(cls, x: torch.Tensor):
+        if not (x.dim() == 2 and x.dtype in cls._NP and x.stride(1) == 1):
+            raise ValueError("expected a [C, N] float32 / int16 / float64 tensor with contiguous rows")
 
     def noise_stats(self, y_noise: torch.Tensor):
         self._check(y_noise)
         st = torch.cuda.current_stream().cuda_stream if y_noise.is_cuda else None
-        self.gate.noise_stats_device(y_noise.data_ptr(), np.float32, y_noise.shape[0], y_noise.shape[1],
+        self.gate.noise_stats_device(y_noise.data_ptr(), self._NP[y_noise.dtype], y_noise.shape[0], y_noise.shape[1],
                                      y_noise.stride(0), st)
 
     def run(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
@@ -46,7 +49,9 @@ class DeviceGate:
         if out is None:
             out = torch.empty_like(x)
         self._check(out)
+        if out.dtype != x.dtype:
+            raise ValueError("out must have x's dtype (the reference returns the input dtype)")
         st = torch.cuda.current_stream().cuda_stream if x.is_cuda else None
-        self.gate.run_device(x.data_ptr(), out.data_ptr(), np.float32, x.shape[0], x.shape[1], x.stride(0),
+        self.gate.run_device(x.data_ptr(), out.data_ptr(), self._NP[x.dtype], x.shape[0], x.shape[1], x.stride(0),
                              out.stride(0), st)
         return out

@@ -150,6 +150,20 @@ def test_device_pointer_path_and_properties(lib):
     # idempotent launch: same input -> bit-identical output (no races in the overlap-add seams)
     y2 = dg.run(x)
     assert torch.equal(y, y2)
+    # native int16 / float64 device rows: the kernels load and store the caller's dtype
+    xi = (x[:2, :1_300_000] * 20000).to(torch.int16)
+    dgi = DeviceGate(sr=sr, stationary=True)
+    dgi.noise_stats(xi)
+    yi = dgi.run(xi)
+    assert yi.dtype == torch.int16
+    refi = O.reduce_noise(xi.cpu().numpy(), sr, cfg=O.GateConfig(sr=sr, stationary=True),
+                          thresh_override=dgi.gate.noise_threshold())
+    assert np.abs(yi.cpu().numpy().astype(np.int32) - refi.astype(np.int32)).max() <= 1
+    xd = x[:1, :700_000].double()
+    dgd = DeviceGate(sr=sr, stationary=False)
+    yd = dgd.run(xd)
+    refd = O.reduce_noise(xd.cpu().numpy(), sr, cfg=O.GateConfig(sr=sr, stationary=False), return_float64=True)
+    assert yd.dtype == torch.float64 and P.relinf(yd.cpu().numpy(), refd) < P.OUT_TOL_TIGHT * 5
 
 
 def test_torchgate_surface(lib, golden_dir):
