@@ -61,7 +61,7 @@ typedef struct b200gate_params {
     int32_t debug_guard_scale;  /* tests only: multiplies the FP32 guard band (0 = 1x), forcing more
                                  * bins through the FP64 re-decision path                          */
     int32_t reserve_sms;        /* SMs the persistent grids leave free (for a concurrent NCCL collective) */
-    int32_t reserved1;
+    int32_t disable_fused;      /* 1: never use the single-pass fused kernel (tests / A-B measurements)   */
     int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
     int64_t padding;
     double sr;
@@ -88,6 +88,9 @@ typedef struct b200gate_stats {
     double last_run_ms;             /* device time of the last run, CUDA events on its stream     */
     double last_h2d_ms, last_d2h_ms;
     double k1_ms, smooth_ms, k2_ms; /* per-kernel device time summed over the run's batches       */
+    double fused_ms;                /* single-pass kernel (k1/smooth/k2 are 0 when it ran)        */
+    int64_t fused_path;             /* 1: the single-pass kernel produced the result              */
+    int64_t fused_fallbacks;        /* 1: top_db floor could trigger -> redone on the two-pass path */
 } b200gate_stats;
 
 int b200gate_create(const b200gate_params* params, b200gate_handle** out);

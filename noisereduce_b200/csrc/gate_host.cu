@@ -5,6 +5,7 @@
 // k1_analyze -> k_rowfloor -> k_smooth -> k2_synthesize per batch of units on the caller's stream.
 #include "../../include/b200gate.h"
 #include "gate_kernels_2k.cuh"
+#include "gate_fused.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -44,6 +45,11 @@ struct b200gate_handle {
     float* d_tthr = nullptr;                       // torch surface: thresholds from xn, [tthr_units][FPad]
     int tthr_units = 0;
     bool have_thresh = false;
+    double min_floor_amp = 0.0;                    // min_f 10^((thresh+top_db)/20): smallest |X| that lifts a row
+    bool force_two_pass = false;
+    unsigned* d_maxabs = nullptr;
+    char* d_fscratch = nullptr;                    // fused kernel: per-warp spectra + decision rows
+    size_t fscratch_bytes = 0;
     std::vector<double> thr, mean, sd;
     // workspace
     char* d_ws_buf = nullptr;
@@ -215,6 +221,7 @@ int build_threshold_tables(b200gate_handle* h) {
         double Tf = pow(10.0, (h->thr[f] + h->p.top_db) / 20.0) - kEps64;
         if (!(Tf > 0.0)) Tf = 0.0;
         t2[f] = T * T;
+        if (f == 0 || Tf < h->min_floor_amp) h->min_floor_amp = Tf;
         thr4[f] = (float)(4.0 * T * T);
         gco[f] = (float)(8.0 * T * kKappa * kEps32 * (h->p.debug_guard_scale > 0 ? h->p.debug_guard_scale : 1));
         floor4[f] = (float)(4.0 * Tf * Tf);
@@ -364,6 +371,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     if (p->reserve_sms > 0 && p->reserve_sms < h->num_sm) h->num_sm -= p->reserve_sms;   // leave room for NCCL
     int rc = build_static_tables(h);
     if (rc == B200GATE_OK) {
+        cudaMalloc((void**)&h->d_maxabs, sizeof(unsigned));
         e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
         if (e != cudaSuccess) rc = fail(h, B200GATE_ERR_CUDA, "cudaMalloc counters: %s", cudaGetErrorString(e));
     }
@@ -383,6 +391,8 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k1n_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n2_smem_floats() * 4);
         cudaFuncSetAttribute(k2_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k22_smem_floats() * 4);
+        for (int dt = 0; dt < 3; ++dt)
+            B200_WITH_DTYPE(dt, { cudaFuncSetAttribute(k_fused<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kfused_smem_floats() * 4); });
         cudaFuncSetAttribute(k_smooth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 #endif
     }
@@ -398,7 +408,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
 void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
-                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
+                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_maxabs, h->d_fscratch, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
                     h->d_dbg_mask, h->d_dbg_bits};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -684,9 +694,13 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
 
     // ---- workspace / batching ---------------------------------------------------------------------
     const bool stat = p.stationary != 0;
-    const size_t per_unit = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
-                                  : 2 * (size_t)g.T * FP * 4 + 64) +
-                            (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
+    // single-pass fused kernel: stationary gate, n_fft 1024, filter extents the in-warp smoother handles
+    const bool use_fused = stat && native && !h->force_two_pass && !p.disable_fused &&
+                           (2 * p.n_grad_freq + 1 <= 12) && (p.n_grad_time + 1 <= 14);
+    const size_t per_unit_2pass = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
+                                        : 2 * (size_t)g.T * FP * 4 + 64) +
+                                  (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
+    const size_t per_unit = use_fused ? 64 : per_unit_2pass;      // the fused kernel keeps no per-unit buffers
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
@@ -720,7 +734,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t off_tthr = off_trow + al((size_t)ub * kFPad * 4);
     const size_t end_tstat = off_tthr + al((size_t)ub * kFPad * 4);
     {
-        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
+        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat));
         if (rc) return rc;
     }
     float* d_tdb = (float*)(h->d_ws_buf + off_tdb);
@@ -757,6 +771,22 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const int nf = p.n_grad_freq, nt = p.n_grad_time;
     const double D = (double)(nf + 1) * (nf + 1) * (nt + 1) * (nt + 1);
     const int resident = h->num_sm * 3;
+    int fused_run = 0, fused_max_pairs = 0;
+    if (use_fused) {
+        const int ntE = (nt + 1) & ~1;
+        const long long hops = h_hi - h_lo;
+        long long want = (long long)resident * kWarps * 3;
+        long long run = ((long long)std::min(ub, U) * hops + want - 1) / want;
+        fused_run = (int)std::max(32LL, std::min(128LL, run));
+        fused_run += fused_run & 1;
+        fused_max_pairs = (fused_run + 4 + 2 * ntE + 2) / 2 + 2;
+        const size_t workers = (size_t)resident * kWarps;
+        const size_t zbytes = workers * (size_t)fused_max_pairs * 1024 * sizeof(float2);
+        const size_t bbytes = workers * (size_t)(2 * fused_max_pairs) * kFusedRowWords * 4;
+        int rc = ensure(h, (void**)&h->d_fscratch, &h->fscratch_bytes, zbytes + bbytes + 256);
+        if (rc) return rc;
+        CK(h, cudaMemsetAsync(h->d_maxabs, 0, sizeof(unsigned), st));
+    }
 
     const size_t n_batches = (size_t)((U + ub - 1) / ub);
     while (h->stage_ev.size() < 4 * n_batches) {
@@ -801,7 +831,37 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         dbg.spec = h->d_dbg_spec;
         dbg.mask = h->d_dbg_mask;
 
-        if (stat) {
+        if (use_fused) {
+            KFArgs fa{};
+            fa.g = g; fa.tb = tb; fa.x = xb; fa.y = yb;
+            const size_t workers = (size_t)resident * kWarps;
+            fa.zscratch = (float2*)h->d_fscratch;
+            fa.bitscratch = (unsigned*)(h->d_fscratch + workers * (size_t)fused_max_pairs * 1024 * sizeof(float2));
+            fa.max_pairs = fused_max_pairs; fa.max_rows = 2 * fused_max_pairs;
+            fa.maxabs = h->d_maxabs; fa.cnt = h->d_cnt;
+            fa.pD = (float)(p.prop_decrease / D); fa.one_minus_p = (float)(1.0 - p.prop_decrease);
+            fa.nf = nf; fa.nt = nt;
+            {
+                unsigned char tb8[12] = {0};
+                for (int d = -nf; d <= nf; ++d) tb8[d + nf] = (unsigned char)(nf + 1 - abs(d));
+                memcpy(fa.taps, tb8, 12);
+            }
+            fa.run = fused_run;
+            fa.n_runs = (int)((h_hi - h_lo + fused_run - 1) / fused_run);
+            fa.dbg = dbg;
+            fa.dbg_bits = dbg.ul >= 0 ? h->d_dbg_bits : nullptr;
+            if (dbg.ul >= 0) CK(h, cudaMemsetAsync(h->d_dbg_bits, 0, (size_t)g.T * kFW * 4, st));
+            cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+            if (tf_hi > tf_lo) {
+                B200_WITH_DTYPE(kdt, { auto kern_ = k_fused<8, T>;
+                    B200_LAUNCH(kern_, dim3(grid_1d((long long)nu * fa.n_runs, kWarps, resident)), dim3(kThreads),
+                                kfused_smem_floats() * 4, st, fa); });
+                ++launches;
+            }
+            cudaEventRecord(h->stage_ev[4 * bi + 1], st);
+            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+        } else if (stat) {
             if (torch_sem) {
                 // TorchGate: |X| -> dB, per-row statistics over the row's own frames (or xn's), compare
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
@@ -1006,7 +1066,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
             }
         }
-        if (dbg.ul >= 0 && stat) {
+        if (dbg.ul >= 0 && stat && !use_fused) {
             // tapped mask words with the row floor folded in, as the smoothing kernel consumes them
             std::vector<unsigned> fl(kFW);
             CK(h, cudaStreamSynchronize(st));
@@ -1060,8 +1120,22 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
 
     // ---- stats (forces completion; device callers pay one sync for exactness bookkeeping) -----------
     Counters cnt{};
+    unsigned maxabs_bits = 0;
     CK(h, cudaMemcpyAsync(&cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    if (use_fused) CK(h, cudaMemcpyAsync(&maxabs_bits, h->d_maxabs, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    if (use_fused) {
+        float mx;
+        memcpy(&mx, &maxabs_bits, 4);
+        // |X[f,t]| <= max|x| (the scaled analysis window sums to 1): below the smallest floor no row can be lifted
+        if (!((double)mx < 0.999 * h->min_floor_amp)) {
+            h->force_two_pass = true;
+            const int rc2 = b200gate_run(h, in, out, dtype, C, N, in_stride, out_stride, is_device, stream);
+            h->force_two_pass = false;
+            h->stats.fused_fallbacks = 1;
+            return rc2;
+        }
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, evk0, evk1);
     h->stats.units = U;
@@ -1072,11 +1146,13 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     h->stats.rowfloor_flags = (int64_t)cnt.floor_flags;
     h->stats.rowfloor_ambiguous = (int64_t)cnt.floor_ambiguous;
     h->stats.last_run_ms = ms;
+    h->stats.fused_path = use_fused ? 1 : 0;
     for (size_t b = 0; b < n_batches; ++b) {
         float t1 = 0.f, t2 = 0.f, t3 = 0.f;
         cudaEventElapsedTime(&t1, h->stage_ev[4 * b + 0], h->stage_ev[4 * b + 1]);
         cudaEventElapsedTime(&t2, h->stage_ev[4 * b + 1], h->stage_ev[4 * b + 2]);
         cudaEventElapsedTime(&t3, h->stage_ev[4 * b + 2], h->stage_ev[4 * b + 3]);
+        if (use_fused) { h->stats.fused_ms += t1; continue; }
         h->stats.k1_ms += t1;
         h->stats.smooth_ms += t2;
         h->stats.k2_ms += t3;

@@ -43,6 +43,48 @@ def test_stationary_chunked_two_channels(lib):
     _assert_stationary(P.check_stationary(lib, y, cfg, tap_unit=(0, 1)))
 
 
+SR48 = 48000      # n_grad_freq = 5, n_grad_time = 9: the geometry of configs 2 / 5 -> single-pass fused kernel
+
+
+def test_fused_single_pass_kernel(lib):
+    """k_fused (one forward FFT per frame) vs the oracle and vs the two-pass path it replaces."""
+    y = synth_small(C=2, n=12000)
+    cases = [(dict(chunk_size=5000, padding=600), [(1, 1), (0, 0), (2, 1)]),
+             (dict(chunk_size=2500, padding=0, prop_decrease=0.8), [(2, 0)]),
+             (dict(), [(0, 1)]),
+             (dict(chunk_size=4000, padding=300, freq_mask_smooth_hz=200, time_mask_smooth_ms=20), [(1, 0)])]
+    for kw, units in cases:
+        cfg = O.GateConfig(sr=SR48, stationary=True, **kw)
+        for unit in units:
+            res = P.check_stationary(lib, y, cfg, tap_unit=unit)
+            assert res["stats"]["fused_path"] == 1 and res["stats"]["fused_fallbacks"] == 0
+            _assert_stationary(res)
+        two = P.check_stationary(lib, y, cfg, tap_unit=units[0], disable_fused=1)
+        assert two["stats"]["fused_path"] == 0
+        _assert_stationary(two)
+        assert P.relinf(res["out"], two["out"]) < P.OUT_TOL_TIGHT
+    # FP64 re-decision inside the fused analysis phase, int16 rows, multi-slab host streaming
+    cfg = O.GateConfig(sr=SR48, stationary=True, chunk_size=4000, padding=600)
+    res = P.check_stationary(lib, y, cfg, tap_unit=(1, 0), debug_guard_scale=100000)
+    assert res["stats"]["fused_path"] == 1 and res["stats"]["bins_rechecked_fp64"] > 100
+    _assert_stationary(res)
+    res = P.check_stationary(lib, (y * 20000).astype(np.int16), cfg, tap_unit=(2, 1), workspace_limit_bytes=200.0)
+    assert res["stats"]["fused_path"] == 1 and res["out_dtype_ok"] and res["out_max_lsb"] <= 1
+
+
+def test_fused_falls_back_when_the_row_floor_can_trigger(lib):
+    n = 6000
+    t = np.arange(n) / SR48
+    rng = np.random.default_rng(5)
+    y = (1e-5 * rng.standard_normal(n) + 0.9 * np.sin(2 * np.pi * 3000 * t)).astype(np.float32)[None, :]
+    noise = (1e-5 * rng.standard_normal(4000)).astype(np.float32)[None, :]
+    cfg = O.GateConfig(sr=SR48, stationary=True, chunk_size=None, padding=300)
+    res = P.check_stationary(lib, y, cfg, y_noise=noise)
+    assert res["stats"]["fused_fallbacks"] == 1 and res["stats"]["fused_path"] == 0
+    assert res["stats"]["rowfloor_flags"] > 0
+    _assert_stationary(res)
+
+
 def test_pipelined_host_path_one_chunk_per_slab(lib):
     """Host float32 input is streamed slab by slab (H2D / kernels / D2H on three streams); a tiny
     workspace limit forces one chunk per slab so slab seams and buffer recycling are exercised."""
