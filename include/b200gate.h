@@ -61,7 +61,9 @@ typedef struct b200gate_params {
     int32_t debug_guard_scale;  /* tests only: multiplies the FP32 guard band (0 = 1x), forcing more
                                  * bins through the FP64 re-decision path                          */
     int32_t reserve_sms;        /* SMs the persistent grids leave free (for a concurrent NCCL collective) */
-    int32_t disable_fused;      /* 1: never use the single-pass fused kernel (tests / A-B measurements)   */
+    int32_t path_flags;         /* bit 0: use the experimental single-pass kernel (gate_fused.cuh; slower,
+                                 * kept for A/B); bit 1: do not cache spectra between analysis and synthesis
+                                 * (re-transform instead; saves 8 KB of workspace per frame pair)          */
     int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
     int64_t padding;
     double sr;

@@ -36,7 +36,7 @@ class Params(C.Structure):
         ("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop_length", C.c_int32),
         ("n_grad_freq", C.c_int32), ("n_grad_time", C.c_int32), ("std_ddof", C.c_int32),
         ("clip_noise", C.c_int32), ("n_movemean", C.c_int32), ("debug_guard_scale", C.c_int32),
-        ("reserve_sms", C.c_int32), ("disable_fused", C.c_int32),
+        ("reserve_sms", C.c_int32), ("path_flags", C.c_int32),
         ("chunk_size", C.c_int64), ("padding", C.c_int64),
         ("sr", C.c_double), ("prop_decrease", C.c_double), ("n_std_thresh", C.c_double),
         ("top_db", C.c_double), ("time_constant_s", C.c_double), ("thresh_n_mult", C.c_double),

@@ -315,9 +315,9 @@ int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, 
     } while (0)
 
 void launch_k1n(const Geom& g, const Tables& tb, const void* x, int kdt, float* mag, const DebugTap& dbg, int resident,
-                cudaStream_t st) {
+                cudaStream_t st, float2* zc = nullptr) {
     K1nArgs a1{};
-    a1.g = g; a1.tb = tb; a1.x = x; a1.mag = mag; a1.dbg = dbg;
+    a1.g = g; a1.tb = tb; a1.x = x; a1.mag = mag; a1.dbg = dbg; a1.zcache = zc; a1.zpairs = (g.T + 1) / 2;
     long long want = (long long)resident * kWarps * 4;
     long long run = ((long long)g.n_units * g.T + want - 1) / want;
     run = std::max(8LL, std::min(64LL, run));
@@ -684,7 +684,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     if (jp_hi > g.pad) {
         h_lo = (int)((g.pad + NFFT / 2) / g.H);
         h_hi = (int)((jp_hi + NFFT / 2 + g.H - 1) / g.H);
-        tf_lo = std::max(0, h_lo - 3);
+        tf_lo = std::max(0, h_lo - 3) & ~1;          // even: k2 walks k1's (2j, 2j+1) frame pairs when spectra are cached
         tf_hi = std::min(h_hi, g.T);
     }
     const bool tail_zeros = !torch_sem && (g.pad + g.step > sig_len);     // stationary.py:126 leaves the tail zero
@@ -695,13 +695,17 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // ---- workspace / batching ---------------------------------------------------------------------
     const bool stat = p.stationary != 0;
     // single-pass fused kernel: stationary gate, n_fft 1024, filter extents the in-warp smoother handles
-    const bool use_fused = stat && native && !h->force_two_pass && !p.disable_fused &&
+    const bool use_fused = stat && native && !h->force_two_pass && (p.path_flags & 1) &&
                            (2 * p.n_grad_freq + 1 <= 12) && (p.n_grad_time + 1 <= 14);
     const size_t per_unit_2pass = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
                                         : 2 * (size_t)g.T * FP * 4 + 64) +
                                   (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
-    const size_t per_unit = use_fused ? 64 : per_unit_2pass;      // the fused kernel keeps no per-unit buffers
-    double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 16.0 * 1024 * 1024 * 1024;
+    // spectrum cache: k1 / k1n keep the packed spectrum of every frame pair so k2 does not re-transform
+    const int zpairs = (g.T + 1) / 2;
+    const bool use_zcache = !use_fused && !two_k && !(p.path_flags & 2);
+    const size_t zunit = use_zcache ? (size_t)zpairs * 1024 * sizeof(float2) : 0;
+    const size_t per_unit = use_fused ? 64 : per_unit_2pass + zunit;      // the fused kernel keeps no per-unit buffers
+    double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 24.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
@@ -733,13 +737,17 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t off_trow = off_tdb + al((size_t)ub * g.T * kFPad * 4);
     const size_t off_tthr = off_trow + al((size_t)ub * kFPad * 4);
     const size_t end_tstat = off_tthr + al((size_t)ub * kFPad * 4);
+    const size_t end_base = use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
+    const size_t off_z = al(end_base);
+    const size_t end_all = off_z + al((size_t)ub * zunit);
     {
-        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat));
+        int rc = ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, end_all);
         if (rc) return rc;
     }
     float* d_tdb = (float*)(h->d_ws_buf + off_tdb);
     float* d_trow = (float*)(h->d_ws_buf + off_trow);
     float* d_tthr_self = (float*)(h->d_ws_buf + off_tthr);
+    float2* d_zcache = use_zcache ? (float2*)(h->d_ws_buf + off_z) : nullptr;
     unsigned* d_bits = (unsigned*)(h->d_ws_buf + off_bits);
     unsigned* d_rowmax = (unsigned*)(h->d_ws_buf + off_rowmax);
     unsigned* d_rowflag = (unsigned*)(h->d_ws_buf + off_rowflag);
@@ -865,7 +873,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (torch_sem) {
                 // TorchGate: |X| -> dB, per-row statistics over the row's own frames (or xn's), compare
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, kdt, d_tdb, dbg, resident, st);
+                launch_k1n(g, tb, xb, kdt, d_tdb, dbg, resident, st, d_zcache);
                 TStatArgs ta{};
                 ta.n_units = nu; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64;
                 ta.top_db = (float)p.top_db; ta.n_std = (float)p.n_std_thresh; ta.ddof = p.std_ddof;
@@ -889,6 +897,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 // k1: frames per work item: enough items to fill the machine, runs long enough to amortise
                 K1Args a1{};
                 a1.g = g; a1.tb = tb; a1.x = xb; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
+                a1.zcache = d_zcache; a1.zpairs = zpairs;
                 {
                     long long want = (long long)h->num_sm * B200_K1_MINBLOCKS * kWarps * 4;
                     long long run = ((long long)nu * g.T + want - 1) / want;
@@ -938,7 +947,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
                 cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                 K2Args a2{};
-                a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.num = d_num;
+                a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.num = d_num; a2.zcache = d_zcache; a2.zpairs = zpairs;
                 a2.pD = (float)(p.prop_decrease / D);
                 a2.one_minus_p = (float)(1.0 - p.prop_decrease);
                 a2.nt = nt;
@@ -1014,7 +1023,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
             } else {
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, kdt, d_mag, dbg, resident, st);
+                launch_k1n(g, tb, xb, kdt, d_mag, dbg, resident, st, d_zcache);
                 cudaEventRecord(h->stage_ev[4 * bi + 1], st);
                 if (torch_sem) {
                     TMovArgs ma{};
@@ -1046,7 +1055,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
                     cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                     K2Args a2{};
-                    a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.fmask = d_mag;
+                    a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.fmask = d_mag; a2.zcache = d_zcache; a2.zpairs = zpairs;
                     a2.nt = nt;
                     a2.dbg = dbg;
                     {

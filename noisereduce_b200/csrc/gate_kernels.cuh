@@ -233,6 +233,9 @@ struct K1Args {
     DebugTap dbg;
     int run;                   // frames per work item (even)
     int n_runs;                // ceil(T / run)
+    float2* zcache;            // optional [n_units][ceil(T/2)][32 slots][32 lanes]: the packed spectrum of every
+                               // frame pair, kept so that k2 need not transform the frames a second time
+    int zpairs;                // ceil(T/2)
 };
 
 constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats + kWarps * 2 * kFW + 8; }
@@ -289,6 +292,11 @@ __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const 
             float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
             const float S = sqrtf(warp_sum(e));
             warp_fft1024(re, im, tile, s_tw, lane);
+            if (a.zcache) {                                   // warp-uniform
+                float2* zp = a.zcache + ((long long)ul * a.zpairs + (t >> 1)) * 1024 + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) zp[32 * q] = make_float2(re[brev5(q)], im[brev5(q)]);
+            }
 
             unsigned wordA = 0u, wordB = 0u;
             unsigned anyamb = 0u;
@@ -624,6 +632,8 @@ struct K2Args {
     int run;                       // output hops per work item
     int n_runs;
     DebugTap dbg;
+    const float2* zcache;          // optional: spectra stored by k1 / k1n (frames then are not re-transformed)
+    int zpairs;
 };
 
 constexpr int k2_smem_floats(int H) { return 2 * kN + 2 * kN + H + kFPad + kWarps * kExchFloats; }
@@ -682,7 +692,8 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         const int hs = h_lo + run * a.run;
         const int he = min(hs + a.run, h_hi);
         if (hs >= he) continue;
-        const int t_start = max(0, hs - (NH - 1));
+        int t_start = max(0, hs - (NH - 1));
+        if (a.zcache) t_start &= ~1;                 // k1 packed frames (2j, 2j+1): walk the same pairs
         const int t_last = min(he - 1, g.T - 1);
         const T* xrow = static_cast<const T*>(a.x) + (long long)c * g.in_stride;
         T* yrow = static_cast<T*>(a.y) + (long long)c * g.out_stride;
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                 float re[32], im[32];
                 // (no register pre-load of the next pair's rows here: k2 is at its register budget; the
                 //  mask loads below were the dominant exposed latency)
-                load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
+                if (!a.zcache) load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
                 const long long offA = (long long)t * kFPad, offB = (long long)(vb ? t + 1 : t) * kFPad;
                 // the masks of this pair are requested now, a whole FFT before the apply step needs them
                 float mka[kFW], mkb[FMASK ? kFW : 1];         // uint16 numerators travel packed two per register
@@ -740,9 +751,19 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                 // phase 0: forward FFT + mask apply; phase 1: inverse FFT.  One copy of the FFT code
                 // serves both: the apply step leaves Z' with real/imaginary parts exchanged and in
                 // natural slot order, so ifft(Z') = swap(fft(swap(Z'))) is the very same call.
+                const bool cached = a.zcache != nullptr;
+                if (cached) {                                // the forward transform of this pair was done by k1
+                    const float2* zp = a.zcache + ((long long)ul * a.zpairs + (t >> 1)) * 1024 + lane;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float2 v = __ldg(zp + 32 * q);
+                        re[brev5(q)] = v.x;
+                        im[brev5(q)] = v.y;
+                    }
+                }
 #pragma unroll 1
                 for (int ph = 0; ph < 2; ++ph) {
-                    warp_fft1024(re, im, tile, s_tw, lane);
+                    if (!(cached && ph == 0)) warp_fft1024(re, im, tile, s_tw, lane);
                     if (ph == 0) {
 #pragma unroll
                         for (int q = 0; q < kFW; ++q) {
@@ -867,6 +888,8 @@ struct K1nArgs {
     float* mag;                // [n_units][T][FPad]
     DebugTap dbg;
     int run, n_runs;
+    float2* zcache;            // optional, as in K1Args
+    int zpairs;
 };
 
 constexpr int k1n_smem_floats() { return kN + 2 * kN + kWarps * kExchFloats; }
@@ -907,6 +930,11 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
             float re[32], im[32];
             load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
             warp_fft1024(re, im, tile, s_tw, lane);
+            if (a.zcache) {
+                float2* zp = a.zcache + ((long long)ul * a.zpairs + (t >> 1)) * 1024 + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) zp[32 * q] = make_float2(re[brev5(q)], im[brev5(q)]);
+            }
             float* dstA = a.mag + ((long long)ul * g.T + t) * kFPad;
 #pragma unroll
             for (int q = 0; q < kFW; ++q) {

@@ -60,11 +60,13 @@ def test_config2_shaped_chunks_mask_bit_exact(lib):
         _assert_stationary(res)
         assert res["T"] == 2579
         worst = max(worst, res["out_relinf"])
-    assert res["stats"]["fused_path"] == 1          # this geometry runs the single-pass kernel ...
-    two = P.check_stationary(lib, y, cfg, tap_unit=(1, 2), disable_fused=1)    # ... and the two-pass path stays exact
-    assert two["stats"]["fused_path"] == 0
-    _assert_stationary(two)
-    assert P.relinf(res["out"], two["out"]) < P.OUT_TOL_TIGHT
+    # the default path caches spectra between analysis and synthesis; the re-transform variant (path_flags 2)
+    # and the experimental single-pass kernel (path_flags 1) must agree with it and with the oracle
+    for flags in (2, 1):
+        alt = P.check_stationary(lib, y, cfg, tap_unit=(1, 2), path_flags=flags)
+        assert alt["stats"]["fused_path"] == (1 if flags == 1 else 0)
+        _assert_stationary(alt)
+        assert P.relinf(res["out"], alt["out"]) < P.OUT_TOL_TIGHT
     print("config-2 geometry: worst rel-inf", worst, "rechecked", res["stats"]["bins_rechecked_fp64"])
     # the library's own thresholds, end to end
     res = P.check_stationary(lib, y, cfg, tap_unit=(1, 0), inject_thresh=False)
