@@ -211,7 +211,7 @@ def main():
         chained_noise_stats(dg, x, rank, world)
     gathered = torch.empty((world * C, n), dtype=torch.float32, device=device) if world > 1 else None
     comm_stream = torch.cuda.Stream() if world > 1 else None
-    acc_stats = {"k1_ms": 0.0, "smooth_ms": 0.0, "k2_ms": 0.0, "kernel_launches": 0}
+    acc_stats = {"k1_ms": 0.0, "smooth_ms": 0.0, "k2_ms": 0.0, "fused_ms": 0.0, "kernel_launches": 0}
 
     def step():
         if world == 1:
