@@ -193,6 +193,32 @@ __device__ __forceinline__ void prefetch_next_pair(const T* __restrict__ xrow, l
     }
 }
 
+// Asynchronous global -> shared copies (LDGSTS): the next frame pair's cached spectrum is requested one whole
+// iteration before it is needed and costs no registers while in flight.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef B200_CUSIM_BUILD
+    memcpy(smem_dst, gmem_src, 16);
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+#ifndef B200_CUSIM_BUILD
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef B200_CUSIM_BUILD
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef B200_CUSIM_BUILD
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 #ifdef B200_CUSIM_BUILD
 #define B200_NOINLINE __attribute__((noinline))
 #else
@@ -636,7 +662,7 @@ struct K2Args {
     int zpairs;
 };
 
-constexpr int k2_smem_floats(int H) { return 2 * kN + 2 * kN + H + kFPad + kWarps * kExchFloats; }
+constexpr int k2_smem_floats(int H) { return 2 * kN + 2 * kN + H + kFPad + kWarps * kExchFloats + 8 + kWarps * 2 * kN; }
 
 // time edge factor of the zero-padded smoothing: sum of the triangle taps that stay inside [0, T)
 __device__ __forceinline__ float time_edge(int t, int T, int nt) {
@@ -669,6 +695,8 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = s_tiles + warp * kExchFloats;
+    // per-warp staging buffer of one cached spectrum (8 KB), 16-byte aligned behind the tiles
+    float2* zbuf = reinterpret_cast<float2*>(s_tiles + kWarps * kExchFloats + 8) + warp * kN;
     const int pl = (32 - lane) & 31;
     const long long n_items = (long long)g.n_units * a.n_runs;
     const bool blend = (a.one_minus_p != 0.f);
@@ -706,6 +734,15 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         float nx[2 * HR];
 #pragma unroll
         for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
+
+        auto stage_spectrum = [&](int tt) {            // request pair (tt, tt+1)'s spectrum into zbuf
+            const char* src = reinterpret_cast<const char*>(a.zcache + ((long long)ul * a.zpairs + (tt >> 1)) * 1024);
+            char* dst = reinterpret_cast<char*>(zbuf);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cp_async16(dst + (lane + 32 * j) * 16, src + (lane + 32 * j) * 16);
+            cp_async_commit();
+        };
+        if (a.zcache && t_start <= t_last) stage_spectrum(t_start);
 
         for (int t = t_start; t < he; t += 2) {
             const bool va = (t <= t_last), vb = (t + 1 <= t_last);
@@ -753,13 +790,16 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                 // natural slot order, so ifft(Z') = swap(fft(swap(Z'))) is the very same call.
                 const bool cached = a.zcache != nullptr;
                 if (cached) {                                // the forward transform of this pair was done by k1
-                    const float2* zp = a.zcache + ((long long)ul * a.zpairs + (t >> 1)) * 1024 + lane;
+                    cp_async_wait_all();
+                    __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
-                        const float2 v = __ldg(zp + 32 * q);
+                        const float2 v = zbuf[32 * q + lane];
                         re[brev5(q)] = v.x;
                         im[brev5(q)] = v.y;
                     }
+                    __syncwarp();
+                    if (t + 2 <= t_last) stage_spectrum(t + 2);   // next pair streams in behind this pair's math
                 }
 #pragma unroll 1
                 for (int ph = 0; ph < 2; ++ph) {
