@@ -202,7 +202,9 @@ def main():
     x = synth_device(torch, C, n, rank * C, device)
     out = torch.empty_like(x)
     # multi-GPU: the persistent grids leave 16 SMs free so the NCCL all-gather kernels run concurrently
-    dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256, reserve_sms=16 if world > 1 else 0)
+    # workspace: bits + mask numerators + cached spectra of all 3072 units (41 GB) in one batch -> one launch per kernel
+    dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256, reserve_sms=16 if world > 1 else 0,
+                    workspace_limit_bytes=64e9)
     # noise statistics once (stationary.py:61-81): the reference's sequential channel mean, chained over ranks
     if world == 1:
         dg.noise_stats(x)
@@ -304,7 +306,8 @@ def main():
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * C * n,
                      "kernel_ms": {"k1_analyze+k_rowfloor": k1 / args.steps, "k_smooth": sm / args.steps, "k2_synthesize": k2_ms},
                      "whole_step": {"achieved": pipe_ach, "frac": pipe_ach / (peak * world)},
-                     "note": "FP32-issue/shared-memory bound, not HBM bound: ~80k thread-instructions per 256-sample frame"},
+                     "traffic_note": "ncu dram bytes of k2 (cached spectra 31.7 GB + mask numerators 8.6 GB + waveform) -- profiles/k2_traffic.json",
+                     "note": "instruction-issue / dependency bound, not HBM bound (k2: ~2000 warp-instructions per frame pair, 60 % issue-active)"},
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": clocks,

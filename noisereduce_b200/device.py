@@ -19,7 +19,8 @@ class DeviceGate:
     def __init__(self, sr, stationary=True, prop_decrease=1.0, time_constant_s=2.0, freq_mask_smooth_hz=500,
                  time_mask_smooth_ms=50, thresh_n_mult_nonstationary=2, sigmoid_slope_nonstationary=10,
                  n_std_thresh_stationary=1.5, chunk_size=600000, padding=30000, n_fft=1024, win_length=None,
-                 hop_length=None, clip_noise_stationary=True, lib=None, reserve_sms=0):
+                 hop_length=None, clip_noise_stationary=True, lib=None, reserve_sms=0, workspace_limit_bytes=0.0,
+                 path_flags=0):
         # reuse the reference-mirroring argument resolution (defaults, smoothing extents, errors)
         geo = SpectralGate(np.zeros(1, np.float32), sr, prop_decrease, chunk_size, padding, n_fft, win_length,
                            hop_length, time_constant_s, freq_mask_smooth_hz, time_mask_smooth_ms, None, False, 1)
@@ -27,7 +28,8 @@ class DeviceGate:
         p.update(stationary=1 if stationary else 0, n_std_thresh=float(n_std_thresh_stationary),
                  clip_noise=1 if clip_noise_stationary else 0, time_constant_s=float(time_constant_s),
                  thresh_n_mult=float(thresh_n_mult_nonstationary), sigmoid_slope=float(sigmoid_slope_nonstationary),
-                 reserve_sms=int(reserve_sms))
+                 reserve_sms=int(reserve_sms), workspace_limit_bytes=float(workspace_limit_bytes),
+                 path_flags=int(path_flags))
         self.gate = _cabi.Gate(lib=lib, **p)
         self.stationary = stationary
 
