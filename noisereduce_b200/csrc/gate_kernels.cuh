@@ -123,32 +123,16 @@ __device__ __forceinline__ bool pair_window_interior(long long base, long long i
     return base >= 0 && base + span <= Lp && g0 >= 0 && g0 + span <= n_total;
 }
 
-// Software pipelining of the HBM latency: the 2*HR rows of the NEXT pair that this pair has not
-// touched are requested before this pair's FFT and sit in registers until the next iteration; the
-// other 32-HR rows were read by this pair and come back from L1.
-template <int HR, typename T>
-__device__ __forceinline__ void load_new_rows(float (&nx)[2 * HR], const T* __restrict__ xrow, long long base_next,
-                                              long long i1, int lane) {
-    const T* p = xrow + i1 + base_next + 32 * (32 - HR) + lane;
-#pragma unroll
-    for (int r = 0; r < 2 * HR; ++r) nx[r] = ld_sample(p + 32 * r);
-}
-
-// Load (or assemble from the pre-loaded rows) the raw samples of the pair, window them and pack the
-// two frames as one complex signal.  Returns this lane's contribution to ||frame pair||^2.
+// Load the raw samples of the pair (coalesced 128-byte rows straight into FFT order), window them and pack
+// the two frames as one complex signal.  Returns this lane's contribution to ||frame pair||^2.
+// (Measured and dropped: prefetch.global.L1 of the next pair's rows -- no effect -- and a register pre-load
+//  of them -- more bookkeeping than hidden latency; see profiles/r01_scaling_notes.md.)
 template <int HR, typename T>
 __device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32], const T* __restrict__ xrow,
                                                  long long base, long long i1, long long Lp, long long n_total,
-                                                 const float* __restrict__ s_wa, int lane, bool vb,
-                                                 const float (&nx)[2 * HR], bool have_nx) {
+                                                 const float* __restrict__ s_wa, int lane, bool vb) {
     float xr[32 + HR];
-    if (have_nx) {                                   // interior pair whose new rows were pre-loaded
-        const T* p = xrow + i1 + base + lane;
-#pragma unroll
-        for (int r = 0; r < 32 - HR; ++r) xr[r] = ld_sample(p + 32 * r);
-#pragma unroll
-        for (int r = 0; r < 2 * HR; ++r) xr[32 - HR + r] = nx[r];
-    } else if (pair_window_interior<HR>(base, i1, Lp, n_total)) {
+    if (pair_window_interior<HR>(base, i1, Lp, n_total)) {
         const T* p = xrow + i1 + base + lane;
 #pragma unroll
         for (int r = 0; r < 32 + HR; ++r) xr[r] = ld_sample(p + 32 * r);
@@ -172,25 +156,6 @@ __device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32
         for (int r = 0; r < 32; ++r) im[r] = 0.f;
     }
     return e;
-}
-
-// Pull the next frame pair's new samples (2 hops) towards L1 while this pair is being transformed.
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-#ifndef B200_CUSIM_BUILD
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-template <int HR, typename T>
-__device__ __forceinline__ void prefetch_next_pair(const T* __restrict__ xrow, long long base_next, long long i1,
-                                                   long long Lp, long long n_total, int lane) {
-    // rows 32-HR .. 31+HR of the next pair are the ones this pair has not touched: 2*HR rows of 128 B
-    if (lane < 2 * HR) {
-        const long long j = base_next + 32LL * (32 - HR + lane);
-        const long long gidx = i1 + j;
-        if (j >= 0 && j + 32 <= Lp && gidx >= 0 && gidx + 32 <= n_total) prefetch_l1(xrow + gidx);
-    }
 }
 
 // Asynchronous global -> shared copies (LDGSTS): the next frame pair's cached spectrum is requested one whole
@@ -307,15 +272,11 @@ __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const 
 #pragma unroll
         for (int q = 0; q < kFW; ++q) mx[q] = 0.f;
 
-        float nx[2 * HR];
-#pragma unroll
-        for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
-            // (measured: pre-loading the next pair's rows costs k1 more bookkeeping than it hides)
-            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
+            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb);
             const float S = sqrtf(warp_sum(e));
             warp_fft1024(re, im, tile, s_tw, lane);
             if (a.zcache) {                                   // warp-uniform
@@ -731,9 +692,6 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         float acc[32 + HR];
 #pragma unroll
         for (int r = 0; r < 32 + HR; ++r) acc[r] = 0.f;
-        float nx[2 * HR];
-#pragma unroll
-        for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
 
         auto stage_spectrum = [&](int tt) {            // request pair (tt, tt+1)'s spectrum into zbuf
             const char* src = reinterpret_cast<const char*>(a.zcache + ((long long)ul * a.zpairs + (tt >> 1)) * 1024);
@@ -749,9 +707,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
             if (va) {                                   // vb implies va
                 const long long base = (long long)t * H - kN / 2;
                 float re[32], im[32];
-                // (no register pre-load of the next pair's rows here: k2 is at its register budget; the
-                //  mask loads below were the dominant exposed latency)
-                if (!a.zcache) load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
+                if (!a.zcache) load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb);
                 const long long offA = (long long)t * kFPad, offB = (long long)(vb ? t + 1 : t) * kFPad;
                 // the masks of this pair are requested now, a whole FFT before the apply step needs them
                 float mka[kFW], mkb[FMASK ? kFW : 1];         // uint16 numerators travel packed two per register
@@ -961,14 +917,11 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
         const T* xrow = static_cast<const T*>(a.x) + (long long)c * g.in_stride;
         const int t0 = run * a.run;
         const int t1 = min(t0 + a.run, g.T);
-        float nx[2 * HR];
-#pragma unroll
-        for (int r = 0; r < 2 * HR; ++r) nx[r] = 0.f;
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
-            load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb, nx, false);
+            load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb);
             warp_fft1024(re, im, tile, s_tw, lane);
             if (a.zcache) {
                 float2* zp = a.zcache + ((long long)ul * a.zpairs + (t >> 1)) * 1024 + lane;

@@ -12,9 +12,9 @@
 // Only __syncwarp() is needed: a warp never waits for another warp.  The radix-32 butterfly is a
 // fully unrolled radix-2 DIF network whose 32-point twiddles are compile-time immediates.
 //
-// Bit-reversal is never executed: the DIF network leaves frequency q in register slot brev5(q); all
-// callers index slots through brev5() with compile-time q, and dft32<true> accepts bit-reversed
-// slots and returns natural ones, so forward/inverse chains need no permutation instructions.
+// Bit-reversal is never executed: the DIF network leaves frequency q in register slot brev5(q) and all
+// callers index slots through brev5() with compile-time q.  Stages 2..5 of the network run on packed
+// f32x2 registers (dft32_packed); dft32_scalar is the reference form of the same network.
 //
 // Inverse transform: ifft(z) = swap(fft(swap(z))) / N with swap(a + ib) = b + ia, i.e. simply call
 // warp_fft1024(im, re) -- the scaling is folded into the synthesis window by the callers.
