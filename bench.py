@@ -266,27 +266,40 @@ def main():
     # ---- end to end through the C ABI with host buffers ----------------------------------------------
     e2e = None
     if not args.no_e2e:
-        hx = torch.empty((C, n), dtype=torch.float32, pin_memory=True)
-        hy = torch.empty((C, n), dtype=torch.float32, pin_memory=True)
-        hx.copy_(x)
-        st = torch.cuda.current_stream().cuda_stream
-        def e2e_step():
-            dg.gate._check(dg.gate.lib.dll.b200gate_run(dg.gate._h, hx.data_ptr(), hy.data_ptr(), 0, C, n, n, n, 0, st))
-        e2e_step()
-        barrier()
-        ksteps = max(2, min(args.steps, 4))
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
+        try:
+            hx = torch.empty((C, n), dtype=torch.float32, pin_memory=True)
+            hy = torch.empty((C, n), dtype=torch.float32, pin_memory=True)
+            hx.copy_(x)
+            st = torch.cuda.current_stream().cuda_stream
+
+            def e2e_step():
+                dg.gate._check(dg.gate.lib.dll.b200gate_run(dg.gate._h, hx.data_ptr(), hy.data_ptr(), 0, C, n, n, n, 0, st))
+
             e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / ksteps
+            barrier()
+            ksteps = max(2, min(args.steps, 4))
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / ksteps
+            ok = 1.0
+        except Exception as exc:                      # e.g. pinned-memory limits with many ranks on one host
+            dt, ok, ksteps = 0.0, 0.0, 0
+            e2e_err = repr(exc)[:200]
         if world > 1:
-            tt = torch.tensor([dt], device=device)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        e2e = {"value": world * C * n / dt, "unit": UNIT, "h2d_bytes_per_step": C * n * 4, "d2h_bytes_per_step": C * n * 4,
-               "ms_per_step": dt * 1e3, "steps": ksteps, "parity_vs_device_path": float((hy.to(device) - out).abs().max().item())}
-        del hx, hy
+            tt = torch.tensor([dt, ok], device=device)
+            dist.all_reduce(tt[0:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt[1:2], op=dist.ReduceOp.MIN)
+            dt, ok = float(tt[0].item()), float(tt[1].item())
+        if ok > 0 and dt > 0:
+            e2e = {"value": world * C * n / dt, "unit": UNIT, "h2d_bytes_per_step": C * n * 4,
+                   "d2h_bytes_per_step": C * n * 4, "ms_per_step": dt * 1e3, "steps": ksteps,
+                   "parity_vs_device_path": float((hy.to(device) - out).abs().max().item()),
+                   "note": "per-rank host buffers (pinned), slab-pipelined H2D / kernels / D2H; no collective in this leg"}
+        else:
+            e2e = {"value": None, "unit": UNIT, "error": locals().get("e2e_err", "failed on another rank")}
+        hx = hy = None
 
     if rank != 0:
         if world > 1:
