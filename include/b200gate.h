@@ -133,6 +133,13 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
 int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64_t C, int64_t N,
                  int64_t in_stride, int64_t out_stride, int is_device, void* cuda_stream);
 
+/* Sub-range processing for the next b200gate_run calls (SpectralGate.get_traces(start_frame, end_frame),
+ * base.py:167-226).  mode 0: the whole recording (default).  mode 1: only chunks [a, b] of the chunk grid
+ * anchored at sample 0 (the reference's chunked branch); samples outside those chunks are not written.
+ * mode 2: one padded chunk covering [0, a) whose padding is read from the recording itself (the reference's
+ * `filter_chunk(0, end_frame)` branch, base.py:222); only out[:, 0:a] is written. */
+int b200gate_set_range(b200gate_handle* h, int32_t mode, int64_t a, int64_t b);
+
 int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out);
 
 /* ---- parity-test taps (tests/ only; read back stage outputs of the last run) ---------------- */

@@ -25,7 +25,7 @@ EXPORTS = [
     "b200gate_noise_stats_collapsed", "b200gate_channel_sum", "b200gate_set_noise_threshold",
     "b200gate_get_noise_threshold", "b200gate_get_noise_mean_std", "b200gate_set_window",
     "b200gate_torch_set_noise",
-    "b200gate_run", "b200gate_get_stats", "b200gate_debug_select_unit", "b200gate_debug_dims",
+    "b200gate_run", "b200gate_set_range", "b200gate_get_stats", "b200gate_debug_select_unit", "b200gate_debug_dims",
     "b200gate_debug_read_bits", "b200gate_debug_read_mask", "b200gate_debug_read_spec",
 ]
 
@@ -92,6 +92,7 @@ class GateLibrary:
         d.b200gate_set_window.argtypes = [vp, C.POINTER(C.c_float), i32]
         d.b200gate_torch_set_noise.argtypes = [vp, vp, C.c_int, i64, i64, i64, C.c_int, vp]
         d.b200gate_run.argtypes = [vp, vp, vp, C.c_int, i64, i64, i64, i64, C.c_int, vp]
+        d.b200gate_set_range.argtypes = [vp, i32, i64, i64]
         d.b200gate_get_stats.argtypes = [vp, C.POINTER(Stats)]
         d.b200gate_debug_select_unit.argtypes = [vp, i64, i64]
         d.b200gate_debug_dims.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
@@ -205,6 +206,9 @@ class Gate:
     def run_device(self, in_ptr, out_ptr, dtype, C_, N, in_stride, out_stride, stream=None):
         self._check(self.lib.dll.b200gate_run(
             self._h, in_ptr, out_ptr, dtype_code(dtype), C_, N, in_stride, out_stride, 1, stream))
+
+    def set_range(self, mode: int, a: int = 0, b: int = 0):
+        self._check(self.lib.dll.b200gate_set_range(self._h, mode, a, b))
 
     def stats(self) -> dict:
         s = Stats()

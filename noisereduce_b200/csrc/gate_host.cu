@@ -47,6 +47,8 @@ struct b200gate_handle {
     bool have_thresh = false;
     double min_floor_amp = 0.0;                    // min_f 10^((thresh+top_db)/20): smallest |X| that lifts a row
     bool force_two_pass = false;
+    int range_mode = 0;                            // b200gate_set_range
+    long long range_a = 0, range_b = 0;
     unsigned* d_maxabs = nullptr;
     char* d_fscratch = nullptr;                    // fused kernel: per-warp spectra + decision rows
     size_t fscratch_bytes = 0;
@@ -546,6 +548,14 @@ int b200gate_debug_read_spec(b200gate_handle* h, float* spec) {
     return B200GATE_OK;
 }
 
+int b200gate_set_range(b200gate_handle* h, int32_t mode, int64_t a, int64_t b) {
+    if (!h) return B200GATE_ERR_ARG;
+    if (mode < 0 || mode > 2 || (mode == 1 && (a < 0 || b < a)) || (mode == 2 && a <= 0))
+        return fail(h, B200GATE_ERR_ARG, "bad range (mode %d, %lld, %lld)", mode, (long long)a, (long long)b);
+    h->range_mode = mode; h->range_a = a; h->range_b = b;
+    return B200GATE_OK;
+}
+
 int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out) {
     if (!h || !out) return B200GATE_ERR_ARG;
     *out = h->stats;
@@ -607,6 +617,28 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     h->stats = b200gate_stats{};
     long long launches = 0;
 
+    // ---- which part of the recording (base.py:167-226; b200gate_set_range) -----------------------------
+    // range_mode 2: the reference's single padded chunk [0, a) inside a longer recording (base.py:222)
+    const bool single_to = !torch_sem && h->range_mode == 2;
+    if (single_to && h->range_a > N) return fail(h, B200GATE_ERR_ARG, "range end %lld beyond the recording", h->range_a);
+    const bool chunked = !torch_sem && !single_to && p.chunk_size > 0 && N > p.chunk_size;
+    const long long step = chunked ? p.chunk_size : (single_to ? h->range_a : N);
+    const long long n_chunks = chunked ? (N - 1) / p.chunk_size + 1 : 1;
+    // range_mode 1: a sub-range of the chunk grid
+    long long chunk_first = 0, chunk_count = n_chunks;
+    if (!torch_sem && h->range_mode == 1) {
+        if (!chunked || h->range_b >= n_chunks) return fail(h, B200GATE_ERR_ARG, "chunk range outside the chunk grid");
+        chunk_first = h->range_a;
+        chunk_count = h->range_b - h->range_a + 1;
+    }
+    // samples written [o_lo, o_hi) and samples read [w_lo, w_hi)
+    const long long o_lo = chunk_first * step;
+    const long long o_hi = torch_sem ? No : std::min<long long>(N, (chunk_first + chunk_count) * step);
+    const long long rpad = torch_sem ? 0 : p.padding;
+    const long long w_lo = torch_sem ? 0 : std::max(0LL, o_lo - rpad);
+    const long long w_hi = torch_sem ? N : std::min<long long>(N, o_hi + rpad);
+    const long long Wn = w_hi - w_lo, On = o_hi - o_lo;
+
     // ---- where the kernels read / write ---------------------------------------------------------------
     // The n_fft = 1024 numpy-surface kernels are templated on the sample dtype: they read the caller's
     // float32 / int16 / float64 rows directly and cast on store (base.py:140, :218-226).  The 2048 family and
@@ -621,36 +653,38 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // Host input that the reference would chunk: stream it through the GPU slab by slab (H2D of slab k+1,
     // kernels of slab k and D2H of slab k-1 overlap on three streams) instead of staging the whole
     // recording -- the role of _read_chunk + the memmap write-back (base.py:130-187).
-    const bool pipelined = !is_device && kdt == dtype && !torch_sem && h->p.chunk_size > 0 &&
-                           N > h->p.chunk_size && h->p.padding >= h->p.hop_length;
+    const bool pipelined = !is_device && kdt == dtype && chunked && h->p.padding >= h->p.hop_length;
     if (direct || pipelined) {
         x = in;
         y = out;
     } else {
+        // stage the window that is read / written; the kernels keep absolute sample indices through virtual
+        // row bases (x - w_lo, y - o_lo)
         int rc;
-        if ((rc = ensure(h, (void**)&h->d_in, &h->in_bytes, (size_t)C * N * kes))) return rc;
-        if ((rc = ensure(h, (void**)&h->d_out, &h->out_bytes, (size_t)C * N * kes))) return rc;
-        x = h->d_in;
-        y = h->d_out;
-        xs = ys = N;
-        if (kdt == dtype) {                                   // host rows, whole recording at once
-            CK(h, cudaMemcpy2DAsync(h->d_in, (size_t)N * es, in, (size_t)in_stride * es, (size_t)N * es, (size_t)C,
-                                    cudaMemcpyHostToDevice, st));
+        if ((rc = ensure(h, (void**)&h->d_in, &h->in_bytes, (size_t)C * Wn * kes))) return rc;
+        if ((rc = ensure(h, (void**)&h->d_out, &h->out_bytes, (size_t)C * On * kes))) return rc;
+        x = (const char*)h->d_in - (size_t)w_lo * kes;
+        y = (char*)h->d_out - (size_t)o_lo * kes;
+        xs = Wn;
+        ys = On;
+        if (kdt == dtype) {                                   // host rows
+            CK(h, cudaMemcpy2DAsync(h->d_in, (size_t)Wn * es, (const char*)in + (size_t)w_lo * es, (size_t)in_stride * es,
+                                    (size_t)Wn * es, (size_t)C, cudaMemcpyHostToDevice, st));
         } else {                                              // float32-only kernel family: convert at the edge
-            const void* raw = in;
+            const void* raw = (const char*)in + (size_t)w_lo * es;
             long long rs = in_stride;
             if (!is_device) {
-                if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * N * es))) return rc;
-                CK(h, cudaMemcpy2DAsync(h->d_raw, (size_t)N * es, in, (size_t)in_stride * es, (size_t)N * es, (size_t)C,
+                if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * std::max(Wn, On) * es))) return rc;
+                CK(h, cudaMemcpy2DAsync(h->d_raw, (size_t)Wn * es, raw, (size_t)in_stride * es, (size_t)Wn * es, (size_t)C,
                                         cudaMemcpyHostToDevice, st));
                 raw = h->d_raw;
-                rs = N;
+                rs = Wn;
             }
-            const int gr = grid_1d((long long)C * N, 256, h->num_sm * 16);
+            const int gr = grid_1d((long long)C * Wn, 256, h->num_sm * 16);
             if (dtype == B200GATE_I16)
-                { auto kern_ = k_to_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const short*)raw, (float*)h->d_in, (long long)C, (long long)N, rs, (long long)N); }
+                { auto kern_ = k_to_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const short*)raw, (float*)h->d_in, (long long)C, (long long)Wn, rs, (long long)Wn); }
             else
-                { auto kern_ = k_to_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const double*)raw, (float*)h->d_in, (long long)C, (long long)N, rs, (long long)N); }
+                { auto kern_ = k_to_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const double*)raw, (float*)h->d_in, (long long)C, (long long)Wn, rs, (long long)Wn); }
             ++launches;
         }
     }
@@ -662,16 +696,16 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     g.H = p.hop_length;
     g.C = (int)C;
     g.n_total = N;
-    const bool chunked = !torch_sem && p.chunk_size > 0 && N > p.chunk_size;
-    g.step = chunked ? p.chunk_size : N;
-    g.n_chunks = chunked ? (int)((N - 1) / p.chunk_size) + 1 : 1;
+    g.step = step;
+    g.n_chunks = (int)n_chunks;
     g.pad = torch_sem ? 0 : p.padding;                 // TorchGate filters the whole row, no chunk padding
     g.Lp = g.step + 2 * g.pad;
     g.T = (int)(g.Lp / g.H) + 1;
     g.in_stride = xs;
     g.out_stride = ys;
-    const long long U = (long long)g.n_chunks * C;
-    if (U > 0x7fffffffLL || g.Lp / g.H > 0x3fffffffLL) return fail(h, B200GATE_ERR_ARG, "problem too large");
+    const long long U = chunk_count * C;
+    const long long Ubase = chunk_first * C;               // first unit of the selected range
+    if (Ubase + U > 0x7fffffffLL || g.Lp / g.H > 0x3fffffffLL) return fail(h, B200GATE_ERR_ARG, "problem too large");
 
     const int NFFT = p.n_fft;
     const bool two_k = NFFT == kN2;
@@ -689,7 +723,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     }
     const bool tail_zeros = !torch_sem && (g.pad + g.step > sig_len);     // stationary.py:126 leaves the tail zero
     if (tail_zeros) {
-        for (long long c = 0; c < C; ++c) CK(h, cudaMemsetAsync((char*)y + (size_t)c * ys * kes, 0, (size_t)N * kes, st));
+        for (long long c = 0; c < C; ++c)
+            CK(h, cudaMemsetAsync((char*)y + ((size_t)c * ys + (size_t)o_lo) * kes, 0, (size_t)On * kes, st));
     }
 
     // ---- workspace / batching ---------------------------------------------------------------------
@@ -711,7 +746,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
     if (pipelined) {
         // ~512 MB of input per slab, whole chunks, within the workspace limit
-        slab_chunks = std::max(1LL, std::min<long long>(g.n_chunks, (512LL << 20) / std::max<long long>(1, C * g.step * (long long)es)));
+        slab_chunks = std::max(1LL, std::min<long long>(chunk_count, (512LL << 20) / std::max<long long>(1, C * g.step * (long long)es)));
         slab_chunks = std::max(1LL, std::min(slab_chunks, ub / C));
         if (ub < C) return fail(h, B200GATE_ERR_NOMEM, "workspace limit too small for one chunk of all channels");
         ub = slab_chunks * C;
@@ -811,13 +846,13 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     cudaEventRecord(evk0, st);
     for (long long u0 = 0; u0 < U; u0 += ub, ++bi) {
         const int nu = (int)std::min(ub, U - u0);
-        g.u0 = (int)u0;
+        g.u0 = (int)(Ubase + u0);
         g.n_units = nu;
         const void* xb = x;
         void* yb = y;
         if (pipelined) {
             // slab = chunks [c0, c1): input window [w0, w1) of every channel, output [c0*step, o1)
-            const long long c0 = u0 / C, c1 = c0 + nu / C;
+            const long long c0 = (Ubase + u0) / C, c1 = c0 + nu / C;
             const long long w0 = std::max(0LL, c0 * g.step - g.pad), w1 = std::min<long long>(N, c1 * g.step + g.pad);
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
@@ -835,7 +870,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             (void)o1;
         }
         DebugTap dbg{};
-        dbg.ul = (dbg_u >= u0 && dbg_u < u0 + nu) ? (int)(dbg_u - u0) : -1;
+        dbg.ul = (dbg_u >= Ubase + u0 && dbg_u < Ubase + u0 + nu) ? (int)(dbg_u - Ubase - u0) : -1;
         dbg.spec = h->d_dbg_spec;
         dbg.mask = h->d_dbg_mask;
 
@@ -1087,7 +1122,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         }
         CK(h, cudaGetLastError());
         if (pipelined) {
-            const long long c0 = u0 / C, c1 = c0 + nu / C;
+            const long long c0 = (Ubase + u0) / C, c1 = c0 + nu / C;
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
             const void* d2h_src = h->d_slab_out[ib];
@@ -1106,22 +1141,23 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
 
     // ---- results back -------------------------------------------------------------------------------
     if (!direct && !pipelined) {
+        void* out_w = (char*)out + (size_t)o_lo * es;             // first written sample of row 0
         if (kdt == dtype) {
-            CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, y, (size_t)ys * es, (size_t)No * es, (size_t)C,
+            CK(h, cudaMemcpy2DAsync(out_w, (size_t)out_stride * es, h->d_out, (size_t)On * es, (size_t)On * es, (size_t)C,
                                     cudaMemcpyDeviceToHost, st));
         } else {
             int rc;
-            if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * N * es))) return rc;
-            const int gr = grid_1d((long long)C * No, 256, h->num_sm * 16);
-            void* dst = is_device ? out : h->d_raw;
-            const long long ds = is_device ? out_stride : No;
+            if ((rc = ensure(h, &h->d_raw, &h->raw_bytes, (size_t)C * std::max(Wn, On) * es))) return rc;
+            const int gr = grid_1d((long long)C * On, 256, h->num_sm * 16);
+            void* dst = is_device ? out_w : h->d_raw;
+            const long long ds = is_device ? out_stride : On;
             if (dtype == B200GATE_I16)
-                { auto kern_ = k_from_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (short*)dst, (long long)C, (long long)No, ys, ds); }
+                { auto kern_ = k_from_f32<short>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)h->d_out, (short*)dst, (long long)C, (long long)On, (long long)On, ds); }
             else
-                { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)y, (double*)dst, (long long)C, (long long)No, ys, ds); }
+                { auto kern_ = k_from_f32<double>; B200_LAUNCH(kern_, dim3(gr), dim3(256), 0, st, (const float*)h->d_out, (double*)dst, (long long)C, (long long)On, (long long)On, ds); }
             ++launches;
             if (!is_device)
-                CK(h, cudaMemcpy2DAsync(out, (size_t)out_stride * es, h->d_raw, (size_t)No * es, (size_t)No * es, (size_t)C,
+                CK(h, cudaMemcpy2DAsync(out_w, (size_t)out_stride * es, h->d_raw, (size_t)On * es, (size_t)On * es, (size_t)C,
                                         cudaMemcpyDeviceToHost, st));
         }
     }

@@ -110,9 +110,10 @@ class SpectralGate:
             return np.ascontiguousarray(y2d)
         return np.ascontiguousarray(y2d, dtype=np.float64)
 
-    def _run(self, y2d):
+    def _run(self, y2d, lo=0, hi=None):
+        """One library call; returns columns [lo, hi) of the (partially written) output rows."""
         x = self._samples_for_device(y2d)
-        out = self._gate.run_host(x)
+        out = self._gate.run_host(x)[:, lo:hi]
         if out.dtype != self._dtype:
             with np.errstate(invalid="ignore"):
                 out = out.astype(self._dtype)                  # base.py:218-226
@@ -120,14 +121,28 @@ class SpectralGate:
 
     def get_traces(self, start_frame=None, end_frame=None):
         """base.py:167-226.  With both bounds None this is the whole recording (what reduce_noise
-        calls); a sub-range reproduces the reference's chunk-grid-anchored result by slicing."""
+        calls).  A sub-range runs only the units the reference would: the chunks
+        int(start/cs)..int((end-1)/cs) of the grid anchored at sample 0 when the range is longer
+        than chunk_size (base.py:175-217), else ONE padded chunk covering [0, end_frame) whose
+        padding is read from the recording (base.py:222 -- start_frame is ignored there, as in
+        the reference)."""
         if start_frame is None:
             start_frame = 0
         if end_frame is None:
             end_frame = self.n_frames
-        full = self._run(self.y)
         if self._chunk_size is not None and end_frame - start_frame > self._chunk_size:
-            res = full[:, start_frame:end_frame]
+            # the reference's memmap has end-start columns; a range past the recording fails there too
+            if start_frame < 0 or end_frame > self.n_frames:
+                raise ValueError("start_frame / end_frame outside the recording")
+            self._gate.set_range(1, int(start_frame / self._chunk_size), int((end_frame - 1) / self._chunk_size))
+            lo = start_frame
         else:
-            res = full[:, 0:end_frame]                          # base.py:222 ignores start_frame
+            if not 0 < end_frame <= self.n_frames:
+                raise ValueError("end_frame outside the recording")
+            self._gate.set_range(2, int(end_frame))
+            lo = 0
+        try:
+            res = self._run(self.y, lo, end_frame)
+        finally:
+            self._gate.set_range(0)
         return res.flatten() if self.flat else res

@@ -86,21 +86,35 @@ def smoothing_extents(sr, n_fft, hop_length, freq_mask_smooth_hz, time_mask_smoo
     return True, n_grad_freq, n_grad_time
 
 
-def chunk_table(n_frames: int, chunk_size: Optional[int], padding: int) -> List[Tuple[int, int, int, int]]:
-    """base.py:167-226 (get_traces with start_frame=0, end_frame=n_frames).
+def chunk_table(n_frames: int, chunk_size: Optional[int], padding: int,
+                start_frame: Optional[int] = None, end_frame: Optional[int] = None) -> List[Tuple[int, int, int, int]]:
+    """base.py:167-226 (get_traces; start_frame / end_frame default to the whole recording).
 
     Returns a list of (i1, i2, out_lo, out_hi): the padded span [i1, i2) read by _read_chunk
     (base.py:130-142, zeros outside [0, n_frames)) and the output span [out_lo, out_hi) its centre
-    fills.  One entry when n_frames <= chunk_size (base.py:222), else one per chunk.
+    fills.  Chunked branch (base.py:175-217): chunks int(start/cs) .. int((end-1)/cs) of the grid
+    anchored at sample 0, trimmed to [start, end).  Otherwise (base.py:222) ONE padded chunk
+    covering [0, end_frame) -- start_frame is ignored there, as in the reference.
     """
-    if chunk_size is not None and n_frames > chunk_size:
-        last = int((n_frames - 1) / chunk_size)
+    start = 0 if start_frame is None else start_frame
+    end = n_frames if end_frame is None else end_frame
+    if chunk_size is not None and end - start > chunk_size:
         tab = []
-        for ich in range(last + 1):
+        for ich in range(int(start / chunk_size), int((end - 1) / chunk_size) + 1):
             s, e = ich * chunk_size, (ich + 1) * chunk_size
-            tab.append((s - padding, e + padding, s, min(e, n_frames)))
+            tab.append((s - padding, e + padding, max(s, start), min(e, end)))
         return tab
-    return [(-padding, n_frames + padding, 0, n_frames)]
+    return [(-padding, end + padding, 0, end)]
+
+
+def traces_span(n_frames: int, chunk_size: Optional[int], start_frame: Optional[int] = None,
+                end_frame: Optional[int] = None) -> Tuple[int, int]:
+    """The sample span get_traces returns (base.py:175 vs :222)."""
+    start = 0 if start_frame is None else start_frame
+    end = n_frames if end_frame is None else end_frame
+    if chunk_size is not None and end - start > chunk_size:
+        return start, end
+    return 0, end
 
 
 def read_chunk(y2d: np.ndarray, i1: int, i2: int) -> np.ndarray:
@@ -344,10 +358,12 @@ def cast_like_reference(out64: np.ndarray, dtype) -> np.ndarray:
 
 def reduce_noise(y, sr, y_noise=None, cfg: Optional[GateConfig] = None, return_float64=False,
                  unit_taps: Optional[Dict[Tuple[int, int], Taps]] = None, thresh_override=None,
-                 info: Optional[dict] = None):
+                 info: Optional[dict] = None, start_frame: Optional[int] = None, end_frame: Optional[int] = None):
     """noisereduce/noisereduce.py:13-185 with use_torch=False, as a loop over chunk_table x channels.
 
     unit_taps: optional dict keyed (chunk_index, channel) -> Taps to be filled.
+    start_frame / end_frame: SpectralGate.get_traces(start_frame, end_frame) (base.py:167-226) instead of
+    the whole recording.
     """
     cfg = cfg or GateConfig(sr=sr)
     y2d, flat = _as_2d(y)
@@ -376,7 +392,7 @@ def reduce_noise(y, sr, y_noise=None, cfg: Optional[GateConfig] = None, return_f
         info.update(n_grad_freq=nf, n_grad_time=nt, smooth=smooth, filt=filt)
 
     out = np.zeros((C, n))
-    for ich, (i1, i2, lo, hi) in enumerate(chunk_table(n, cfg.chunk_size, cfg.padding)):
+    for ich, (i1, i2, lo, hi) in enumerate(chunk_table(n, cfg.chunk_size, cfg.padding, start_frame, end_frame)):
         chunk = read_chunk(y2d, i1, i2)
         for c in range(C):
             taps = None
@@ -387,6 +403,8 @@ def reduce_noise(y, sr, y_noise=None, cfg: Optional[GateConfig] = None, return_f
             else:
                 yc = gate_nonstationary_unit(chunk[c], cfg, filt, taps)
             out[c, lo:hi] = yc[lo - i1: hi - i1]                   # base.py:150, :164
+    s0, s1 = traces_span(n, cfg.chunk_size, start_frame, end_frame)
+    out = out[:, s0:s1]
     if return_float64:
         return out[0] if flat else out
     res = cast_like_reference(out, dtype)

@@ -46,6 +46,16 @@ def stationary_thresh(y, sr, **kw):
     return SpectralGateStationary(y=y, sr=sr, **args).noise_thresh
 
 
+def traces(y, sr, start, end, **kw):
+    """SpectralGateStationary.get_traces(start_frame, end_frame) (base.py:167-226)."""
+    args = dict(y_noise=None, n_std_thresh_stationary=1.5, chunk_size=600000,
+                clip_noise_stationary=True, padding=30000, n_fft=1024, win_length=None,
+                hop_length=None, time_constant_s=2.0, freq_mask_smooth_hz=500,
+                time_mask_smooth_ms=50, tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1)
+    args.update(kw)
+    return SpectralGateStationary(y=y, sr=sr, **args).get_traces(start, end)
+
+
 def main():
     # ---- config 1: assets/fish.wav (int16 mono 44.1 kHz), defaults -------------------------
     rate, fish = wavfile.read(os.path.join(REF, "assets", "fish.wav"))
@@ -79,6 +89,16 @@ def main():
         out_stat_single_chunk=nr.reduce_noise(y=y[0], sr=sr, stationary=True),
         out_stat_nosmooth=nr.reduce_noise(y=y, sr=sr, stationary=True, freq_mask_smooth_hz=None,
                                           time_mask_smooth_ms=None, **kw),
+    )
+
+    # ---- get_traces sub-ranges: chunk-grid branch and the single-padded-chunk branch ----------
+    np.savez_compressed(
+        os.path.join(HERE, "synth_traces.npz"),
+        versions=VERSIONS, sr=sr,
+        chunks_13000_28000=traces(y, sr, 13000, 28000, **kw),          # chunks 1..2 of 3, trimmed
+        chunks_500_24500=traces(y, sr, 500, 24500, **kw),              # chunks 0..2, end on a chunk edge + 500
+        single_to_9000=traces(y, sr, 4000, 9000, **kw),                # base.py:222: [0, 9000), right pad = real samples
+        single_to_29000_nochunk=traces(y, sr, None, 29000, chunk_size=None, padding=1500),
     )
 
     # ---- TorchGate surface (reference on CPU) ------------------------------------------------

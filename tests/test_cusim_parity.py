@@ -240,3 +240,60 @@ def test_python_surface_on_simulator(lib, monkeypatch):
         nr.reduce_noise(y=y, sr=SR, stationary=True, use_torch=True, n_jobs=2)
     with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
         nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=512)
+
+
+def test_get_traces_subranges_on_simulator(lib, monkeypatch):
+    """SpectralGate.get_traces(start_frame, end_frame) runs only the reference's units (base.py:167-226):
+    a chunk sub-range of the grid (host rows -> slab pipeline; int16 -> staged window), and the single
+    padded chunk [0, end) whose right padding is real signal."""
+    monkeypatch.setattr(_cabi, "_LIB", lib)
+    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
+    from noisereduce_b200.spectralgate.nonstationary import SpectralGateNonStationary
+    y = synth_small(C=2, n=11000)
+    kw = dict(chunk_size=3000, padding=400)
+    args = dict(y_noise=None, n_std_thresh_stationary=1.5, clip_noise_stationary=True, n_fft=1024, win_length=None,
+                hop_length=None, time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50,
+                tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1, **kw)
+    cfg = O.GateConfig(sr=SR, stationary=True, **kw)
+    sg = SpectralGateStationary(y=y, sr=SR, **args)
+    for a, b in ((3500, 8200), (0, 11000), (6000, 9001)):
+        out = sg.get_traces(a, b)
+        ref = O.reduce_noise(y, SR, cfg=cfg, start_frame=a, end_frame=b)
+        assert out.shape == ref.shape == (2, b - a)
+        assert P.relinf(out, ref) < P.OUT_TOL
+        assert sg._gate.stats()["units"] == 2 * (int((b - 1) / 3000) - int(a / 3000) + 1)
+    out = sg.get_traces(1000, 3500)                                    # base.py:222: [0, 3500), one unit per channel
+    ref = O.reduce_noise(y, SR, cfg=cfg, start_frame=1000, end_frame=3500)
+    assert out.shape == ref.shape == (2, 3500) and P.relinf(out, ref) < P.OUT_TOL
+    assert sg._gate.stats()["units"] == 2
+    full = sg.get_traces()                                             # the range does not stick
+    assert P.relinf(full, O.reduce_noise(y, SR, cfg=cfg)) < P.OUT_TOL
+    with pytest.raises(ValueError):
+        sg.get_traces(0, 12000)
+    # int16 rows, non-stationary gate: staged-window path
+    yi = np.round(y * 20000).astype(np.int16)
+    a2 = dict(args)
+    for k in ("y_noise", "n_std_thresh_stationary", "clip_noise_stationary"):
+        a2.pop(k)
+    a2.update(time_constant_s=0.3, thresh_n_mult_nonstationary=2, sigmoid_slope_nonstationary=10)
+    sn = SpectralGateNonStationary(y=yi, sr=SR, **a2)
+    cfgn = O.GateConfig(sr=SR, stationary=False, time_constant_s=0.3, **kw)
+    out = sn.get_traces(3100, 9500)
+    ref = O.reduce_noise(yi, SR, cfg=cfgn, start_frame=3100, end_frame=9500)
+    assert out.dtype == np.int16 and np.max(np.abs(out.astype(np.int64) - ref.astype(np.int64))) <= 1
+    out = sn.get_traces(None, 2000)
+    ref = O.reduce_noise(yi, SR, cfg=cfgn, end_frame=2000)
+    assert out.shape == (2, 2000) and np.max(np.abs(out.astype(np.int64) - ref.astype(np.int64))) <= 1
+    # "device" rows (the simulator's device memory is host memory): nothing outside the range is written
+    gate = sg._gate
+    yc = np.ascontiguousarray(y)
+    o = np.full_like(yc, 7.0)
+    gate.set_range(1, 1, 2)
+    gate.run_device(yc.ctypes.data, o.ctypes.data, np.float32, 2, 11000, 11000, 11000)
+    gate.set_range(0)
+    assert np.all(o[:, :3000] == 7.0) and np.all(o[:, 9000:] == 7.0)
+    assert P.relinf(o[:, 3000:9000], O.reduce_noise(y, SR, cfg=cfg)[:, 3000:9000]) < P.OUT_TOL
+    with pytest.raises(_cabi.GateError, match="chunk range"):
+        gate.set_range(1, 2, 4)
+        gate.run_device(yc.ctypes.data, o.ctypes.data, np.float32, 2, 11000, 11000, 11000)
+    gate.set_range(0)

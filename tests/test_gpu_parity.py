@@ -140,6 +140,42 @@ def test_golden_fish_and_small(lib, golden_dir):
                                     time_mask_smooth_ms=None, **kw), s["out_stat_nosmooth"]) < P.OUT_TOL
 
 
+def test_get_traces_subranges_golden(lib, golden_dir):
+    """SpectralGate.get_traces(start_frame, end_frame) against reference outputs (base.py:167-226): only
+    the selected units run, and the result equals the reference's chunk-grid / single-chunk branches."""
+    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
+    g = np.load(os.path.join(golden_dir, "synth_traces.npz"))
+    y = synth_small()
+    args = dict(y_noise=None, n_std_thresh_stationary=1.5, clip_noise_stationary=True, n_fft=1024, win_length=None,
+                hop_length=None, time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50,
+                tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1)
+    sg = SpectralGateStationary(y=y, sr=16000, chunk_size=12000, padding=1500, **args)
+    for key, (a, b, units) in {"chunks_13000_28000": (13000, 28000, 4), "chunks_500_24500": (500, 24500, 6),
+                               "single_to_9000": (4000, 9000, 2)}.items():
+        out = sg.get_traces(a, b)
+        assert out.shape == g[key].shape and P.relinf(out, g[key]) < P.OUT_TOL, key
+        assert sg._gate.stats()["units"] == units, key
+    sg = SpectralGateStationary(y=y, sr=16000, chunk_size=None, padding=1500, **args)
+    out = sg.get_traces(None, 29000)
+    assert P.relinf(out, g["single_to_29000_nochunk"]) < P.OUT_TOL
+    # device-resident rows through the same range selection
+    import torch
+    gate = _cabi.Gate(lib, stationary=1, surface=_cabi.SURFACE_NUMPY, n_fft=1024, win_length=1024, hop_length=256,
+                      n_grad_freq=16, n_grad_time=3, chunk_size=12000, padding=1500, sr=16000.0, prop_decrease=1.0,
+                      top_db=80.0, std_ddof=0)
+    gate.noise_stats_host(y)
+    x = torch.from_numpy(y).cuda()
+    o = torch.full_like(x, 7.0)
+    gate.set_range(1, 1, 1)
+    gate.run_device(x.data_ptr(), o.data_ptr(), np.float32, 2, 30000, 30000, 30000)
+    torch.cuda.synchronize()
+    gate.set_range(0)
+    o = o.cpu().numpy()
+    assert np.all(o[:, :12000] == 7.0) and np.all(o[:, 24000:] == 7.0)          # untouched outside chunk 1
+    ref = O.reduce_noise(y, 16000, cfg=O.GateConfig(sr=16000, stationary=True, chunk_size=12000, padding=1500))
+    assert P.relinf(o[:, 12000:24000], ref[:, 12000:24000]) < P.OUT_TOL
+
+
 def test_device_pointer_path_and_properties(lib):
     """Device-resident tensors through the same C call; linearity-in-scale and chunk independence."""
     import torch

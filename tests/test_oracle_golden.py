@@ -199,3 +199,20 @@ def test_ref_port_matches_reference(small, fish):
     assert np.array_equal(out, small["out_nonstat_chunked"])
     out = ref_port.reduce_noise(fish["y"], int(fish["sr"]), O.GateConfig(sr=int(fish["sr"]), stationary=True))
     assert np.array_equal(out, fish["out_stationary"])
+
+
+def test_get_traces_subranges_match_reference(golden_dir):
+    """SpectralGate.get_traces(start_frame, end_frame) (base.py:167-226): chunk-grid branch, and the
+    single padded chunk whose right padding is real signal (base.py:222)."""
+    g = np.load(os.path.join(golden_dir, "synth_traces.npz"))
+    y = synth_small()
+    cfg = O.GateConfig(sr=16000, stationary=True, chunk_size=12000, padding=1500)
+    for key, (a, b) in {"chunks_13000_28000": (13000, 28000), "chunks_500_24500": (500, 24500),
+                        "single_to_9000": (4000, 9000)}.items():
+        out = O.reduce_noise(y, 16000, cfg=cfg, start_frame=a, end_frame=b)
+        assert out.shape == g[key].shape, key
+        assert np.max(np.abs(out.astype(np.float64) - g[key])) < 1e-6 * np.max(np.abs(g[key])), key
+    cfg = O.GateConfig(sr=16000, stationary=True, chunk_size=None, padding=1500)
+    out = O.reduce_noise(y, 16000, cfg=cfg, end_frame=29000)
+    assert out.shape == g["single_to_29000_nochunk"].shape == (2, 29000)
+    assert np.max(np.abs(out.astype(np.float64) - g["single_to_29000_nochunk"])) < 1e-6
