@@ -745,8 +745,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     ub = std::min(ub, U);
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
     if (pipelined) {
-        // ~512 MB of input per slab, whole chunks, within the workspace limit
-        slab_chunks = std::max(1LL, std::min<long long>(chunk_count, (512LL << 20) / std::max<long long>(1, C * g.step * (long long)es)));
+        // ~256 MB of input per slab (measured on B200 + PCIe Gen5: 160-320 MB best, profiles/r01_e2e_slab_sweep.md), whole chunks, within the workspace limit
+        long long slab_bytes = 256LL << 20;
+        if (const char* e = getenv("B200GATE_SLAB_MB")) slab_bytes = std::max(1LL, atoll(e)) << 20;     // tuning knob
+        slab_chunks = std::max(1LL, std::min<long long>(chunk_count, slab_bytes / std::max<long long>(1, C * g.step * (long long)es)));
         slab_chunks = std::max(1LL, std::min(slab_chunks, ub / C));
         if (ub < C) return fail(h, B200GATE_ERR_NOMEM, "workspace limit too small for one chunk of all channels");
         ub = slab_chunks * C;
@@ -837,12 +839,13 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         CK(h, cudaEventCreate(&e));
         h->stage_ev.push_back(e);
     }
-    while (pipelined && h->pipe_ev.size() < 3 * n_batches) {
+    while (pipelined && h->pipe_ev.size() < 4 * n_batches) {
         cudaEvent_t e;
-        CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(h, cudaEventCreate(&e));
         h->pipe_ev.push_back(e);
     }
     size_t bi = 0;
+    int nu_prev = 0;
     cudaEventRecord(evk0, st);
     for (long long u0 = 0; u0 < U; u0 += ub, ++bi) {
         const int nu = (int)std::min(ub, U - u0);
@@ -856,12 +859,25 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const long long w0 = std::max(0LL, c0 * g.step - g.pad), w1 = std::min<long long>(N, c1 * g.step + g.pad);
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
-            if (bi >= 2) CK(h, cudaStreamWaitEvent(h->s_h2d, h->pipe_ev[3 * (bi - 2) + 1], 0));   // slab buffer free
-            CK(h, cudaMemcpy2DAsync(h->d_slab_in[ib], (size_t)slab_w * es, (const char*)in + (size_t)w0 * es,
-                                    (size_t)in_stride * es, (size_t)(w1 - w0) * es, (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
-            CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 0], h->s_h2d));
-            CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * bi + 0], 0));
-            if (bi >= 2) CK(h, cudaStreamWaitEvent(st, h->pipe_ev[3 * (bi - 2) + 2], 0));         // output buffer drained
+            // The head of this slab's window -- [w0, pw1), the 2*padding samples around the slab seam -- is already
+            // on the device at the tail of the previous slab's buffer: copy it device-to-device and bring only
+            // [pw1, w1) over PCIe, so every sample crosses the bus once.
+            const long long pw1 = bi == 0 ? w0 : std::min<long long>(N, c0 * g.step + g.pad);
+            if (bi >= 1) CK(h, cudaStreamWaitEvent(h->s_h2d, h->pipe_ev[4 * (bi - 1) + 3], 0));   // slab buffer free
+            if (w1 > pw1)
+                CK(h, cudaMemcpy2DAsync((char*)h->d_slab_in[ib] + (size_t)(pw1 - w0) * es, (size_t)slab_w * es,
+                                        (const char*)in + (size_t)pw1 * es, (size_t)in_stride * es, (size_t)(w1 - pw1) * es,
+                                        (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 0], h->s_h2d));
+            if (bi >= 1 && pw1 > w0) {
+                const long long pw0 = std::max(0LL, (c0 - nu_prev / C) * g.step - g.pad);           // previous window start
+                CK(h, cudaMemcpy2DAsync(h->d_slab_in[ib], (size_t)slab_w * es,
+                                        (const char*)h->d_slab_in[ib ^ 1] + (size_t)(w0 - pw0) * es, (size_t)slab_w * es,
+                                        (size_t)(pw1 - w0) * es, (size_t)C, cudaMemcpyDeviceToDevice, st));
+            }
+            CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 3], st));     // previous buffer's tail consumed (and its kernels done)
+            CK(h, cudaStreamWaitEvent(st, h->pipe_ev[4 * bi + 0], 0));
+            if (bi >= 2) CK(h, cudaStreamWaitEvent(st, h->pipe_ev[4 * (bi - 2) + 2], 0));         // output buffer drained
             // virtual row bases so the kernels keep absolute sample indices
             xb = (const char*)h->d_slab_in[ib] - (size_t)w0 * es;
             yb = (char*)h->d_slab_out[ib] - (size_t)o0 * es;
@@ -1126,17 +1142,27 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const long long o0 = c0 * g.step, o1 = std::min<long long>(N, c1 * g.step);
             const int ib = (int)(bi & 1);
             const void* d2h_src = h->d_slab_out[ib];
-            CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 1], st));
-            CK(h, cudaStreamWaitEvent(h->s_d2h, h->pipe_ev[3 * bi + 1], 0));
+            CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 1], st));
+            CK(h, cudaStreamWaitEvent(h->s_d2h, h->pipe_ev[4 * bi + 1], 0));
             CK(h, cudaMemcpy2DAsync((char*)out + (size_t)o0 * es, (size_t)out_stride * es, d2h_src, (size_t)slab_ow * es,
                                     (size_t)(o1 - o0) * es, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
-            CK(h, cudaEventRecord(h->pipe_ev[3 * bi + 2], h->s_d2h));
+            CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 2], h->s_d2h));
+            nu_prev = nu;
         }
     }
     cudaEventRecord(evk1, st);
     if (pipelined) {
         CK(h, cudaStreamSynchronize(h->s_d2h));
         CK(h, cudaStreamSynchronize(h->s_h2d));
+        if (getenv("B200GATE_TRACE")) {                       // slab timeline (ms since the first launch) on stderr
+            CK(h, cudaStreamSynchronize(st));
+            for (size_t b = 0; b < n_batches; ++b) {
+                float t[4] = {0, 0, 0, 0};
+                for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], evk0, h->pipe_ev[4 * b + i]);
+                fprintf(stderr, "slab %3zu  h2d_done %8.3f  seam_done %8.3f  kernels_done %8.3f  d2h_done %8.3f\n", b, t[0],
+                        t[3], t[1], t[2]);
+            }
+        }
     }
 
     // ---- results back -------------------------------------------------------------------------------

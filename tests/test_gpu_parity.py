@@ -160,10 +160,7 @@ def test_get_traces_subranges_golden(lib, golden_dir):
     assert P.relinf(out, g["single_to_29000_nochunk"]) < P.OUT_TOL
     # device-resident rows through the same range selection
     import torch
-    gate = _cabi.Gate(lib, stationary=1, surface=_cabi.SURFACE_NUMPY, n_fft=1024, win_length=1024, hop_length=256,
-                      n_grad_freq=16, n_grad_time=3, chunk_size=12000, padding=1500, sr=16000.0, prop_decrease=1.0,
-                      top_db=80.0, std_ddof=0)
-    gate.noise_stats_host(y)
+    gate = SpectralGateStationary(y=y, sr=16000, chunk_size=12000, padding=1500, **args)._gate
     x = torch.from_numpy(y).cuda()
     o = torch.full_like(x, 7.0)
     gate.set_range(1, 1, 1)
