@@ -50,9 +50,11 @@ typedef struct b200gate_params {
     int32_t abi_version;        /* B200GATE_ABI_VERSION                                          */
     int32_t surface;            /* B200GATE_SURFACE_*                                            */
     int32_t stationary;         /* 1: stationary gate, 0: non-stationary gate                    */
-    int32_t n_fft;
-    int32_t win_length;
-    int32_t hop_length;
+    int32_t n_fft;              /* numpy surface: any power of two in [16, 8192]; torch surface: 1024            */
+    int32_t win_length;         /* 1 <= win_length <= n_fft                                      */
+    int32_t hop_length;         /* 1 <= hop_length <= win_length.  n_fft=1024/win=1024/hop=256 (both gates) and
+                                 * 2048/2048/512 (non-stationary) run the tuned FP32 kernels; every other
+                                 * geometry runs the float64 general family (gate_generic.cuh)    */
     int32_t n_grad_freq;        /* smoothing half-widths; 0,0 = mask smoothing disabled          */
     int32_t n_grad_time;
     int32_t std_ddof;           /* 0 numpy surface (np.std), 1 torch surface (std_mean)          */
@@ -63,7 +65,8 @@ typedef struct b200gate_params {
     int32_t reserve_sms;        /* SMs the persistent grids leave free (for a concurrent NCCL collective) */
     int32_t path_flags;         /* bit 0: use the experimental single-pass kernel (gate_fused.cuh; slower,
                                  * kept for A/B); bit 1: do not cache spectra between analysis and synthesis
-                                 * (re-transform instead; saves 8 KB of workspace per frame pair)          */
+                                 * (re-transform instead; saves 8 KB of workspace per frame pair); bit 2: run the
+                                 * float64 general-geometry family even for a tuned geometry (cross-check)  */
     int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
     int64_t padding;
     double sr;

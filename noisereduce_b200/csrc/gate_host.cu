@@ -6,6 +6,7 @@
 #include "../../include/b200gate.h"
 #include "gate_kernels_2k.cuh"
 #include "gate_fused.cuh"
+#include "gate_generic.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -53,6 +54,11 @@ struct b200gate_handle {
     char* d_fscratch = nullptr;                    // fused kernel: per-warp spectra + decision rows
     size_t fscratch_bytes = 0;
     std::vector<double> thr, mean, sd;
+    // general-geometry family (gate_generic.cuh)
+    bool generic = false;
+    int g_logN = 0;
+    double *d_gwa = nullptr, *d_gws = nullptr, *d_gw2 = nullptr, *d_gthr = nullptr;
+    double2* d_gcs = nullptr;
     // workspace
     char* d_ws_buf = nullptr;
     size_t ws_bytes = 0;
@@ -253,8 +259,11 @@ int grid_1d(long long n, int block, int cap) {
     return (int)std::max(1LL, std::min<long long>(g, cap));
 }
 
+int generic_noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, cudaStream_t st);
+
 // collapsed noise clip (float64, device) -> thresholds
 int noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, cudaStream_t st) {
+    if (h->generic) return generic_noise_stats_from_mean(h, d_yn, n, st);
     const int H = h->p.hop_length;
     const int Tn = (int)(n / H) + 1;                     // scipy: (n + 2*(W/2) - W)/H + 1
     double *d_db = nullptr, *d_res = nullptr;
@@ -263,7 +272,7 @@ int noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, c
     K0Args a{};
     a.yn = d_yn; a.n = n; a.H = H; a.Tn = Tn; a.wa64 = h->d_wa64; a.cs64 = h->d_cs64; a.eps = kEps64; a.db = d_db;
     B200_LAUNCH(k0_stft_db, dim3(Tn), dim3(256), kN * sizeof(double2), st, a);
-    B200_LAUNCH(k0_stats, dim3(kF), dim3(256), 0, st, d_db, Tn, h->p.top_db, h->p.std_ddof, h->p.n_std_thresh,
+    B200_LAUNCH(k0_stats, dim3(kF), dim3(256), 0, st, d_db, Tn, kF, h->p.top_db, h->p.std_ddof, h->p.n_std_thresh,
                 d_res, d_res + kF, d_res + 2 * kF);
     CK(h, cudaGetLastError());
     std::vector<double> res(3 * kF);
@@ -275,6 +284,80 @@ int noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, c
     h->sd.assign(res.begin() + kF, res.begin() + 2 * kF);
     h->thr.assign(res.begin() + 2 * kF, res.end());
     return build_threshold_tables(h);
+}
+
+// ---- general-geometry family: tables, noise statistics ----------------------------------------------------------
+int build_generic_tables(b200gate_handle* h) {
+    const int N = h->p.n_fft, W = h->p.win_length;
+    std::vector<double> w(W), wa(W), ws(W), w2(W);
+    double sw = 0.0;
+    for (int n = 0; n < W; ++n) {
+        w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)W);          // scipy get_window('hann', W): periodic
+        sw += w[n];
+    }
+    h->sum_w = sw;
+    for (int n = 0; n < W; ++n) {
+        wa[n] = w[n] / sw;                                                   // scaling='spectrum'
+        ws[n] = w[n] * sw / (double)N;                                       // irfft's 1/N, istft's * sum(w), window
+        w2[n] = w[n] * w[n];
+    }
+    std::vector<double2> cs(N);
+    for (int m = 0; m < N; ++m) {
+        const long double th = 2.0L * M_PIl * (long double)m / (long double)N;
+        cs[m] = make_double2((double)cosl(th), (double)sinl(th));
+    }
+    int rc;
+    if ((rc = upload(h, &h->d_gwa, wa))) return rc;
+    if ((rc = upload(h, &h->d_gws, ws))) return rc;
+    if ((rc = upload(h, &h->d_gw2, w2))) return rc;
+    if ((rc = upload(h, &h->d_gcs, cs))) return rc;
+    return B200GATE_OK;
+}
+
+GTables generic_tables(const b200gate_handle* h) {
+    GTables t{};
+    t.wa = h->d_gwa; t.ws = h->d_gws; t.w2 = h->d_gw2; t.cs = h->d_gcs;
+    return t;
+}
+
+GGeom generic_geom(const b200gate_handle* h, const Geom& g) {
+    GGeom gg{};
+    gg.g = g; gg.N = h->p.n_fft; gg.logN = h->g_logN; gg.W = h->p.win_length; gg.F = h->F;
+    return gg;
+}
+
+int generic_threads(int N) { return N >= 512 ? 256 : std::max(32, N / 2); }
+
+int generic_noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, cudaStream_t st) {
+    const int H = h->p.hop_length, W = h->p.win_length, N = h->p.n_fft, F = h->F;
+    const long long Tn = (n + 2 * (W / 2) - W) / H + 1;
+    if (Tn < 1 || Tn > 0x7fffffffLL) return fail(h, B200GATE_ERR_ARG, "noise clip length %lld unusable", n);
+    double2* d_X = nullptr;
+    double *d_db = nullptr, *d_res = nullptr;
+    CK(h, cudaMalloc((void**)&d_X, (size_t)Tn * F * sizeof(double2)));
+    CK(h, cudaMalloc((void**)&d_db, (size_t)Tn * F * sizeof(double)));
+    CK(h, cudaMalloc((void**)&d_res, 3 * (size_t)F * sizeof(double)));
+    Geom g{};
+    g.H = H; g.C = 1; g.T = (int)Tn; g.n_chunks = 1; g.n_total = n; g.step = n; g.pad = 0; g.Lp = n;
+    g.in_stride = n; g.out_stride = n; g.u0 = 0; g.n_units = 1;
+    GStftArgs<double> a{};
+    a.gg = generic_geom(h, g); a.tb = generic_tables(h); a.x = d_yn; a.X = d_X;
+    { auto kern_ = gk_stft<double>; B200_LAUNCH(kern_, dim3((unsigned)Tn, 1), dim3(generic_threads(N)), (size_t)N * sizeof(double2), st, a); }
+    B200_LAUNCH(gk_noise_db, dim3(grid_1d(Tn * F, 256, 1 << 16)), dim3(256), 0, st, (const double2*)d_X, (long long)Tn * F, kEps64, d_db);
+    B200_LAUNCH(k0_stats, dim3(F), dim3(256), 0, st, d_db, (int)Tn, F, h->p.top_db, h->p.std_ddof, h->p.n_std_thresh,
+                d_res, d_res + F, d_res + 2 * F);
+    CK(h, cudaGetLastError());
+    std::vector<double> res(3 * (size_t)F);
+    CK(h, cudaMemcpyAsync(res.data(), d_res, res.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    cudaFree(d_X); cudaFree(d_db); cudaFree(d_res);
+    h->mean.assign(res.begin(), res.begin() + F);
+    h->sd.assign(res.begin() + F, res.begin() + 2 * F);
+    h->thr.assign(res.begin() + 2 * F, res.end());
+    int rc = upload(h, &h->d_gthr, h->thr);
+    if (rc) return rc;
+    h->have_thresh = true;
+    return B200GATE_OK;
 }
 
 template <typename Tin, typename Tacc>
@@ -346,12 +429,22 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     const bool geo1k = p->n_fft == kN && p->win_length == kN && p->hop_length == kN / 4;
     const bool geo2k = p->n_fft == kN2 && p->win_length == kN2 && p->hop_length == kN2 / 4 &&
                        p->surface == B200GATE_SURFACE_NUMPY && !p->stationary;
-    if (!geo1k && !geo2k)
-        return fail(nullptr, B200GATE_ERR_ARG,
-                    "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d (%s gate): this build runs "
-                    "n_fft=1024 (both gates, both surfaces) and n_fft=2048 (non-stationary gate), each with "
-                    "win_length=n_fft, hop_length=n_fft/4",
-                    p->n_fft, p->win_length, p->hop_length, p->stationary ? "stationary" : "non-stationary");
+    // everything else the reference accepts on the numpy surface runs on the general-geometry family
+    // (path_flags bit 2 forces it for the tuned geometries too: the float64 cross-check of the fast kernels)
+    const bool want_generic = (!geo1k && !geo2k) || ((p->path_flags & 4) && p->surface == B200GATE_SURFACE_NUMPY);
+    int logN = 0;
+    while ((1 << logN) < p->n_fft) ++logN;
+    if (want_generic) {
+        const bool pow2 = p->n_fft >= 16 && p->n_fft <= 8192 && (1 << logN) == p->n_fft;
+        if (p->surface != B200GATE_SURFACE_NUMPY || !pow2 || p->win_length < 1 || p->win_length > p->n_fft ||
+            p->hop_length < 1 || p->hop_length > p->win_length)
+            return fail(nullptr, B200GATE_ERR_ARG,
+                        "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d (%s gate, %s surface): the numpy "
+                        "surface runs any power-of-two n_fft in [16, 8192] with 1 <= hop_length <= win_length <= n_fft; "
+                        "the torch surface runs n_fft=1024, win_length=1024, hop_length=256",
+                        p->n_fft, p->win_length, p->hop_length, p->stationary ? "stationary" : "non-stationary",
+                        p->surface == B200GATE_SURFACE_NUMPY ? "numpy" : "torch");
+    }
     if (p->n_grad_freq < 0 || p->n_grad_time < 0 || p->n_grad_freq > 64 || p->n_grad_time > 64)
         return fail(nullptr, B200GATE_ERR_ARG, "smoothing extents out of range (%d, %d)", p->n_grad_freq, p->n_grad_time);
     if ((long long)(p->n_grad_freq + 1) * (p->n_grad_freq + 1) * (p->n_grad_time + 1) * (p->n_grad_time + 1) > 65535)
@@ -371,7 +464,10 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->num_sm = prop.multiProcessorCount;
     if (p->reserve_sms > 0 && p->reserve_sms < h->num_sm) h->num_sm -= p->reserve_sms;   // leave room for NCCL
-    int rc = build_static_tables(h);
+    h->generic = want_generic;
+    h->g_logN = logN;
+    h->F = want_generic ? p->n_fft / 2 + 1 : (p->n_fft == kN2 ? kF2 : kF);
+    int rc = want_generic ? build_generic_tables(h) : build_static_tables(h);
     if (rc == B200GATE_OK) {
         cudaMalloc((void**)&h->d_maxabs, sizeof(unsigned));
         e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
@@ -396,6 +492,9 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         for (int dt = 0; dt < 3; ++dt)
             B200_WITH_DTYPE(dt, { cudaFuncSetAttribute(k_fused<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kfused_smem_floats() * 4); });
         cudaFuncSetAttribute(k_smooth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        for (int dt = 0; dt < 3; ++dt)
+            B200_WITH_DTYPE(dt, { cudaFuncSetAttribute(gk_stft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16); });
+        cudaFuncSetAttribute(gk_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
 #endif
     }
     if (rc != B200GATE_OK) {
@@ -411,7 +510,7 @@ void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
                     h->d_wa64, h->d_cs64, h->d_tthr, h->d_maxabs, h->d_fscratch, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
-                    h->d_dbg_mask, h->d_dbg_bits};
+                    h->d_dbg_mask, h->d_dbg_bits, h->d_gwa, h->d_gws, h->d_gw2, h->d_gthr, h->d_gcs};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -431,23 +530,29 @@ const char* b200gate_last_error(const b200gate_handle* h) { return h ? h->err.c_
 
 int b200gate_set_noise_threshold(b200gate_handle* h, const double* thresh_db, int32_t n_bins) {
     if (!h || !thresh_db) return B200GATE_ERR_ARG;
-    if (n_bins != kF) return fail(h, B200GATE_ERR_ARG, "expected %d bins, got %d", kF, n_bins);
-    h->thr.assign(thresh_db, thresh_db + kF);
-    h->mean.assign(kF, NAN);
-    h->sd.assign(kF, NAN);
+    const int F = h->generic ? h->F : kF;
+    if (n_bins != F) return fail(h, B200GATE_ERR_ARG, "expected %d bins, got %d", F, n_bins);
+    h->thr.assign(thresh_db, thresh_db + F);
+    h->mean.assign(F, NAN);
+    h->sd.assign(F, NAN);
+    if (h->generic) {
+        int rc = upload(h, &h->d_gthr, h->thr);
+        if (rc == B200GATE_OK) h->have_thresh = true;
+        return rc;
+    }
     return build_threshold_tables(h);
 }
 
 int b200gate_get_noise_threshold(const b200gate_handle* h, double* thresh_db, int32_t n_bins) {
-    if (!h || !thresh_db || n_bins != kF || !h->have_thresh) return B200GATE_ERR_STATE;
-    memcpy(thresh_db, h->thr.data(), kF * sizeof(double));
+    if (!h || !thresh_db || n_bins != (h->generic ? h->F : kF) || !h->have_thresh) return B200GATE_ERR_STATE;
+    memcpy(thresh_db, h->thr.data(), (size_t)n_bins * sizeof(double));
     return B200GATE_OK;
 }
 
 int b200gate_get_noise_mean_std(const b200gate_handle* h, double* mean_db, double* std_db, int32_t n_bins) {
-    if (!h || n_bins != kF || !h->have_thresh) return B200GATE_ERR_STATE;
-    if (mean_db) memcpy(mean_db, h->mean.data(), kF * sizeof(double));
-    if (std_db) memcpy(std_db, h->sd.data(), kF * sizeof(double));
+    if (!h || n_bins != (h->generic ? h->F : kF) || !h->have_thresh) return B200GATE_ERR_STATE;
+    if (mean_db) memcpy(mean_db, h->mean.data(), (size_t)n_bins * sizeof(double));
+    if (std_db) memcpy(std_db, h->sd.data(), (size_t)n_bins * sizeof(double));
     return B200GATE_OK;
 }
 
@@ -523,28 +628,28 @@ int b200gate_debug_select_unit(b200gate_handle* h, int64_t chunk, int64_t channe
 int b200gate_debug_dims(const b200gate_handle* h, int64_t* T, int32_t* F, int32_t* words) {
     if (!h) return B200GATE_ERR_ARG;
     if (T) *T = h->dbg_T;
-    if (F) *F = h->p.n_fft == kN2 ? kF2 : kF;
-    if (words) *words = h->p.n_fft == kN2 ? kFW2 : kFW;
+    if (F) *F = h->generic ? h->F : (h->p.n_fft == kN2 ? kF2 : kF);
+    if (words) *words = h->generic ? (h->F + 31) / 32 : (h->p.n_fft == kN2 ? kFW2 : kFW);
     return B200GATE_OK;
 }
 
 int b200gate_debug_read_bits(b200gate_handle* h, uint32_t* bits) {
     if (!h || !bits || !h->d_dbg_bits || h->dbg_T <= 0) return B200GATE_ERR_STATE;
-    if (h->p.n_fft == kN2) { memset(bits, 0, (size_t)h->dbg_T * kFW2 * 4); return B200GATE_OK; }   // no binary mask in this family
+    if (!h->generic && h->p.n_fft == kN2) { memset(bits, 0, (size_t)h->dbg_T * kFW2 * 4); return B200GATE_OK; }   // no binary mask in this family
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(bits, h->d_dbg_bits, (size_t)h->dbg_T * kFW * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(bits, h->d_dbg_bits, (size_t)h->dbg_T * (h->generic ? (h->F + 31) / 32 : kFW) * 4, cudaMemcpyDeviceToHost));
     return B200GATE_OK;
 }
 int b200gate_debug_read_mask(b200gate_handle* h, float* mask) {
     if (!h || !mask || !h->d_dbg_mask || h->dbg_T <= 0) return B200GATE_ERR_STATE;
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(mask, h->d_dbg_mask, (size_t)h->dbg_T * (h->p.n_fft == kN2 ? kF2 : kF) * 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(mask, h->d_dbg_mask, (size_t)h->dbg_T * (h->generic ? h->F : (h->p.n_fft == kN2 ? kF2 : kF)) * 4, cudaMemcpyDeviceToHost));
     return B200GATE_OK;
 }
 int b200gate_debug_read_spec(b200gate_handle* h, float* spec) {
     if (!h || !spec || !h->d_dbg_spec || h->dbg_T <= 0) return B200GATE_ERR_STATE;
     CK(h, cudaDeviceSynchronize());
-    CK(h, cudaMemcpy(spec, h->d_dbg_spec, (size_t)h->dbg_T * (h->p.n_fft == kN2 ? kF2 : kF) * 8, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(spec, h->d_dbg_spec, (size_t)h->dbg_T * (h->generic ? h->F : (h->p.n_fft == kN2 ? kF2 : kF)) * 8, cudaMemcpyDeviceToHost));
     return B200GATE_OK;
 }
 
@@ -643,7 +748,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // The n_fft = 1024 numpy-surface kernels are templated on the sample dtype: they read the caller's
     // float32 / int16 / float64 rows directly and cast on store (base.py:140, :218-226).  The 2048 family and
     // the torch surface run on float32 rows (other dtypes are converted at the edge).
-    const bool native = !torch_sem && p.n_fft == kN;
+    const bool generic = h->generic;
+    const bool native = !torch_sem && (p.n_fft == kN || generic);
     const int kdt = native ? dtype : B200GATE_F32;            // dtype the kernels see
     const size_t kes = dtype_size(kdt);
     const void* x = nullptr;
@@ -700,7 +806,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     g.n_chunks = (int)n_chunks;
     g.pad = torch_sem ? 0 : p.padding;                 // TorchGate filters the whole row, no chunk padding
     g.Lp = g.step + 2 * g.pad;
-    g.T = (int)(g.Lp / g.H) + 1;
+    g.T = generic ? (int)((g.Lp + 2 * (p.win_length / 2) - p.win_length) / g.H) + 1 : (int)(g.Lp / g.H) + 1;
     g.in_stride = xs;
     g.out_stride = ys;
     const long long U = chunk_count * C;
@@ -708,10 +814,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     if (Ubase + U > 0x7fffffffLL || g.Lp / g.H > 0x3fffffffLL) return fail(h, B200GATE_ERR_ARG, "problem too large");
 
     const int NFFT = p.n_fft;
-    const bool two_k = NFFT == kN2;
-    const int FP = two_k ? kFPad2 : kFPad, FF = two_k ? kF2 : kF;
+    const bool two_k = NFFT == kN2 && !generic;
+    const int FP = two_k ? kFPad2 : kFPad, FF = generic ? h->F : (two_k ? kF2 : kF);
     // frames whose masks k2 needs (same for every full chunk)
-    const long long sig_len = (long long)(g.T - 1) * g.H;
+    const long long sig_len = (long long)(g.T - 1) * g.H + (generic ? (p.win_length & 1) : 0);
     long long jp_hi = std::min(g.pad + g.step, sig_len);
     int tf_lo = 0, tf_hi = 0;
     int h_lo = 0, h_hi = 0;
@@ -721,7 +827,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         tf_lo = std::max(0, h_lo - 3) & ~1;          // even: k2 walks k1's (2j, 2j+1) frame pairs when spectra are cached
         tf_hi = std::min(h_hi, g.T);
     }
-    const bool tail_zeros = !torch_sem && (g.pad + g.step > sig_len);     // stationary.py:126 leaves the tail zero
+    const bool tail_zeros = !torch_sem && !generic && (g.pad + g.step > sig_len);   // (gk_ola writes the zeros itself)     // stationary.py:126 leaves the tail zero
     if (tail_zeros) {
         for (long long c = 0; c < C; ++c)
             CK(h, cudaMemsetAsync((char*)y + ((size_t)c * ys + (size_t)o_lo) * kes, 0, (size_t)On * kes, st));
@@ -730,19 +836,23 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // ---- workspace / batching ---------------------------------------------------------------------
     const bool stat = p.stationary != 0;
     // single-pass fused kernel: stationary gate, n_fft 1024, filter extents the in-warp smoother handles
-    const bool use_fused = stat && native && !h->force_two_pass && (p.path_flags & 1) &&
+    const bool use_fused = stat && native && !generic && !h->force_two_pass && (p.path_flags & 1) &&
                            (2 * p.n_grad_freq + 1 <= 12) && (p.n_grad_time + 1 <= 14);
     const size_t per_unit_2pass = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
                                         : 2 * (size_t)g.T * FP * 4 + 64) +
                                   (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
     // spectrum cache: k1 / k1n keep the packed spectrum of every frame pair so k2 does not re-transform
     const int zpairs = (g.T + 1) / 2;
-    const bool use_zcache = !use_fused && !two_k && !(p.path_flags & 2);
+    const bool use_zcache = !use_fused && !two_k && !generic && !(p.path_flags & 2);
     const size_t zunit = use_zcache ? (size_t)zpairs * 1024 * sizeof(float2) : 0;
-    const size_t per_unit = use_fused ? 64 : per_unit_2pass + zunit;      // the fused kernel keeps no per-unit buffers
+    // general-geometry family: float64 spectrum, mask, scratch and synthesis frames of every unit
+    const size_t g_tf = (size_t)g.T * (size_t)h->F, g_tw = (size_t)g.T * (size_t)p.win_length;
+    const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + 4 * 256;
+    const size_t per_unit = generic ? per_unit_generic : (use_fused ? 64 : per_unit_2pass + zunit);   // the fused kernel keeps no per-unit buffers
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 24.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
+    if (generic) ub = std::min(ub, 65535LL);                 // gk_* put the unit on gridDim.y
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
     if (pipelined) {
         // ~256 MB of input per slab (measured on B200 + PCIe Gen5: 160-320 MB best, profiles/r01_e2e_slab_sweep.md), whole chunks, within the workspace limit
@@ -774,7 +884,11 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t off_trow = off_tdb + al((size_t)ub * g.T * kFPad * 4);
     const size_t off_tthr = off_trow + al((size_t)ub * kFPad * 4);
     const size_t end_tstat = off_tthr + al((size_t)ub * kFPad * 4);
-    const size_t end_base = use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
+    const size_t goff_M = al((size_t)ub * g_tf * 16);
+    const size_t goff_tmp = goff_M + al((size_t)ub * g_tf * 8);
+    const size_t goff_fr = goff_tmp + al((size_t)ub * g_tf * 8);
+    const size_t end_generic = goff_fr + al((size_t)ub * g_tw * 8);
+    const size_t end_base = generic ? end_generic : use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
     const size_t off_z = al(end_base);
     const size_t end_all = off_z + al((size_t)ub * zunit);
     {
@@ -800,9 +914,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (h->d_dbg_spec) cudaFree(h->d_dbg_spec);
             if (h->d_dbg_mask) cudaFree(h->d_dbg_mask);
             if (h->d_dbg_bits) cudaFree(h->d_dbg_bits);
-            CK(h, cudaMalloc((void**)&h->d_dbg_spec, (size_t)g.T * kF2 * 8));
-            CK(h, cudaMalloc((void**)&h->d_dbg_mask, (size_t)g.T * kF2 * 4));
-            CK(h, cudaMalloc((void**)&h->d_dbg_bits, (size_t)g.T * kFW * 4));
+            const size_t fmax_ = (size_t)std::max(kF2, h->F);
+            CK(h, cudaMalloc((void**)&h->d_dbg_spec, (size_t)g.T * fmax_ * 8));
+            CK(h, cudaMalloc((void**)&h->d_dbg_mask, (size_t)g.T * fmax_ * 4));
+            CK(h, cudaMalloc((void**)&h->d_dbg_bits, (size_t)g.T * std::max<size_t>(kFW, (fmax_ + 31) / 32) * 4));
             h->dbg_T_alloc = g.T;
         }
         CK(h, cudaMemsetAsync(h->d_dbg_spec, 0, (size_t)g.T * FF * 8, st));
@@ -890,7 +1005,67 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         dbg.spec = h->d_dbg_spec;
         dbg.mask = h->d_dbg_mask;
 
-        if (use_fused) {
+        if (generic) {
+            const GGeom gg = generic_geom(h, g);
+            const GTables gt = generic_tables(h);
+            const int F = h->F, W = p.win_length, FW = (F + 31) / 32;
+            double2* gX = (double2*)h->d_ws_buf;
+            double* gM = (double*)(h->d_ws_buf + goff_M);
+            double* gTmp = (double*)(h->d_ws_buf + goff_tmp);
+            double* gFr = (double*)(h->d_ws_buf + goff_fr);
+            const int thr_fft = generic_threads(NFFT);
+            const size_t smem_fft = (size_t)NFFT * sizeof(double2);
+            const bool smooth = nf > 0 || nt > 0;
+            if (dbg.ul >= 0) CK(h, cudaMemsetAsync(h->d_dbg_bits, 0, (size_t)g.T * FW * 4, st));
+            cudaEventRecord(h->stage_ev[4 * bi + 0], st);
+            B200_WITH_DTYPE(kdt, {
+                GStftArgs<T> sa{};
+                sa.gg = gg; sa.tb = gt; sa.x = (const T*)xb; sa.X = gX;
+                auto kern_ = gk_stft<T>;
+                B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)nu), dim3(thr_fft), smem_fft, st, sa); });
+            if (stat) {
+                GDecideArgs da{};
+                da.n_units = nu; da.T = g.T; da.F = F; da.eps = kEps64; da.top_db = p.top_db; da.p = p.prop_decrease;
+                da.thr = h->d_gthr; da.X = gX; da.M = gM; da.dbg_ul = dbg.ul; da.FW = FW; da.dbg_bits = h->d_dbg_bits;
+                B200_LAUNCH(gk_decide, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, da);
+            } else {
+                const double tfr = p.time_constant_s * p.sr / (double)p.hop_length;       // nonstationary.py:109-114
+                GFollowArgs fa{};
+                fa.n_units = nu; fa.T = g.T; fa.F = F; fa.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
+                fa.n_mult = p.thresh_n_mult; fa.slope = p.sigmoid_slope; fa.p = p.prop_decrease; fa.blend = smooth ? 0 : 1;
+                fa.X = gX; fa.M = gM; fa.tmp = gTmp;
+                B200_LAUNCH(gk_follow, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, fa);
+            }
+            cudaEventRecord(h->stage_ev[4 * bi + 1], st);
+            launches += 2;
+            if (smooth) {
+                GSmoothArgs ga{};
+                ga.n_units = nu; ga.T = g.T; ga.F = F; ga.nf = nf; ga.nt = nt; ga.inv_D = 1.0 / D; ga.p = p.prop_decrease;
+                ga.blend = stat ? 0 : 1;                                                 // stationary.py blends before smoothing
+                const int gr = grid_1d((long long)nu * g.T * F, 256, h->num_sm * 16);
+                ga.src = gM; ga.dst = gTmp;
+                B200_LAUNCH(gk_smooth_f, dim3(gr), dim3(256), 0, st, ga);
+                ga.src = gTmp; ga.dst = gM;
+                B200_LAUNCH(gk_smooth_t, dim3(gr), dim3(256), 0, st, ga);
+                launches += 2;
+            }
+            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+            {
+                GIstftArgs ia{};
+                ia.gg = gg; ia.tb = gt; ia.X = gX; ia.M = gM; ia.frames = gFr; ia.dbg_ul = dbg.ul;
+                ia.dbg_spec = (float2*)h->d_dbg_spec; ia.dbg_mask = h->d_dbg_mask;
+                B200_LAUNCH(gk_istft, dim3((unsigned)g.T, (unsigned)nu), dim3(thr_fft), smem_fft, st, ia);
+                const long long out_max = std::min<long long>(g.step, N);
+                B200_WITH_DTYPE(kdt, {
+                    GOlaArgs<T> oa{};
+                    oa.gg = gg; oa.tb = gt; oa.frames = gFr; oa.y = (T*)yb;
+                    auto kern_ = gk_ola<T>;
+                    B200_LAUNCH(kern_, dim3((unsigned)grid_1d(out_max, 256, 1 << 16), (unsigned)nu), dim3(256), 0, st, oa); });
+                (void)W;
+                launches += 2;
+            }
+            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
+        } else if (use_fused) {
             KFArgs fa{};
             fa.g = g; fa.tb = tb; fa.x = xb; fa.y = yb;
             const size_t workers = (size_t)resident * kWarps;
@@ -1126,7 +1301,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
             }
         }
-        if (dbg.ul >= 0 && stat && !use_fused) {
+        if (dbg.ul >= 0 && stat && !use_fused && !generic) {
             // tapped mask words with the row floor folded in, as the smoothing kernel consumes them
             std::vector<unsigned> fl(kFW);
             CK(h, cudaStreamSynchronize(st));

@@ -1244,13 +1244,13 @@ __global__ void __launch_bounds__(256) k0_stft_db(const K0Args a) {
 }
 
 // One CTA per bin: top_db floor, mean, std (ddof), thresh.
-__global__ void __launch_bounds__(256) k0_stats(const double* __restrict__ db, int Tn, double top_db, int ddof,
+__global__ void __launch_bounds__(256) k0_stats(const double* __restrict__ db, int Tn, int F, double top_db, int ddof,
                                                 double n_std, double* __restrict__ mean_out,
                                                 double* __restrict__ std_out, double* __restrict__ thr_out) {
     __shared__ double red[256];
     const int f = blockIdx.x;
     double m = -1.0e300;
-    for (int t = threadIdx.x; t < Tn; t += blockDim.x) m = fmax(m, db[(long long)t * kF + f]);
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) m = fmax(m, db[(long long)t * F + f]);
     red[threadIdx.x] = m;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -1260,7 +1260,7 @@ __global__ void __launch_bounds__(256) k0_stats(const double* __restrict__ db, i
     const double fl = red[0] - top_db;
     __syncthreads();
     double sum = 0.0;
-    for (int t = threadIdx.x; t < Tn; t += blockDim.x) sum += fmax(db[(long long)t * kF + f], fl);
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) sum += fmax(db[(long long)t * F + f], fl);
     red[threadIdx.x] = sum;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -1271,7 +1271,7 @@ __global__ void __launch_bounds__(256) k0_stats(const double* __restrict__ db, i
     __syncthreads();
     double ss = 0.0;
     for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
-        const double d = fmax(db[(long long)t * kF + f], fl) - mean;
+        const double d = fmax(db[(long long)t * F + f], fl) - mean;
         ss += d * d;
     }
     red[threadIdx.x] = ss;

@@ -101,6 +101,22 @@ def main():
         single_to_29000_nochunk=traces(y, sr, None, 29000, chunk_size=None, padding=1500),
     )
 
+    # ---- STFT geometries off the default (general-geometry kernel family) ------------------------
+    yi16 = np.round(y * 20000).astype(np.int16)
+    np.savez_compressed(
+        os.path.join(HERE, "synth_geometry.npz"),
+        versions=VERSIONS, sr=sr,
+        stat_512=nr.reduce_noise(y=y, sr=sr, stationary=True, n_fft=512, **kw),
+        thresh_512=stationary_thresh(y, sr, n_fft=512, **kw),
+        nonstat_512_400_100=nr.reduce_noise(y=y, sr=sr, stationary=False, n_fft=512, win_length=400, hop_length=100,
+                                            time_constant_s=0.5, **kw),
+        stat_256_255_50_i16=nr.reduce_noise(y=yi16, sr=sr, stationary=True, n_fft=256, win_length=255, hop_length=50,
+                                            prop_decrease=0.9, **kw),
+        stat_2048=nr.reduce_noise(y=y, sr=sr, stationary=True, n_fft=2048, **kw),
+        nonstat_1024_hop300_f64=nr.reduce_noise(y=y.astype(np.float64), sr=sr, stationary=False, n_fft=1024,
+                                                hop_length=300, time_constant_s=0.5, **kw),
+    )
+
     # ---- TorchGate surface (reference on CPU) ------------------------------------------------
     x = synth_torchgate()                   # float32 [3, 24000]
     xt32 = torch.from_numpy(x)

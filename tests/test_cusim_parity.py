@@ -214,8 +214,6 @@ def test_nonstationary_n_fft_2048(lib):
             res = P.check_nonstationary(lib, y, cfg, tap_unit=unit)
             assert res["spec_err"] < P.SPEC_TOL and res["mask_err"] < P.MASK_TOL_NONSTAT
             assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5
-    with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
-        P.check_stationary(lib, y, O.GateConfig(sr=SR, stationary=True, n_fft=2048))
 
 
 def test_python_surface_on_simulator(lib, monkeypatch):
@@ -239,7 +237,9 @@ def test_python_surface_on_simulator(lib, monkeypatch):
     with pytest.raises(ValueError, match="n_jobs must be 1"):
         nr.reduce_noise(y=y, sr=SR, stationary=True, use_torch=True, n_jobs=2)
     with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
-        nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=512)
+        nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=1000)             # not a power of two
+    with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
+        nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=512, win_length=600)
 
 
 def test_get_traces_subranges_on_simulator(lib, monkeypatch):
@@ -297,3 +297,62 @@ def test_get_traces_subranges_on_simulator(lib, monkeypatch):
         gate.set_range(1, 2, 4)
         gate.run_device(yc.ctypes.data, o.ctypes.data, np.float32, 2, 11000, 11000, 11000)
     gate.set_range(0)
+
+
+GEN_TOL = 2e-7      # float64 kernels; what is left is the float32 cast of the output / taps
+
+
+@pytest.mark.parametrize("geo", [
+    dict(n_fft=512),
+    dict(n_fft=512, win_length=400, hop_length=100),
+    dict(n_fft=256, win_length=255, hop_length=50),          # odd window: one more output sample per chunk
+    dict(n_fft=128, win_length=100, hop_length=33),          # hop does not divide the window
+    dict(n_fft=2048),                                        # stationary 2048 has no tuned kernel
+    dict(n_fft=1024, path_flags=4),                          # tuned geometry forced onto the general family
+], ids=lambda g: "-".join(f"{k}{v}" for k, v in g.items()))
+def test_general_geometry_family(lib, geo):
+    """Any power-of-two n_fft, win_length <= n_fft, hop_length <= win_length (gate_generic.cuh): every stage
+    against the oracle, both gates; decisions bit-exact."""
+    geo = dict(geo)
+    extra = {k: geo.pop(k) for k in list(geo) if k == "path_flags"}
+    y = synth_small(C=2, n=5000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=2000, padding=300, **geo)
+    r = P.check_stationary(lib, y, cfg, tap_unit=(1, 1), inject_thresh=False, **extra)
+    assert r["thresh_err_db"] < P.THRESH_TOL_DB
+    r = P.check_stationary(lib, y, cfg, tap_unit=(2, 0), **extra)
+    assert r["mask0_mismatch"] == 0 and r["mask0_on_frac"] > 0.02
+    assert r["spec_err"] < GEN_TOL and r["mask_err"] < GEN_TOL and r["out_relinf"] < GEN_TOL
+    if "n_fft" in geo and geo["n_fft"] == 2048 and not extra:
+        return                                               # non-stationary 2048 is the tuned family (tested above)
+    cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=2000, padding=300, time_constant_s=0.2, **geo)
+    r = P.check_nonstationary(lib, y, cfg, tap_unit=(1, 1), **extra)
+    assert r["spec_err"] < GEN_TOL and r["mask_err"] < GEN_TOL and r["out_relinf"] < GEN_TOL
+
+
+def test_general_geometry_dtypes_blend_and_ranges(lib, monkeypatch):
+    """int16 / float64 rows, prop_decrease < 1, no smoothing, single chunk, sub-ranges -- through reduce_noise()."""
+    monkeypatch.setattr(_cabi, "_LIB", lib)
+    import noisereduce_b200 as nr
+    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
+    y = synth_small(C=2, n=6000)
+    yi = np.round(y * 20000).astype(np.int16)
+    kw = dict(n_fft=256, win_length=200, hop_length=64, chunk_size=2500, padding=300)
+    out = nr.reduce_noise(y=yi, sr=SR, stationary=True, prop_decrease=0.7, **kw)
+    ref = O.reduce_noise(yi, SR, cfg=O.GateConfig(sr=SR, stationary=True, prop_decrease=0.7, **kw))
+    assert out.dtype == np.int16 and np.abs(out.astype(np.int64) - ref.astype(np.int64)).max() <= 1
+    y64 = y.astype(np.float64)
+    out = nr.reduce_noise(y=y64, sr=SR, stationary=False, prop_decrease=0.6, time_constant_s=0.3, freq_mask_smooth_hz=None,
+                          time_mask_smooth_ms=None, **kw)
+    ref = O.reduce_noise(y64, SR, cfg=O.GateConfig(sr=SR, stationary=False, prop_decrease=0.6, time_constant_s=0.3,
+                                                   freq_mask_smooth_hz=None, time_mask_smooth_ms=None, **kw))
+    assert out.dtype == np.float64 and P.relinf(out, ref) < 1e-12            # float64 end to end
+    out = nr.reduce_noise(y=y[0], sr=SR, stationary=True, n_fft=512)          # one padded chunk, 1-D input
+    ref = O.reduce_noise(y[0], SR, cfg=O.GateConfig(sr=SR, stationary=True, n_fft=512))
+    assert out.shape == (6000,) and P.relinf(out, ref) < GEN_TOL
+    args = dict(y_noise=None, n_std_thresh_stationary=1.5, clip_noise_stationary=True, n_fft=512, win_length=None,
+                hop_length=None, time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50,
+                tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1, chunk_size=2500, padding=300)
+    sg = SpectralGateStationary(y=y, sr=SR, **args)
+    cfg = O.GateConfig(sr=SR, stationary=True, n_fft=512, chunk_size=2500, padding=300)
+    assert P.relinf(sg.get_traces(2600, 5900), O.reduce_noise(y, SR, cfg=cfg, start_frame=2600, end_frame=5900)) < GEN_TOL
+    assert P.relinf(sg.get_traces(100, 2000), O.reduce_noise(y, SR, cfg=cfg, start_frame=100, end_frame=2000)) < GEN_TOL

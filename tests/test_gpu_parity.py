@@ -173,6 +173,50 @@ def test_get_traces_subranges_golden(lib, golden_dir):
     assert P.relinf(o[:, 12000:24000], ref[:, 12000:24000]) < P.OUT_TOL
 
 
+def test_general_geometry_family_golden_and_stages(lib, golden_dir):
+    """STFT geometries off the default run on the float64 general family (gate_generic.cuh): reference
+    outputs (tests/golden/synth_geometry.npz), stage taps against the oracle, and the tuned n_fft=1024
+    kernels cross-checked against the general family on the same input."""
+    import noisereduce_b200 as nr
+    from tests.test_oracle_golden import GEOMETRY_CASES, geometry_input
+    g = np.load(os.path.join(golden_dir, "synth_geometry.npz"))
+    for key, (kw, dt) in GEOMETRY_CASES.items():
+        y = geometry_input(dt)
+        out = nr.reduce_noise(y=y, sr=16000, chunk_size=12000, padding=1500, **kw)
+        assert out.dtype == g[key].dtype and out.shape == g[key].shape, key
+        if dt == np.int16:
+            assert np.abs(out.astype(np.int64) - g[key].astype(np.int64)).max() <= 1, key
+        else:
+            assert P.relinf(out, g[key]) < P.OUT_TOL_TIGHT, key
+    y = synth_small(C=3, n=40000)
+    for geo in (dict(n_fft=512, win_length=400, hop_length=100), dict(n_fft=4096, win_length=2048, hop_length=512),
+                dict(n_fft=64, win_length=63, hop_length=20)):
+        cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=15000, padding=2000, freq_mask_smooth_hz=None,
+                           time_mask_smooth_ms=None if geo["n_fft"] == 4096 else 50, **geo)
+        if geo["n_fft"] == 64:
+            cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=15000, padding=2000, freq_mask_smooth_hz=1000,
+                               time_mask_smooth_ms=20, **geo)
+        r = P.check_stationary(lib, y, cfg, tap_unit=(1, 2))
+        assert r["mask0_mismatch"] == 0 and r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
+        cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=15000, padding=2000, time_constant_s=0.3,
+                           freq_mask_smooth_hz=cfg.freq_mask_smooth_hz, time_mask_smooth_ms=cfg.time_mask_smooth_ms, **geo)
+        r = P.check_nonstationary(lib, y, cfg, tap_unit=(2, 0))
+        assert r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
+    # the tuned FP32 kernels against the float64 family, same library, same thresholds
+    y = synth_small(C=4, n=200000)
+    a = nr.reduce_noise(y=y, sr=SR, stationary=True, chunk_size=60000, padding=3000)
+    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
+    args = dict(y_noise=None, n_std_thresh_stationary=1.5, clip_noise_stationary=True, n_fft=1024, win_length=None,
+                hop_length=None, time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50,
+                tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1, chunk_size=60000, padding=3000)
+    sg = SpectralGateStationary(y=y, sr=SR, **args)
+    import noisereduce_b200._cabi as cabi
+    gen = cabi.Gate(lib, **{**sg._gate_params(), "stationary": 1, "n_std_thresh": 1.5, "clip_noise": 1, "path_flags": 4})
+    gen.set_noise_threshold(sg.noise_thresh)
+    b = gen.run_host(np.ascontiguousarray(y))
+    assert P.relinf(a, b) < P.OUT_TOL_TIGHT
+
+
 def test_device_pointer_path_and_properties(lib):
     """Device-resident tensors through the same C call; linearity-in-scale and chunk independence."""
     import torch

@@ -216,3 +216,37 @@ def test_get_traces_subranges_match_reference(golden_dir):
     out = O.reduce_noise(y, 16000, cfg=cfg, end_frame=29000)
     assert out.shape == g["single_to_29000_nochunk"].shape == (2, 29000)
     assert np.max(np.abs(out.astype(np.float64) - g["single_to_29000_nochunk"])) < 1e-6
+
+
+GEOMETRY_CASES = {
+    "stat_512": (dict(stationary=True, n_fft=512), np.float32),
+    "nonstat_512_400_100": (dict(stationary=False, n_fft=512, win_length=400, hop_length=100, time_constant_s=0.5), np.float32),
+    "stat_256_255_50_i16": (dict(stationary=True, n_fft=256, win_length=255, hop_length=50, prop_decrease=0.9), np.int16),
+    "stat_2048": (dict(stationary=True, n_fft=2048), np.float32),
+    "nonstat_1024_hop300_f64": (dict(stationary=False, n_fft=1024, hop_length=300, time_constant_s=0.5), np.float64),
+}
+
+
+def geometry_input(dtype):
+    y = synth_small()
+    if dtype == np.int16:
+        return np.round(y * 20000).astype(np.int16)
+    return y.astype(dtype)
+
+
+def test_non_default_stft_geometries_match_reference(golden_dir):
+    """n_fft / win_length / hop_length off the defaults (base.py:79-86): odd window, hop not dividing the
+    window, zero-padded FFT -- the oracle restates scipy's framing for all of them."""
+    g = np.load(os.path.join(golden_dir, "synth_geometry.npz"))
+    for key, (kw, dt) in GEOMETRY_CASES.items():
+        y = geometry_input(dt)
+        cfg = O.GateConfig(sr=16000, chunk_size=12000, padding=1500, **kw)
+        out = O.reduce_noise(y, 16000, cfg=cfg)
+        assert out.dtype == g[key].dtype and out.shape == g[key].shape, key
+        if dt == np.int16:
+            assert np.abs(out.astype(np.int64) - g[key].astype(np.int64)).max() <= 1, key
+        else:
+            assert np.max(np.abs(out.astype(np.float64) - g[key])) < 1e-6 * np.max(np.abs(g[key])), key
+    info = {}
+    O.reduce_noise(synth_small(), 16000, cfg=O.GateConfig(sr=16000, stationary=True, n_fft=512, chunk_size=12000, padding=1500), info=info)
+    assert np.max(np.abs(info["thresh"] - g["thresh_512"])) < 1e-9
