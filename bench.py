@@ -167,8 +167,6 @@ def main():
               "channels_per_gpu": C_PER_GPU, "samples_per_channel": int(args.minutes * 60 * SR),
               "chunk_size": 600000, "padding": 30000, "l2_policy": "inputs (7.4 GB) larger than L2"}
     if n_gpus > 1:
-        config["collective"] = ("all-gather of the final [64*N, 28.8M] float32 waveform, issued as each 8-channel group "
-                                "finishes so NVLink traffic overlaps the next group's kernels; 16 SMs reserved for NCCL")
         config["all_gather_bytes_received_per_rank"] = (n_gpus - 1) * C_PER_GPU * int(args.minutes * 60 * SR) * 4
 
     if args.impl == "reference":
@@ -200,20 +198,44 @@ def main():
     C = C_PER_GPU
 
     x = synth_device(torch, C, n, rank * C, device)
-    out = torch.empty_like(x)
-    # multi-GPU: the persistent grids leave 16 SMs free so the NCCL all-gather kernels run concurrently
+    # multi-GPU transport for the path's one collective (the all-gather of the final waveform):
+    #   peer  results pushed into every peer's symmetric-memory buffer by the copy engines (no collective kernels)
+    #   nccl  all-gather kernels per 8-channel group on a side stream, 16 SMs reserved for them
+    pg = None
+    if world > 1 and os.environ.get("B200GATE_GATHER", "peer") == "peer":
+        ok = 1
+        try:
+            from noisereduce_b200.parallel import PeerGather
+            pg = PeerGather(world, rank, (world, C, n), torch.float32, device)
+        except Exception as exc:                             # e.g. no P2P mapping in this sandbox
+            ok = 0
+            print(f"[bench] rank {rank}: peer-memory gather unavailable ({exc!r}); using NCCL", file=sys.stderr)
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            pg = None
+    out = torch.empty_like(x) if pg is None else None
     # workspace: bits + mask numerators + cached spectra of all 3072 units (41 GB) in one batch -> one launch per kernel
-    dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256, reserve_sms=16 if world > 1 else 0,
-                    workspace_limit_bytes=64e9)
+    dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256,
+                    reserve_sms=16 if (world > 1 and pg is None) else 0, workspace_limit_bytes=64e9)
     # noise statistics once (stationary.py:61-81): the reference's sequential channel mean, chained over ranks
     if world == 1:
         dg.noise_stats(x)
     else:
         from noisereduce_b200.parallel import chained_noise_stats
         chained_noise_stats(dg, x, rank, world)
-    gathered = torch.empty((world * C, n), dtype=torch.float32, device=device) if world > 1 else None
+    gathered = torch.empty((world * C, n), dtype=torch.float32, device=device) if (world > 1 and pg is None) else None
     comm_stream = torch.cuda.Stream() if world > 1 else None
     acc_stats = {"k1_ms": 0.0, "smooth_ms": 0.0, "k2_ms": 0.0, "fused_ms": 0.0, "kernel_launches": 0}
+    if n_gpus > 1:
+        config["collective"] = (
+            "all-gather of the final [64*N, 28.8M] float32 waveform: each rank's kernels write into its slice of a "
+            "symmetric-memory buffer and the copy engines push every finished 8-channel group into all peers' buffers over "
+            "NVLink while the next group is computed (no collective kernels, no reserved SMs); device-side barrier per step"
+            if pg is not None else
+            "all-gather of the final [64*N, 28.8M] float32 waveform, issued as each 8-channel group finishes so NVLink "
+            "traffic overlaps the next group's kernels (NCCL kernels; 16 SMs reserved for them)")
+        config["gather_transport"] = "peer-copy-engine" if pg is not None else "nccl"
 
     def step():
         if world == 1:
@@ -221,9 +243,10 @@ def main():
             s_ = dg.gate.stats()
             for k_ in acc_stats:
                 acc_stats[k_] += s_[k_]
+        elif pg is not None:
+            from noisereduce_b200.parallel import sharded_run_peer_push
+            sharded_run_peer_push(dg, x, pg, groups=8)
         else:
-            # the path's single collective -- the all-gather of the final waveform -- is issued per
-            # channel group so NVLink traffic overlaps the kernels of the next group
             # (measured on 2 and 4 B200s: this beats both one monolithic all-gather after the kernels and
             #  64 per-channel zero-copy gathers -- profiles/r01_scaling_notes.md)
             from noisereduce_b200.parallel import sharded_run_overlapped
@@ -262,6 +285,18 @@ def main():
     ms_per_step = ms / args.steps
     value = world * C * n / (ms_per_step * 1e-3)
     stats = dg.gate.stats()
+    # the gathered waveform every rank holds must be what each owner computed: compare per-rank checksums
+    gather_verified = None
+    if world > 1:
+        full = pg.buf if pg is not None else gathered.view(world, C, n)
+        mine = full[rank].sum(dtype=torch.float64).view(1)
+        owners = torch.empty(world, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(owners, mine)
+        seen = torch.stack([full[r].sum(dtype=torch.float64) for r in range(world)])
+        okf = torch.tensor([1.0 if bool((seen == owners).all().item()) else 0.0], device=device)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        gather_verified = bool(okf.item() > 0)
+    ref_out = out if out is not None else pg.buf[rank]
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------
     e2e = None
@@ -295,7 +330,7 @@ def main():
         if ok > 0 and dt > 0:
             e2e = {"value": world * C * n / dt, "unit": UNIT, "h2d_bytes_per_step": C * n * 4,
                    "d2h_bytes_per_step": C * n * 4, "ms_per_step": dt * 1e3, "steps": ksteps,
-                   "parity_vs_device_path": float((hy.to(device) - out).abs().max().item()),
+                   "parity_vs_device_path": float((hy.to(device) - ref_out).abs().max().item()),
                    "note": "per-rank host buffers (pinned), slab-pipelined H2D / kernels / D2H; no collective in this leg"}
         else:
             e2e = {"value": None, "unit": UNIT, "error": locals().get("e2e_err", "failed on another rank")}
@@ -323,6 +358,7 @@ def main():
                      "note": "instruction-issue / dependency bound, not HBM bound (k2: ~2000 warp-instructions per frame pair, 60 % issue-active)"},
         "e2e": e2e,
         "gpu_launches": launches,
+        "gather_verified": gather_verified,
         "clocks": clocks,
         "exactness": {k: stats[k] for k in ("bins_rechecked_fp64", "bins_unresolved", "rowfloor_flags", "rowfloor_ambiguous")},
     }

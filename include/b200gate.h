@@ -140,7 +140,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
  * base.py:167-226).  mode 0: the whole recording (default).  mode 1: only chunks [a, b] of the chunk grid
  * anchored at sample 0 (the reference's chunked branch); samples outside those chunks are not written.
  * mode 2: one padded chunk covering [0, a) whose padding is read from the recording itself (the reference's
- * `filter_chunk(0, end_frame)` branch, base.py:222); only out[:, 0:a] is written. */
+ * `filter_chunk(0, end_frame)` branch, base.py:222); only out[:, 0:a] is written.
+ * In modes 1 and 2 `out` is still the address of (row 0, sample 0), but only the range is addressed: a caller
+ * may pass `slab - first_sample` with out_stride = the slab's row pitch (>= the range length) to have the range
+ * written densely into a [C][range] slab (noisereduce_b200/parallel.py gathers such slabs across GPUs). */
 int b200gate_set_range(b200gate_handle* h, int32_t mode, int64_t a, int64_t b);
 
 int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out);

@@ -710,7 +710,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     if (!h || !in || !out || C <= 0 || N <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
     const bool torch_sem = h->p.surface == B200GATE_SURFACE_TORCH;
     const int64_t No = torch_sem ? (N / h->p.hop_length) * h->p.hop_length : N;    // torchgate.py:255-262 length
-    if (in_stride < N || out_stride < No) return fail(h, B200GATE_ERR_ARG, "row strides too small");
+    // In a range mode only samples [o_lo, o_hi) of a row are addressed, so `out` may be a virtual base
+    // (slab - o_lo) over rows as short as the range: the stride check below uses the range length.
+    if (in_stride < N || (out_stride < No && (torch_sem || h->range_mode == 0)))
+        return fail(h, B200GATE_ERR_ARG, "row strides too small");
     if (torch_sem && N < 2 * h->p.win_length) return fail(h, B200GATE_ERR_ARG, "x must be bigger than %d", 2 * h->p.win_length);
     if (torch_sem && h->tthr_units > 1 && h->tthr_units != C)
         return fail(h, B200GATE_ERR_ARG, "xn has %d rows, x has %lld", h->tthr_units, (long long)C);
@@ -743,6 +746,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const long long w_lo = torch_sem ? 0 : std::max(0LL, o_lo - rpad);
     const long long w_hi = torch_sem ? N : std::min<long long>(N, o_hi + rpad);
     const long long Wn = w_hi - w_lo, On = o_hi - o_lo;
+    if (out_stride < On) return fail(h, B200GATE_ERR_ARG, "output row stride %lld shorter than the range (%lld samples)",
+                                     (long long)out_stride, On);
 
     // ---- where the kernels read / write ---------------------------------------------------------------
     // The n_fft = 1024 numpy-surface kernels are templated on the sample dtype: they read the caller's

@@ -57,3 +57,25 @@ class DeviceGate:
         self.gate.run_device(x.data_ptr(), out.data_ptr(), self._NP[x.dtype], x.shape[0], x.shape[1], x.stride(0),
                              out.stride(0), st)
         return out
+
+    def run_chunks(self, x: torch.Tensor, slab: torch.Tensor, first: int, last: int) -> torch.Tensor:
+        """Denoise only chunks [first, last] of the chunk grid (base.py:175-217) and write them densely into
+        `slab` ([C, >= range length], contiguous rows): the library addresses the output through the virtual
+        base `slab - first * chunk_size` (b200gate_set_range mode 1).  Returns the written view."""
+        self._check(x)
+        self._check(slab)
+        cs = int(self.gate.params.chunk_size)
+        C, N = x.shape
+        if cs <= 0 or N <= cs:
+            raise ValueError("run_chunks needs a chunked recording (N > chunk_size)")
+        lo, hi = first * cs, min(N, (last + 1) * cs)
+        if slab.dtype != x.dtype or slab.shape[0] != C or slab.shape[1] < hi - lo:
+            raise ValueError("slab must be [C, >= range length] in x's dtype")
+        st = torch.cuda.current_stream().cuda_stream if x.is_cuda else None
+        self.gate.set_range(1, first, last)
+        try:
+            self.gate.run_device(x.data_ptr(), slab.data_ptr() - lo * x.element_size(), self._NP[x.dtype], C, N,
+                                 x.stride(0), slab.stride(0), st)
+        finally:
+            self.gate.set_range(0)
+        return slab[:, : hi - lo]

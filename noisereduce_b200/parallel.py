@@ -109,3 +109,164 @@ def interleaved_run_overlapped(dg, x_local: torch.Tensor, out_local: torch.Tenso
                 dist.all_gather_into_tensor(gathered[c].view(-1), out_local[c], group=group)
     cur.wait_stream(comm_stream)
     return gathered
+
+
+# ---- config 5: the gathered result does not fit one GPU -> gather slab by slab into a ring ------------------
+def make_slab_ring(C: int, slab_len: int, world: int, dtype, device):
+    """Two dense [C, slab] compute buffers and two [world, C, slab] gather slots."""
+    bufs = [torch.empty((C, slab_len), dtype=dtype, device=device) for _ in range(2)]
+    ring = [torch.empty((world, C, slab_len), dtype=dtype, device=device) for _ in range(2)] if world > 1 else None
+    return bufs, ring
+
+
+def sharded_run_slab_ring(dg, x_local: torch.Tensor, world: int, comm_stream=None, slab_chunks: int = 1,
+                          consume=None, group=None, buffers=None, peer: "PeerGather | None" = None):
+    """Channel-sharded run whose all-gathered result (world * C * N samples) is larger than one GPU's memory
+    (BASELINE config 5: 512 ch x 60 min = 354 GB).  The recording is walked in slabs of `slab_chunks` chunks
+    of the reference's chunk grid: each slab is denoised into one of two dense [C, slab] buffers
+    (DeviceGate.run_chunks), all-gathered on `comm_stream` into one of two [world, C, slab] ring slots while
+    the next slab is being computed, and handed to `consume(gathered_view, first_sample, slab_index)` (run on
+    the communication stream: a checksum, a writer, the next stage); nothing else is retained.
+    Returns the list of consume() results.  Thresholds must already be set (chained_noise_stats).
+    With `peer` (a PeerGather of shape [2, world, C, slab]) the ring lives in symmetric memory: the kernels
+    write slab s into peer.buf[s & 1, rank] and the copy engines push it to every peer (no NCCL kernels)."""
+    if peer is not None:
+        return _slab_ring_peer(dg, x_local, world, slab_chunks, consume, peer)
+    C, N = x_local.shape
+    cs = int(dg.gate.params.chunk_size)
+    n_chunks = (N - 1) // cs + 1
+    slab_len = slab_chunks * cs
+    bufs, ring = buffers if buffers is not None else make_slab_ring(C, slab_len, world, x_local.dtype, x_local.device)
+    cuda = x_local.is_cuda
+    cur = torch.cuda.current_stream() if cuda else None
+    gathered_free = [None, None]           # events: ring slot / dense buffer consumed
+    results = []
+    for si, first in enumerate(range(0, n_chunks, slab_chunks)):
+        last = min(n_chunks - 1, first + slab_chunks - 1)
+        k = si & 1
+        if cuda and gathered_free[k] is not None:
+            cur.wait_event(gathered_free[k])                   # slot k's previous gather + consume finished
+        view = dg.run_chunks(x_local, bufs[k], first, last)    # [C, n_s]
+        n_s = view.shape[1]
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            comm_stream.wait_event(ev)
+        ctx = torch.cuda.stream(comm_stream) if cuda else _Null()
+        with ctx:
+            if world > 1:
+                if n_s == slab_len:
+                    dist.all_gather_into_tensor(ring[k].view(-1), bufs[k].view(-1), group=group)
+                    g = ring[k]
+                else:                                          # ragged last slab: gather the dense part only
+                    part = view.contiguous()
+                    g = ring[k].view(-1)[: world * C * n_s].view(world, C, n_s)
+                    dist.all_gather_into_tensor(g.view(-1), part.view(-1), group=group)
+            else:
+                g = view.unsqueeze(0)
+            results.append(consume(g, first * cs, si) if consume is not None else None)
+            if cuda:
+                gathered_free[k] = torch.cuda.Event()
+                gathered_free[k].record(comm_stream)
+    if cuda:
+        cur.wait_stream(comm_stream)
+    return results
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+# ---- peer-memory gather: results pushed into every peer's buffer by the copy engines over NVLink ----------
+class PeerGather:
+    """The all-gather of the final waveform without collective kernels.
+
+    The gathered [world, C, N] tensor lives in symmetric memory (torch.distributed._symmetric_memory: every
+    rank's buffer is mapped into every peer's address space over NVLink / NVSwitch).  A rank's kernels write
+    its own rows straight into its slice of the local buffer; as soon as a channel group is finished, plain
+    device-to-device copies -- copy engines, no SMs, one stream per peer -- push those rows into the same
+    slice of every peer's buffer while the next group is computed.  A device-side barrier at the end of the
+    step makes all pushes visible.  Compared with NCCL all-gather kernels running next to the persistent
+    gate kernels this leaves all SMs to the gate (no reserve_sms) and removes the kernels' HBM contention.
+    """
+
+    def __init__(self, world: int, rank: int, shape, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.shape = world, rank, tuple(shape)
+        self.buf = symm.empty(self.shape, dtype=dtype, device=device)
+        self.h = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.views = [self.buf if r == rank else self.h.get_buffer(r, self.shape, dtype) for r in range(world)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(world)]
+        self.h.barrier()
+
+    def push(self, index, after: "torch.cuda.Event"):
+        """Copy self.buf[index] into the same place of every peer's buffer once `after` has fired."""
+        src = self.buf[index]
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            st = self.streams[r]
+            st.wait_event(after)
+            with torch.cuda.stream(st):
+                self.views[r][index].copy_(src, non_blocking=True)
+
+    def finish(self):
+        """Join the push streams into the current stream, then a device-side barrier across ranks."""
+        cur = torch.cuda.current_stream()
+        for r in range(self.world):
+            if r != self.rank:
+                cur.wait_stream(self.streams[r])
+        self.h.barrier()
+
+
+def sharded_run_peer_push(dg, x_local: torch.Tensor, pg: PeerGather, groups: int = 8):
+    """Channel-sharded run with the peer-memory gather: pg.buf is the final [world, C, N] waveform on every
+    rank when this returns (stream-ordered).  Thresholds must already be set (chained_noise_stats)."""
+    C, N = x_local.shape
+    gs = (C + groups - 1) // groups
+    cur = torch.cuda.current_stream()
+    mine = pg.buf[pg.rank]
+    for g0 in range(0, C, gs):
+        g1 = min(C, g0 + gs)
+        dg.run(x_local[g0:g1], mine[g0:g1])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        pg.push((pg.rank, slice(g0, g1)), ev)
+    pg.finish()
+    return pg.buf
+
+
+def _slab_ring_peer(dg, x_local, world, slab_chunks, consume, pg: PeerGather):
+    C, N = x_local.shape
+    cs = int(dg.gate.params.chunk_size)
+    n_chunks = (N - 1) // cs + 1
+    cur = torch.cuda.current_stream()
+    comm = pg.streams[pg.rank]                       # consume() runs here
+    slot_free = [None, None]
+    results = []
+    for si, first in enumerate(range(0, n_chunks, slab_chunks)):
+        last = min(n_chunks - 1, first + slab_chunks - 1)
+        k = si & 1
+        if slot_free[k] is not None:
+            cur.wait_event(slot_free[k])             # every rank consumed slot k's previous slab (barrier-ordered)
+        view = dg.run_chunks(x_local, pg.buf[k, pg.rank], first, last)
+        n_s = view.shape[1]
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        pg.push((k, pg.rank), ev)                    # whole slot rows: dense [C, slab] block, one copy per peer
+        comm.wait_event(ev)
+        for r in range(world):
+            if r != pg.rank:
+                comm.wait_stream(pg.streams[r])
+        with torch.cuda.stream(comm):
+            pg.h.barrier()                           # all ranks' pushes of this slab have landed
+            results.append(consume(pg.buf[k, :, :, :n_s], first * cs, si) if consume is not None else None)
+            pg.h.barrier(channel=1)                  # ... and have been consumed everywhere before the slot is reused
+            slot_free[k] = torch.cuda.Event()
+            slot_free[k].record(comm)
+    cur.wait_stream(comm)
+    return results

@@ -97,3 +97,50 @@ def test_interleaved_ownership_equals_one_process(tmp_path):
     dg.noise_stats(y)
     assert np.array_equal(r["thr"], dg.gate.noise_threshold())
     assert np.array_equal(r["full"], dg.run(y).numpy())
+
+
+def _worker_ring(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    from noisereduce_b200.device import DeviceGate
+    from noisereduce_b200.parallel import chained_noise_stats, sharded_run_slab_ring
+    from tests.cusim_util import cusim_library
+    from tests.synth_host import synth_small
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    y = torch.from_numpy(synth_small(C=4, n=11000))
+    cpr = y.shape[0] // world
+    x_local = y[rank * cpr: (rank + 1) * cpr].contiguous()
+    dg = DeviceGate(sr=SR, stationary=True, lib=cusim_library(), chunk_size=3000, padding=400)
+    chained_noise_stats(dg, x_local, rank, world)
+    res = {}
+    for slab_chunks in (1, 3):                       # 4 slabs (ragged last) / 2 slabs (ragged last)
+        full = torch.zeros((world * cpr, y.shape[1]))
+        sums = sharded_run_slab_ring(
+            dg, x_local, world, slab_chunks=slab_chunks,
+            consume=lambda g, first, si: (full.view(world, cpr, -1)[:, :, first: first + g.shape[2]].copy_(g),
+                                          float(g.double().sum()))[1])
+        res[f"full{slab_chunks}"] = full.numpy()
+        res[f"sums{slab_chunks}"] = np.array(sums)
+    allsums = [None] * world
+    dist.all_gather_object(allsums, res["sums1"].tolist())
+    if rank == 0:
+        np.savez(result_path, same_checksums=np.array(allsums[0] == allsums[1]), **res)
+    dist.destroy_process_group()
+
+
+def test_slab_ring_gather_equals_one_process(tmp_path):
+    """Config 5's data path at world_size 2: slabs of the chunk grid are denoised densely (set_range +
+    virtual output base), all-gathered into ring slots and consumed; the stitched result equals one process."""
+    from noisereduce_b200.device import DeviceGate
+    from tests.cusim_util import cusim_library
+    from tests.synth_host import synth_small
+    cusim_library()
+    result = str(tmp_path / "res3.npz")
+    mp.spawn(_worker_ring, args=(2, _free_port(), result), nprocs=2, join=True)
+    r = np.load(result)
+    y = torch.from_numpy(synth_small(C=4, n=11000))
+    dg = DeviceGate(sr=SR, stationary=True, lib=cusim_library(), chunk_size=3000, padding=400)
+    dg.noise_stats(y)
+    single = dg.run(y).numpy()
+    assert np.array_equal(r["full1"], single) and np.array_equal(r["full3"], single)
+    assert bool(r["same_checksums"]) and len(r["sums1"]) == 4 and len(r["sums3"]) == 2
+    assert abs(r["sums1"].sum() - single.astype(np.float64).sum()) < 1e-6
