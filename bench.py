@@ -206,7 +206,8 @@ def main():
         ok = 1
         try:
             from noisereduce_b200.parallel import PeerGather
-            pg = PeerGather(world, rank, (world, C, n), torch.float32, device)
+            pg = PeerGather(world, rank, (world, C, n), torch.float32, device,
+                            splits=int(os.environ.get("B200GATE_PUSH_SPLITS", "1")))
         except Exception as exc:                             # e.g. no P2P mapping in this sandbox
             ok = 0
             print(f"[bench] rank {rank}: peer-memory gather unavailable ({exc!r}); using NCCL", file=sys.stderr)

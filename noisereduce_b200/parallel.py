@@ -194,13 +194,15 @@ class PeerGather:
     gate kernels this leaves all SMs to the gate (no reserve_sms) and removes the kernels' HBM contention.
     """
 
-    def __init__(self, world: int, rank: int, shape, dtype, device, group=None):
+    def __init__(self, world: int, rank: int, shape, dtype, device, group=None, splits: int = 1):
         import torch.distributed._symmetric_memory as symm
         self.world, self.rank, self.shape = world, rank, tuple(shape)
+        self.splits = max(1, int(splits))            # concurrent sub-copies per peer (more copy engines in flight)
         self.buf = symm.empty(self.shape, dtype=dtype, device=device)
         self.h = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
         self.views = [self.buf if r == rank else self.h.get_buffer(r, self.shape, dtype) for r in range(world)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(world)]
+        self.sub = [[torch.cuda.Stream(device=device) for _ in range(self.splits - 1)] for _ in range(world)]
         self.h.barrier()
 
     def push(self, index, after: "torch.cuda.Event"):
@@ -209,10 +211,18 @@ class PeerGather:
         for r in range(self.world):
             if r == self.rank:
                 continue
-            st = self.streams[r]
-            st.wait_event(after)
-            with torch.cuda.stream(st):
-                self.views[r][index].copy_(src, non_blocking=True)
+            dst = self.views[r][index]
+            rows = src.shape[0]
+            parts = min(self.splits, rows) if src.dim() >= 2 else 1
+            step = (rows + parts - 1) // parts if parts > 1 else rows
+            for i in range(parts):
+                st = self.streams[r] if i == 0 else self.sub[r][i - 1]
+                st.wait_event(after)
+                with torch.cuda.stream(st):
+                    if parts == 1:
+                        dst.copy_(src, non_blocking=True)
+                    else:
+                        dst[i * step: (i + 1) * step].copy_(src[i * step: (i + 1) * step], non_blocking=True)
 
     def finish(self):
         """Join the push streams into the current stream, then a device-side barrier across ranks."""
@@ -220,6 +230,8 @@ class PeerGather:
         for r in range(self.world):
             if r != self.rank:
                 cur.wait_stream(self.streams[r])
+                for st in self.sub[r]:
+                    cur.wait_stream(st)
         self.h.barrier()
 
 
@@ -262,6 +274,8 @@ def _slab_ring_peer(dg, x_local, world, slab_chunks, consume, pg: PeerGather):
         for r in range(world):
             if r != pg.rank:
                 comm.wait_stream(pg.streams[r])
+                for st in pg.sub[r]:
+                    comm.wait_stream(st)
         with torch.cuda.stream(comm):
             pg.h.barrier()                           # all ranks' pushes of this slab have landed
             results.append(consume(pg.buf[k, :, :, :n_s], first * cs, si) if consume is not None else None)
