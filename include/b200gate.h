@@ -50,10 +50,10 @@ typedef struct b200gate_params {
     int32_t abi_version;        /* B200GATE_ABI_VERSION                                          */
     int32_t surface;            /* B200GATE_SURFACE_*                                            */
     int32_t stationary;         /* 1: stationary gate, 0: non-stationary gate                    */
-    int32_t n_fft;              /* numpy surface: any power of two in [16, 8192]; torch surface: 1024            */
+    int32_t n_fft;              /* any power of two in [16, 8192]                                 */
     int32_t win_length;         /* 1 <= win_length <= n_fft                                      */
-    int32_t hop_length;         /* 1 <= hop_length <= win_length.  n_fft=1024/win=1024/hop=256 (both gates) and
-                                 * 2048/2048/512 (non-stationary) run the tuned FP32 kernels; every other
+    int32_t hop_length;         /* 1 <= hop_length <= win_length.  n_fft=1024/win=1024/hop=256 (both gates, both
+                                 * surfaces) and 2048/2048/512 (numpy surface, non-stationary) run the tuned FP32 kernels; every other
                                  * geometry runs the float64 general family (gate_generic.cuh)    */
     int32_t n_grad_freq;        /* smoothing half-widths; 0,0 = mask smoothing disabled          */
     int32_t n_grad_time;

@@ -19,7 +19,8 @@ namespace b200 {
 
 struct GGeom {
     Geom g;                 // chunk table; g.T = (Lp + 2 (W/2) - W) / H + 1
-    int N, logN, W, F;      // n_fft, log2, win_length, N/2 + 1
+    int N, logN, W, F;      // n_fft, log2, frame length (win_length; n_fft on the torch surface), N/2 + 1
+    long long out_len;      // > 0: samples written per row (torch surface: (L / H) * H); 0: the chunk centre
 };
 
 struct GTables {
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(256) gk_stft(const GStftArgs<T> a) {
 struct GDecideArgs {
     int n_units, T, F;
     double eps, top_db, p;
-    const double* thr;      // [F] dB
+    const double* thr;      // [thr_units][F] dB (thr_units 1: shared by every unit)
+    int thr_units;
     const double2* X;
     double* M;              // [n_units][T][F]: dB scratch, then mask0 * p + (1 - p)
     int dbg_ul, FW;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(128) gk_decide(const GDecideArgs a) {
         M[(size_t)t * a.F] = db;
         mx = fmax(mx, db);
     }
-    const double fl = mx - a.top_db, th = a.thr[f];
+    const double fl = mx - a.top_db, th = a.thr[(size_t)(a.thr_units == 1 ? 0 : ul) * a.F + f];
     for (int t = 0; t < a.T; ++t) {
         const bool on = fmax(M[(size_t)t * a.F], fl) > th;                   // utils.py:16, stationary.py:99-106
         M[(size_t)t * a.F] = (on ? 1.0 : 0.0) * a.p + (1.0 - a.p);           // stationary.py:108-110
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(256) gk_ola(const GOlaArgs<T> a) {
     const int u = g.u0 + ul;
     const long long chunk = u / g.C, ch = u - chunk * g.C;
     const long long start = chunk * g.step;
-    const long long out_len = min((long long)g.step, (long long)(g.n_total - start));
+    const long long out_len = a.gg.out_len > 0 ? a.gg.out_len : min((long long)g.step, (long long)(g.n_total - start));
     const long long sig_len = (long long)(g.T - 1) * H + (W & 1);           // istft length after the boundary crop
     T* yrow = a.y + ch * g.out_stride + start;
     const double* fr = a.frames + (size_t)ul * g.T * W;
@@ -269,6 +271,72 @@ __global__ void __launch_bounds__(256) gk_noise_db(const double2* __restrict__ X
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double2 v = X[i];
         db[i] = 20.0 * log10(hypot(v.x, v.y) + eps);
+    }
+}
+
+
+// ---- TorchGate surface (torchgate.py:127-198): per-row statistics, moving-mean follower --------------------------
+struct GTStatArgs {
+    int n_units, T, F, ddof;
+    double eps, top_db, n_std;
+    const double2* X;
+    double* scratch;        // [n_units][T][F] dB scratch
+    double* thr;            // [n_units][F]
+};
+__global__ void __launch_bounds__(128) gk_tstats(const GTStatArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)a.n_units * a.F) return;
+    const int ul = (int)(i / a.F), f = (int)(i - (long long)ul * a.F);
+    const double2* X = a.X + (size_t)ul * a.T * a.F + f;
+    double* D = a.scratch + (size_t)ul * a.T * a.F + f;
+    double mx = -1.0e300;
+    for (int t = 0; t < a.T; ++t) {
+        const double2 v = X[(size_t)t * a.F];
+        const double db = 20.0 * log10(hypot(v.x, v.y) + a.eps);            // torchgate/utils.py:6-23
+        D[(size_t)t * a.F] = db;
+        mx = fmax(mx, db);
+    }
+    const double fl = mx - a.top_db;
+    double sum = 0.0;
+    for (int t = 0; t < a.T; ++t) sum += fmax(D[(size_t)t * a.F], fl);
+    const double mean = sum / a.T;
+    double ss = 0.0;
+    for (int t = 0; t < a.T; ++t) {
+        const double d = fmax(D[(size_t)t * a.F], fl) - mean;
+        ss += d * d;
+    }
+    a.thr[(size_t)ul * a.F + f] = mean + sqrt(ss / (double)(a.T - a.ddof)) * a.n_std;   // torch.std_mean: unbiased
+}
+
+struct GMovArgs {
+    int n_units, T, F, n;
+    double n_thresh, inv_temp, p;
+    const double2* X;
+    double* M;              // mask out
+    double* tmp;            // |X|
+};
+__global__ void __launch_bounds__(128) gk_movmean(const GMovArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)a.n_units * a.F) return;
+    const int ul = (int)(i / a.F), f = (int)(i - (long long)ul * a.F);
+    const size_t o = (size_t)ul * a.T * a.F + f;
+    const double2* X = a.X + o;
+    double* M = a.M + o;
+    double* A = a.tmp + o;
+    for (int t = 0; t < a.T; ++t) {
+        const double2 v = X[(size_t)t * a.F];
+        A[(size_t)t * a.F] = hypot(v.x, v.y);
+    }
+    const int left = (a.n - 1) / 2, right = a.n - 1 - left;                  // conv1d padding='same', zero padded
+    for (int t = 0; t < a.T; ++t) {
+        double s = 0.0;                                                      // summed in window order like the oracle's cumsum
+        const int lo = max(0, t - left), hi = min(a.T - 1, t + right);
+        for (int k = lo; k <= hi; ++k) s += A[(size_t)k * a.F];
+        s /= (double)a.n;
+        const double Av = A[(size_t)t * a.F];
+        const double r = (Av - s) / s;
+        const double m = 1.0 / (1.0 + exp(-(r - a.n_thresh) * a.inv_temp)); // torchgate/utils.py:39
+        M[(size_t)t * a.F] = m * a.p + (1.0 - a.p);                          // torchgate.py:241 blends before smoothing
     }
 }
 

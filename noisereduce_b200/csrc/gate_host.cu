@@ -57,6 +57,8 @@ struct b200gate_handle {
     // general-geometry family (gate_generic.cuh)
     bool generic = false;
     int g_logN = 0;
+    int g_W = 0;                                   // frame length: win_length (numpy surface) / n_fft (torch surface)
+    double* d_gtthr = nullptr;                     // torch surface: thresholds from xn, [tthr_units][F]
     double *d_gwa = nullptr, *d_gws = nullptr, *d_gw2 = nullptr, *d_gthr = nullptr;
     double2* d_gcs = nullptr;
     // workspace
@@ -289,17 +291,26 @@ int noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, c
 // ---- general-geometry family: tables, noise statistics ----------------------------------------------------------
 int build_generic_tables(b200gate_handle* h) {
     const int N = h->p.n_fft, W = h->p.win_length;
-    std::vector<double> w(W), wa(W), ws(W), w2(W);
+    const bool torch_sem = h->p.surface == B200GATE_SURFACE_TORCH;
+    std::vector<double> w(W);
     double sw = 0.0;
     for (int n = 0; n < W; ++n) {
-        w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)W);          // scipy get_window('hann', W): periodic
+        if ((int)h->user_window.size() == W) w[n] = (double)h->user_window[n];             // torch.hann_window (float32)
+        else if (torch_sem) w[n] = (double)(cosf((float)n * (float)(M_PI * 2.0 / W)) * -0.5f + 0.5f);
+        else w[n] = 0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)W);                  // scipy get_window('hann', W): periodic
         sw += w[n];
     }
     h->sum_w = sw;
+    // numpy surface: frames of win_length samples, spectrum scaled by 1 / sum(w) (scaling='spectrum'), rfft pads at
+    // the END.  torch surface (torch.stft, center=True): frames of n_fft samples under the window centre-padded
+    // to n_fft, no scaling (torchgate.py:223-232).
+    const int Wf = torch_sem ? N : W, left = torch_sem ? (N - W) / 2 : 0;
+    h->g_W = Wf;
+    std::vector<double> wa(Wf, 0.0), ws(Wf, 0.0), w2(Wf, 0.0);
     for (int n = 0; n < W; ++n) {
-        wa[n] = w[n] / sw;                                                   // scaling='spectrum'
-        ws[n] = w[n] * sw / (double)N;                                       // irfft's 1/N, istft's * sum(w), window
-        w2[n] = w[n] * w[n];
+        wa[left + n] = torch_sem ? w[n] : w[n] / sw;
+        ws[left + n] = torch_sem ? w[n] / (double)N : w[n] * sw / (double)N;               // irfft's 1/N (* sum(w) in scipy's istft)
+        w2[left + n] = w[n] * w[n];
     }
     std::vector<double2> cs(N);
     for (int m = 0; m < N; ++m) {
@@ -322,7 +333,7 @@ GTables generic_tables(const b200gate_handle* h) {
 
 GGeom generic_geom(const b200gate_handle* h, const Geom& g) {
     GGeom gg{};
-    gg.g = g; gg.N = h->p.n_fft; gg.logN = h->g_logN; gg.W = h->p.win_length; gg.F = h->F;
+    gg.g = g; gg.N = h->p.n_fft; gg.logN = h->g_logN; gg.W = h->g_W; gg.F = h->F; gg.out_len = 0;
     return gg;
 }
 
@@ -431,17 +442,15 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
                        p->surface == B200GATE_SURFACE_NUMPY && !p->stationary;
     // everything else the reference accepts on the numpy surface runs on the general-geometry family
     // (path_flags bit 2 forces it for the tuned geometries too: the float64 cross-check of the fast kernels)
-    const bool want_generic = (!geo1k && !geo2k) || ((p->path_flags & 4) && p->surface == B200GATE_SURFACE_NUMPY);
+    const bool want_generic = (!geo1k && !geo2k) || (p->path_flags & 4);
     int logN = 0;
     while ((1 << logN) < p->n_fft) ++logN;
     if (want_generic) {
         const bool pow2 = p->n_fft >= 16 && p->n_fft <= 8192 && (1 << logN) == p->n_fft;
-        if (p->surface != B200GATE_SURFACE_NUMPY || !pow2 || p->win_length < 1 || p->win_length > p->n_fft ||
-            p->hop_length < 1 || p->hop_length > p->win_length)
+        if (!pow2 || p->win_length < 1 || p->win_length > p->n_fft || p->hop_length < 1 || p->hop_length > p->win_length)
             return fail(nullptr, B200GATE_ERR_ARG,
-                        "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d (%s gate, %s surface): the numpy "
-                        "surface runs any power-of-two n_fft in [16, 8192] with 1 <= hop_length <= win_length <= n_fft; "
-                        "the torch surface runs n_fft=1024, win_length=1024, hop_length=256",
+                        "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d (%s gate, %s surface): n_fft must "
+                        "be a power of two in [16, 8192] with 1 <= hop_length <= win_length <= n_fft",
                         p->n_fft, p->win_length, p->hop_length, p->stationary ? "stationary" : "non-stationary",
                         p->surface == B200GATE_SURFACE_NUMPY ? "numpy" : "torch");
     }
@@ -510,7 +519,7 @@ void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
                     h->d_wa64, h->d_cs64, h->d_tthr, h->d_maxabs, h->d_fscratch, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
-                    h->d_dbg_mask, h->d_dbg_bits, h->d_gwa, h->d_gws, h->d_gw2, h->d_gthr, h->d_gcs};
+                    h->d_dbg_mask, h->d_dbg_bits, h->d_gwa, h->d_gws, h->d_gw2, h->d_gthr, h->d_gcs, h->d_gtthr};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -558,6 +567,11 @@ int b200gate_get_noise_mean_std(const b200gate_handle* h, double* mean_db, doubl
 
 int b200gate_set_window(b200gate_handle* h, const float* window, int32_t win_length) {
     if (!h || !window) return B200GATE_ERR_ARG;
+    if (h->generic) {
+        if (win_length != h->p.win_length) return fail(h, B200GATE_ERR_ARG, "window length %d != win_length %d", win_length, h->p.win_length);
+        h->user_window.assign(window, window + win_length);
+        return build_generic_tables(h);
+    }
     if (win_length != h->p.n_fft) return fail(h, B200GATE_ERR_ARG, "window length %d != n_fft %d", win_length, h->p.n_fft);
     h->user_window.assign(window, window + win_length);
     return build_static_tables(h);
@@ -685,6 +699,30 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
     Geom g{};
     g.H = h->p.hop_length; g.C = (int)Bn; g.n_total = Ln; g.step = Ln; g.n_chunks = 1; g.pad = 0; g.Lp = Ln;
     g.T = (int)(Ln / g.H) + 1; g.in_stride = xs; g.out_stride = xs; g.u0 = 0; g.n_units = (int)Bn;
+    if (h->generic) {                                  // general family: float64 statistics of xn's own frames
+        const int F = h->F, N = h->p.n_fft;
+        if (Bn > 65535) return fail(h, B200GATE_ERR_ARG, "xn has too many rows");
+        double2* gX = nullptr;
+        double* gD = nullptr;
+        CK(h, cudaMalloc((void**)&gX, (size_t)Bn * g.T * F * sizeof(double2)));
+        CK(h, cudaMalloc((void**)&gD, (size_t)Bn * g.T * F * sizeof(double)));
+        if (h->d_gtthr) cudaFree(h->d_gtthr);
+        h->d_gtthr = nullptr;
+        CK(h, cudaMalloc((void**)&h->d_gtthr, (size_t)Bn * F * sizeof(double)));
+        GStftArgs<float> sa{};
+        sa.gg = generic_geom(h, g); sa.tb = generic_tables(h); sa.x = x; sa.X = gX;
+        { auto kern_ = gk_stft<float>; B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)Bn), dim3(generic_threads(N)), (size_t)N * sizeof(double2), st, sa); }
+        GTStatArgs ta{};
+        ta.n_units = (int)Bn; ta.T = g.T; ta.F = F; ta.ddof = h->p.std_ddof; ta.eps = kEps64; ta.top_db = h->p.top_db;
+        ta.n_std = h->p.n_std_thresh; ta.X = gX; ta.scratch = gD; ta.thr = h->d_gtthr;
+        B200_LAUNCH(gk_tstats, dim3((unsigned)(((long long)Bn * F + 127) / 128)), dim3(128), 0, st, ta);
+        CK(h, cudaGetLastError());
+        CK(h, cudaStreamSynchronize(st));
+        cudaFree(gX); cudaFree(gD);
+        if (tmp) cudaFree(tmp);
+        h->tthr_units = (int)Bn;
+        return B200GATE_OK;
+    }
     float *mag = nullptr, *rowmax = nullptr;
     CK(h, cudaMalloc((void**)&mag, (size_t)Bn * g.T * kFPad * 4));
     CK(h, cudaMalloc((void**)&rowmax, (size_t)Bn * kFPad * 4));
@@ -811,7 +849,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     g.n_chunks = (int)n_chunks;
     g.pad = torch_sem ? 0 : p.padding;                 // TorchGate filters the whole row, no chunk padding
     g.Lp = g.step + 2 * g.pad;
-    g.T = generic ? (int)((g.Lp + 2 * (p.win_length / 2) - p.win_length) / g.H) + 1 : (int)(g.Lp / g.H) + 1;
+    g.T = generic ? (int)((g.Lp + 2 * (h->g_W / 2) - h->g_W) / g.H) + 1 : (int)(g.Lp / g.H) + 1;
     g.in_stride = xs;
     g.out_stride = ys;
     const long long U = chunk_count * C;
@@ -822,7 +860,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const bool two_k = NFFT == kN2 && !generic;
     const int FP = two_k ? kFPad2 : kFPad, FF = generic ? h->F : (two_k ? kF2 : kF);
     // frames whose masks k2 needs (same for every full chunk)
-    const long long sig_len = (long long)(g.T - 1) * g.H + (generic ? (p.win_length & 1) : 0);
+    const long long sig_len = (long long)(g.T - 1) * g.H + (generic ? (h->g_W & 1) : 0);
     long long jp_hi = std::min(g.pad + g.step, sig_len);
     int tf_lo = 0, tf_hi = 0;
     int h_lo = 0, h_hi = 0;
@@ -851,8 +889,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const bool use_zcache = !use_fused && !two_k && !generic && !(p.path_flags & 2);
     const size_t zunit = use_zcache ? (size_t)zpairs * 1024 * sizeof(float2) : 0;
     // general-geometry family: float64 spectrum, mask, scratch and synthesis frames of every unit
-    const size_t g_tf = (size_t)g.T * (size_t)h->F, g_tw = (size_t)g.T * (size_t)p.win_length;
-    const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + 4 * 256;
+    const size_t g_tf = (size_t)g.T * (size_t)h->F, g_tw = (size_t)g.T * (size_t)h->g_W;
+    const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + (size_t)h->F * 8 + 5 * 256;
     const size_t per_unit = generic ? per_unit_generic : (use_fused ? 64 : per_unit_2pass + zunit);   // the fused kernel keeps no per-unit buffers
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 24.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
@@ -892,7 +930,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t goff_M = al((size_t)ub * g_tf * 16);
     const size_t goff_tmp = goff_M + al((size_t)ub * g_tf * 8);
     const size_t goff_fr = goff_tmp + al((size_t)ub * g_tf * 8);
-    const size_t end_generic = goff_fr + al((size_t)ub * g_tw * 8);
+    const size_t goff_thr = goff_fr + al((size_t)ub * g_tw * 8);          // torch surface: per-row thresholds
+    const size_t end_generic = goff_thr + al((size_t)ub * h->F * 8);
     const size_t end_base = generic ? end_generic : use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
     const size_t off_z = al(end_base);
     const size_t end_all = off_z + al((size_t)ub * zunit);
@@ -1011,9 +1050,10 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         dbg.mask = h->d_dbg_mask;
 
         if (generic) {
-            const GGeom gg = generic_geom(h, g);
+            GGeom gg = generic_geom(h, g);
+            if (torch_sem) gg.out_len = No;                 // torch.istft length (torchgate.py:255-262)
             const GTables gt = generic_tables(h);
-            const int F = h->F, W = p.win_length, FW = (F + 31) / 32;
+            const int F = h->F, W = h->g_W, FW = (F + 31) / 32;
             double2* gX = (double2*)h->d_ws_buf;
             double* gM = (double*)(h->d_ws_buf + goff_M);
             double* gTmp = (double*)(h->d_ws_buf + goff_tmp);
@@ -1031,8 +1071,29 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (stat) {
                 GDecideArgs da{};
                 da.n_units = nu; da.T = g.T; da.F = F; da.eps = kEps64; da.top_db = p.top_db; da.p = p.prop_decrease;
-                da.thr = h->d_gthr; da.X = gX; da.M = gM; da.dbg_ul = dbg.ul; da.FW = FW; da.dbg_bits = h->d_dbg_bits;
+                da.thr = h->d_gthr; da.thr_units = 1;
+                da.X = gX; da.M = gM; da.dbg_ul = dbg.ul; da.FW = FW; da.dbg_bits = h->d_dbg_bits;
+                if (torch_sem) {                        // torchgate.py:127-165: per-row statistics (own frames or xn's)
+                    if (h->tthr_units > 0) {
+                        da.thr = h->tthr_units == 1 ? h->d_gtthr : h->d_gtthr + (size_t)u0 * F;
+                        da.thr_units = h->tthr_units == 1 ? 1 : nu;
+                    } else {
+                        double* gThr = (double*)(h->d_ws_buf + goff_thr);
+                        GTStatArgs ta{};
+                        ta.n_units = nu; ta.T = g.T; ta.F = F; ta.ddof = p.std_ddof; ta.eps = kEps64; ta.top_db = p.top_db;
+                        ta.n_std = p.n_std_thresh; ta.X = gX; ta.scratch = gM; ta.thr = gThr;
+                        B200_LAUNCH(gk_tstats, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, ta);
+                        ++launches;
+                        da.thr = gThr;
+                        da.thr_units = nu;
+                    }
+                }
                 B200_LAUNCH(gk_decide, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, da);
+            } else if (torch_sem) {                     // torchgate.py:168-198: moving-mean follower
+                GMovArgs ma{};
+                ma.n_units = nu; ma.T = g.T; ma.F = F; ma.n = std::max(1, p.n_movemean); ma.n_thresh = p.thresh_n_mult;
+                ma.inv_temp = p.sigmoid_slope; ma.p = p.prop_decrease; ma.X = gX; ma.M = gM; ma.tmp = gTmp;
+                B200_LAUNCH(gk_movmean, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, ma);
             } else {
                 const double tfr = p.time_constant_s * p.sr / (double)p.hop_length;       // nonstationary.py:109-114
                 GFollowArgs fa{};
@@ -1046,7 +1107,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (smooth) {
                 GSmoothArgs ga{};
                 ga.n_units = nu; ga.T = g.T; ga.F = F; ga.nf = nf; ga.nt = nt; ga.inv_D = 1.0 / D; ga.p = p.prop_decrease;
-                ga.blend = stat ? 0 : 1;                                                 // stationary.py blends before smoothing
+                ga.blend = (stat || torch_sem) ? 0 : 1;                                  // stationary.py / torchgate.py blend before smoothing
                 const int gr = grid_1d((long long)nu * g.T * F, 256, h->num_sm * 16);
                 ga.src = gM; ga.dst = gTmp;
                 B200_LAUNCH(gk_smooth_f, dim3(gr), dim3(256), 0, st, ga);
@@ -1060,7 +1121,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 ia.gg = gg; ia.tb = gt; ia.X = gX; ia.M = gM; ia.frames = gFr; ia.dbg_ul = dbg.ul;
                 ia.dbg_spec = (float2*)h->d_dbg_spec; ia.dbg_mask = h->d_dbg_mask;
                 B200_LAUNCH(gk_istft, dim3((unsigned)g.T, (unsigned)nu), dim3(thr_fft), smem_fft, st, ia);
-                const long long out_max = std::min<long long>(g.step, N);
+                const long long out_max = torch_sem ? No : std::min<long long>(g.step, N);
                 B200_WITH_DTYPE(kdt, {
                     GOlaArgs<T> oa{};
                     oa.gg = gg; oa.tb = gt; oa.frames = gFr; oa.y = (T*)yb;

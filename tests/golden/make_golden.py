@@ -136,6 +136,17 @@ def main():
         out_nonstat_f32=tg_n(xt32).numpy(),
         out_stat_xn_p07_f64=tg_x(xt64, xn).numpy(),
     )
+    # ---- TorchGate off the default STFT geometry (general family, torch surface) -------------------
+    xg = x[:2, :12000]
+    xg64 = torch.from_numpy(xg).double()
+    np.savez_compressed(
+        os.path.join(HERE, "torchgate_geometry.npz"),
+        versions=VERSIONS, sr=sr,
+        window_400=torch.hann_window(400).numpy(),
+        stat_512_400_100_f64=TorchGate(sr=sr, n_fft=512, win_length=400, hop_length=100)(xg64).numpy(),
+        nonstat_512_f64=TorchGate(sr=sr, nonstationary=True, n_fft=512)(xg64).numpy(),
+        stat_2048_xn_f32=TorchGate(sr=sr, n_fft=2048, prop_decrease=0.8)(torch.from_numpy(xg), torch.from_numpy(xg[:1, :6000])).numpy(),
+    )
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

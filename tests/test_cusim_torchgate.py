@@ -55,3 +55,23 @@ def test_xn_and_dtypes_and_module_contract(lib):
         TorchGate(sr=16000, prop_decrease=1.5)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         tg(torch.zeros(1, 4096))                                           # product path: no CPU fallback
+
+
+@pytest.mark.parametrize("geo", [
+    dict(n_fft=512), dict(n_fft=512, win_length=400, hop_length=100), dict(n_fft=256, win_length=255, hop_length=50),
+    dict(n_fft=2048),
+], ids=lambda g: "-".join(f"{k}{v}" for k, v in g.items()))
+def test_non_default_geometry_runs_on_the_general_family(lib, geo):
+    """TorchGate off n_fft=1024/hop=256: float64 general family with torch.stft framing (gate_generic.cuh)."""
+    x = synth_torchgate(B=2, n=6000)
+    w = torch.hann_window(geo.get("win_length", geo["n_fft"])).numpy()
+    for kw in (dict(prop_decrease=0.7), dict(nonstationary=True, n_movemean_nonstationary=7),
+               dict(freq_mask_smooth_hz=None, time_mask_smooth_ms=None)):
+        tg = TorchGate(sr=16000, **geo, **kw)
+        y = tg(torch.from_numpy(x), _lib=lib)
+        ref = TO.torchgate_forward(x.astype(np.float64), 16000, window=w, **geo, **kw)
+        assert tuple(y.shape) == ref.shape and rel(y.numpy(), ref) < 5e-7
+    tg = TorchGate(sr=16000, **geo)
+    for xn in (x[0, :5000], x[:, 500:5500]):
+        y = tg(torch.from_numpy(x), torch.from_numpy(xn), _lib=lib).numpy()
+        assert rel(y, TO.torchgate_forward(x.astype(np.float64), 16000, xn=xn.astype(np.float64), window=w, **geo)) < 5e-7

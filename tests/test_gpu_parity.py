@@ -310,3 +310,19 @@ def test_batching_slabs_and_config5_geometry(lib):
     out = nr.reduce_noise(y=yi, sr=sr, stationary=True)
     ref = O.reduce_noise(yi, sr, cfg=O.GateConfig(sr=sr, stationary=True))
     assert out.dtype == np.int16 and np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+
+
+def test_torchgate_general_geometry_golden(lib, golden_dir):
+    """TorchGate off the default STFT geometry on the GPU (general family, torch framing) against reference outputs."""
+    import torch
+    from noisereduce_b200.torchgate import TorchGate
+    from tests.synth_host import synth_torchgate
+    from tests.test_oracle_golden import TG_GEOMETRY_CASES
+    g = np.load(os.path.join(golden_dir, "torchgate_geometry.npz"))
+    x = synth_torchgate()[:2, :12000]
+    for key, (kw, xn_idx, dt) in TG_GEOMETRY_CASES.items():
+        xt = torch.from_numpy(x.astype(dt)).cuda()
+        xn = None if xn_idx is None else xt[xn_idx]
+        y = TorchGate(sr=16000, **kw)(xt, xn)
+        assert y.dtype == xt.dtype and tuple(y.shape) == g[key].shape, key
+        assert P.relinf(y.cpu().numpy(), g[key]) < 5e-5, key

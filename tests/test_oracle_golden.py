@@ -250,3 +250,24 @@ def test_non_default_stft_geometries_match_reference(golden_dir):
     info = {}
     O.reduce_noise(synth_small(), 16000, cfg=O.GateConfig(sr=16000, stationary=True, n_fft=512, chunk_size=12000, padding=1500), info=info)
     assert np.max(np.abs(info["thresh"] - g["thresh_512"])) < 1e-9
+
+
+TG_GEOMETRY_CASES = {
+    "stat_512_400_100_f64": (dict(n_fft=512, win_length=400, hop_length=100), None, np.float64),
+    "nonstat_512_f64": (dict(nonstationary=True, n_fft=512), None, np.float64),
+    "stat_2048_xn_f32": (dict(n_fft=2048, prop_decrease=0.8), (slice(0, 1), slice(0, 6000)), np.float32),
+}
+
+
+def test_torchgate_non_default_geometries_match_reference(golden_dir):
+    """TorchGate with n_fft / win_length / hop_length off the defaults: window centre-padded to n_fft, pad n_fft/2
+    (torch.stft center=True), output (L // hop) * hop (torchgate.py:223-262)."""
+    g = np.load(os.path.join(golden_dir, "torchgate_geometry.npz"))
+    x = synth_torchgate()[:2, :12000]
+    for key, (kw, xn_idx, dt) in TG_GEOMETRY_CASES.items():
+        xn = None if xn_idx is None else x[xn_idx].astype(np.float64)
+        out = TO.torchgate_forward(x.astype(np.float64), 16000, xn=xn, **kw)
+        assert out.shape == g[key].shape, key
+        assert relinf(out, g[key]) < (TG_TOL if dt == np.float64 else 20 * TG_TOL), key
+    assert np.array_equal(TO.hann_window_f32(400), g["window_400"]) or \
+        np.abs(TO.hann_window_f32(400) - g["window_400"]).max() <= 2 ** -23
