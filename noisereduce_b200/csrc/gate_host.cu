@@ -70,15 +70,12 @@ struct b200gate_handle {
     size_t raw_bytes = 0;
     Counters* d_cnt = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> stage_ev;
-    std::vector<cudaEvent_t> pipe_ev;              // 3 per batch (input landed, compute done, output landed)
+    std::vector<cudaEvent_t> stage_ev;             // 4 per batch: analysis start, analysis end, smoothing end, synthesis end
+    std::vector<cudaEvent_t> pipe_ev;              // 4 per batch: input landed, compute done, output landed, seam copied
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined host path
     void* d_slab_in[2] = {nullptr, nullptr};       // caller-dtype slabs
     void* d_slab_out[2] = {nullptr, nullptr};
     size_t slab_in_bytes[2] = {0, 0}, slab_out_bytes[2] = {0, 0};
-    void* d_slab_raw_in[2] = {nullptr, nullptr};   // int16 / float64 host callers: raw-dtype slabs, converted on device
-    void* d_slab_raw_out[2] = {nullptr, nullptr};
-    size_t slab_raw_in_bytes[2] = {0, 0}, slab_raw_out_bytes[2] = {0, 0};             // 4 per batch: k1 start, k1 end(+rowfloor), smooth end, k2 end
     b200gate_stats stats{};
     // debug taps
     long long dbg_chunk = -1, dbg_channel = -1;
@@ -114,6 +111,17 @@ int upload(b200gate_handle* h, T** dptr, const std::vector<T>& v) {
     CK(h, cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return B200GATE_OK;
 }
+
+// one-call device scratch: freed on every return path
+struct Scratch {
+    void* p = nullptr;
+    ~Scratch() { if (p) cudaFree(p); }
+    Scratch() = default;
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return (T*)p; }
+};
 
 int ensure(b200gate_handle* h, void** p, size_t* have, size_t need) {
     if (*have >= need) return B200GATE_OK;
@@ -268,9 +276,10 @@ int noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, c
     if (h->generic) return generic_noise_stats_from_mean(h, d_yn, n, st);
     const int H = h->p.hop_length;
     const int Tn = (int)(n / H) + 1;                     // scipy: (n + 2*(W/2) - W)/H + 1
-    double *d_db = nullptr, *d_res = nullptr;
-    CK(h, cudaMalloc((void**)&d_db, (size_t)Tn * kF * sizeof(double)));
-    CK(h, cudaMalloc((void**)&d_res, 3 * kF * sizeof(double)));
+    Scratch s_db, s_res;
+    CK(h, s_db.alloc((size_t)Tn * kF * sizeof(double)));
+    CK(h, s_res.alloc(3 * kF * sizeof(double)));
+    double *d_db = s_db.as<double>(), *d_res = s_res.as<double>();
     K0Args a{};
     a.yn = d_yn; a.n = n; a.H = H; a.Tn = Tn; a.wa64 = h->d_wa64; a.cs64 = h->d_cs64; a.eps = kEps64; a.db = d_db;
     B200_LAUNCH(k0_stft_db, dim3(Tn), dim3(256), kN * sizeof(double2), st, a);
@@ -280,8 +289,6 @@ int noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, c
     std::vector<double> res(3 * kF);
     CK(h, cudaMemcpyAsync(res.data(), d_res, res.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
-    cudaFree(d_db);
-    cudaFree(d_res);
     h->mean.assign(res.begin(), res.begin() + kF);
     h->sd.assign(res.begin() + kF, res.begin() + 2 * kF);
     h->thr.assign(res.begin() + 2 * kF, res.end());
@@ -343,11 +350,12 @@ int generic_noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long l
     const int H = h->p.hop_length, W = h->p.win_length, N = h->p.n_fft, F = h->F;
     const long long Tn = (n + 2 * (W / 2) - W) / H + 1;
     if (Tn < 1 || Tn > 0x7fffffffLL) return fail(h, B200GATE_ERR_ARG, "noise clip length %lld unusable", n);
-    double2* d_X = nullptr;
-    double *d_db = nullptr, *d_res = nullptr;
-    CK(h, cudaMalloc((void**)&d_X, (size_t)Tn * F * sizeof(double2)));
-    CK(h, cudaMalloc((void**)&d_db, (size_t)Tn * F * sizeof(double)));
-    CK(h, cudaMalloc((void**)&d_res, 3 * (size_t)F * sizeof(double)));
+    Scratch s_X, s_db, s_res;
+    CK(h, s_X.alloc((size_t)Tn * F * sizeof(double2)));
+    CK(h, s_db.alloc((size_t)Tn * F * sizeof(double)));
+    CK(h, s_res.alloc(3 * (size_t)F * sizeof(double)));
+    double2* d_X = s_X.as<double2>();
+    double *d_db = s_db.as<double>(), *d_res = s_res.as<double>();
     Geom g{};
     g.H = H; g.C = 1; g.T = (int)Tn; g.n_chunks = 1; g.n_total = n; g.step = n; g.pad = 0; g.Lp = n;
     g.in_stride = n; g.out_stride = n; g.u0 = 0; g.n_units = 1;
@@ -361,7 +369,6 @@ int generic_noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long l
     std::vector<double> res(3 * (size_t)F);
     CK(h, cudaMemcpyAsync(res.data(), d_res, res.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
-    cudaFree(d_X); cudaFree(d_db); cudaFree(d_res);
     h->mean.assign(res.begin(), res.begin() + F);
     h->sd.assign(res.begin() + F, res.begin() + 2 * F);
     h->thr.assign(res.begin() + 2 * F, res.end());
@@ -383,22 +390,19 @@ int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, 
     const size_t es = dtype_size(dtype);
     const void* src = y;
     long long sstride = stride;
-    void* tmp = nullptr;
+    Scratch tmp;
     if (!is_device) {
-        CK(h, cudaMalloc(&tmp, (size_t)C * n * es));
-        CK(h, cudaMemcpy2DAsync(tmp, (size_t)n * es, y, (size_t)stride * es, (size_t)n * es, (size_t)C,
+        CK(h, tmp.alloc((size_t)C * n * es));
+        CK(h, cudaMemcpy2DAsync(tmp.p, (size_t)n * es, y, (size_t)stride * es, (size_t)n * es, (size_t)C,
                                 cudaMemcpyHostToDevice, st));
-        src = tmp;
+        src = tmp.p;
         sstride = n;
     }
     if (dtype == B200GATE_F32) launch_channel_sum<float, float>(src, C, n, sstride, acc, init, st);
     else if (dtype == B200GATE_I16) launch_channel_sum<short, double>(src, C, n, sstride, acc, init, st);
     else launch_channel_sum<double, double>(src, C, n, sstride, acc, init, st);
     CK(h, cudaGetLastError());
-    if (tmp) {
-        CK(h, cudaStreamSynchronize(st));
-        cudaFree(tmp);
-    }
+    if (tmp.p) CK(h, cudaStreamSynchronize(st));          // the staging copy is freed on return
     return B200GATE_OK;
 }
 
@@ -589,23 +593,20 @@ int b200gate_noise_stats_collapsed(b200gate_handle* h, const void* noise_mean, i
     if (dtype != B200GATE_F32 && dtype != B200GATE_F64) return fail(h, B200GATE_ERR_ARG, "collapsed noise must be f32 or f64");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t es = dtype_size(dtype);
-    void* d_src = nullptr;
-    double* d_yn = nullptr;
-    CK(h, cudaMalloc((void**)&d_yn, (size_t)n * sizeof(double)));
+    Scratch s_src, s_yn;
+    CK(h, s_yn.alloc((size_t)n * sizeof(double)));
+    double* d_yn = s_yn.as<double>();
     const void* src = noise_mean;
     if (!is_device) {
-        CK(h, cudaMalloc(&d_src, (size_t)n * es));
-        CK(h, cudaMemcpyAsync(d_src, noise_mean, (size_t)n * es, cudaMemcpyHostToDevice, st));
-        src = d_src;
+        CK(h, s_src.alloc((size_t)n * es));
+        CK(h, cudaMemcpyAsync(s_src.p, noise_mean, (size_t)n * es, cudaMemcpyHostToDevice, st));
+        src = s_src.p;
     }
     if (dtype == B200GATE_F32)
         { auto kern_ = k0_mean_to_f64<float>; B200_LAUNCH(kern_, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const float*)src, (long long)n, 1LL, d_yn); }
     else
         { auto kern_ = k0_mean_to_f64<double>; B200_LAUNCH(kern_, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const double*)src, (long long)n, 1LL, d_yn); }
-    int rc = noise_stats_from_mean(h, d_yn, n, st);
-    cudaFree(d_yn);
-    if (d_src) cudaFree(d_src);
-    return rc;
+    return noise_stats_from_mean(h, d_yn, n, st);          // synchronises the stream before the scratch is freed
 }
 
 int b200gate_noise_stats(b200gate_handle* h, const void* y_noise, int dtype, int64_t C, int64_t N, int64_t stride,
@@ -615,10 +616,11 @@ int b200gate_noise_stats(b200gate_handle* h, const void* y_noise, int dtype, int
     long long n = N;
     if (h->p.clip_noise && h->p.chunk_size > 0 && n > h->p.chunk_size) n = h->p.chunk_size;   // stationary.py:63-64
     const bool f32 = (dtype == B200GATE_F32);
-    void* d_acc = nullptr;
-    double* d_yn = nullptr;
-    CK(h, cudaMalloc(&d_acc, (size_t)n * (f32 ? 4 : 8)));
-    CK(h, cudaMalloc((void**)&d_yn, (size_t)n * sizeof(double)));
+    Scratch s_acc, s_yn;
+    CK(h, s_acc.alloc((size_t)n * (f32 ? 4 : 8)));
+    CK(h, s_yn.alloc((size_t)n * sizeof(double)));
+    void* d_acc = s_acc.p;
+    double* d_yn = s_yn.as<double>();
     int rc = channel_sum_impl(h, y_noise, dtype, C, n, stride, is_device, d_acc, 1, st);
     if (rc == B200GATE_OK) {
         if (f32)
@@ -627,8 +629,6 @@ int b200gate_noise_stats(b200gate_handle* h, const void* y_noise, int dtype, int
             { auto kern_ = k0_mean_to_f64<double>; B200_LAUNCH(kern_, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const double*)d_acc, n, (long long)C, d_yn); }
         rc = noise_stats_from_mean(h, d_yn, n, st);
     }
-    cudaFree(d_acc);
-    cudaFree(d_yn);
     return rc;
 }
 
@@ -689,12 +689,12 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
     if (Bn <= 0 || Ln <= 0 || dtype != B200GATE_F32) return fail(h, B200GATE_ERR_ARG, "xn must be float32 [Bn][Ln]");
     cudaStream_t st = (cudaStream_t)stream;
     const float* x = (const float*)xn;
-    float* tmp = nullptr;
+    Scratch s_tmp;
     long long xs = stride;
     if (!is_device) {
-        CK(h, cudaMalloc((void**)&tmp, (size_t)Bn * Ln * 4));
-        CK(h, cudaMemcpy2DAsync(tmp, (size_t)Ln * 4, xn, (size_t)stride * 4, (size_t)Ln * 4, (size_t)Bn, cudaMemcpyHostToDevice, st));
-        x = tmp; xs = Ln;
+        CK(h, s_tmp.alloc((size_t)Bn * Ln * 4));
+        CK(h, cudaMemcpy2DAsync(s_tmp.p, (size_t)Ln * 4, xn, (size_t)stride * 4, (size_t)Ln * 4, (size_t)Bn, cudaMemcpyHostToDevice, st));
+        x = s_tmp.as<float>(); xs = Ln;
     }
     Geom g{};
     g.H = h->p.hop_length; g.C = (int)Bn; g.n_total = Ln; g.step = Ln; g.n_chunks = 1; g.pad = 0; g.Lp = Ln;
@@ -702,10 +702,11 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
     if (h->generic) {                                  // general family: float64 statistics of xn's own frames
         const int F = h->F, N = h->p.n_fft;
         if (Bn > 65535) return fail(h, B200GATE_ERR_ARG, "xn has too many rows");
-        double2* gX = nullptr;
-        double* gD = nullptr;
-        CK(h, cudaMalloc((void**)&gX, (size_t)Bn * g.T * F * sizeof(double2)));
-        CK(h, cudaMalloc((void**)&gD, (size_t)Bn * g.T * F * sizeof(double)));
+        Scratch s_gX, s_gD;
+        CK(h, s_gX.alloc((size_t)Bn * g.T * F * sizeof(double2)));
+        CK(h, s_gD.alloc((size_t)Bn * g.T * F * sizeof(double)));
+        double2* gX = s_gX.as<double2>();
+        double* gD = s_gD.as<double>();
         if (h->d_gtthr) cudaFree(h->d_gtthr);
         h->d_gtthr = nullptr;
         CK(h, cudaMalloc((void**)&h->d_gtthr, (size_t)Bn * F * sizeof(double)));
@@ -718,14 +719,13 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
         B200_LAUNCH(gk_tstats, dim3((unsigned)(((long long)Bn * F + 127) / 128)), dim3(128), 0, st, ta);
         CK(h, cudaGetLastError());
         CK(h, cudaStreamSynchronize(st));
-        cudaFree(gX); cudaFree(gD);
-        if (tmp) cudaFree(tmp);
         h->tthr_units = (int)Bn;
         return B200GATE_OK;
     }
-    float *mag = nullptr, *rowmax = nullptr;
-    CK(h, cudaMalloc((void**)&mag, (size_t)Bn * g.T * kFPad * 4));
-    CK(h, cudaMalloc((void**)&rowmax, (size_t)Bn * kFPad * 4));
+    Scratch s_mag, s_rowmax;
+    CK(h, s_mag.alloc((size_t)Bn * g.T * kFPad * 4));
+    CK(h, s_rowmax.alloc((size_t)Bn * kFPad * 4));
+    float *mag = s_mag.as<float>(), *rowmax = s_rowmax.as<float>();
     if (h->d_tthr) cudaFree(h->d_tthr);
     h->d_tthr = nullptr;
     CK(h, cudaMalloc((void**)&h->d_tthr, (size_t)Bn * kFPad * 4));
@@ -737,8 +737,6 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
     B200_LAUNCH(k_tgate_stats, dim3(grid_1d(Bn * kFPad, 128, 1 << 30)), dim3(128), 0, st, ta);
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(st));
-    cudaFree(mag); cudaFree(rowmax);
-    if (tmp) cudaFree(tmp);
     h->tthr_units = (int)Bn;
     return B200GATE_OK;
 }
