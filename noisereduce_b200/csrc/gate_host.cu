@@ -415,9 +415,10 @@ int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, 
     } while (0)
 
 void launch_k1n(const Geom& g, const Tables& tb, const void* x, int kdt, float* mag, const DebugTap& dbg, int resident,
-                cudaStream_t st, float2* zc = nullptr) {
+                cudaStream_t st, float2* zc = nullptr, int z_lo = 0, int z_hi = 0x7fffffff) {
     K1nArgs a1{};
     a1.g = g; a1.tb = tb; a1.x = x; a1.mag = mag; a1.dbg = dbg; a1.zcache = zc; a1.zpairs = (g.T + 1) / 2;
+    a1.z_lo = z_lo; a1.z_hi = z_hi;
     long long want = (long long)resident * kWarps * 4;
     long long run = ((long long)g.n_units * g.T + want - 1) / want;
     run = std::max(8LL, std::min(64LL, run));
@@ -1163,7 +1164,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (torch_sem) {
                 // TorchGate: |X| -> dB, per-row statistics over the row's own frames (or xn's), compare
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, kdt, d_tdb, dbg, resident, st, d_zcache);
+                launch_k1n(g, tb, xb, kdt, d_tdb, dbg, resident, st, d_zcache, tf_lo, tf_hi + 1);
                 TStatArgs ta{};
                 ta.n_units = nu; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64;
                 ta.top_db = (float)p.top_db; ta.n_std = (float)p.n_std_thresh; ta.ddof = p.std_ddof;
@@ -1188,6 +1189,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 K1Args a1{};
                 a1.g = g; a1.tb = tb; a1.x = xb; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
                 a1.zcache = d_zcache; a1.zpairs = zpairs;
+                a1.z_lo = tf_lo; a1.z_hi = tf_hi + 1;           // k2 walks pairs (2j, 2j+1) of frames [tf_lo, tf_hi)
                 {
                     long long want = (long long)h->num_sm * B200_K1_MINBLOCKS * kWarps * 4;
                     long long run = ((long long)nu * g.T + want - 1) / want;
@@ -1313,7 +1315,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
             } else {
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, kdt, d_mag, dbg, resident, st, d_zcache);
+                launch_k1n(g, tb, xb, kdt, d_mag, dbg, resident, st, d_zcache, tf_lo, tf_hi + 1);
                 cudaEventRecord(h->stage_ev[4 * bi + 1], st);
                 if (torch_sem) {
                     TMovArgs ma{};

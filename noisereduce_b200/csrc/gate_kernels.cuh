@@ -227,6 +227,7 @@ struct K1Args {
     float2* zcache;            // optional [n_units][ceil(T/2)][32 slots][32 lanes]: the packed spectrum of every
                                // frame pair, kept so that k2 need not transform the frames a second time
     int zpairs;                // ceil(T/2)
+    int z_lo, z_hi;            // only frames [z_lo, z_hi) are read back by k2 (chunk centre + halo): the rest is not stored
 };
 
 constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats + kWarps * 2 * kFW + 8; }
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const 
             float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb);
             const float S = sqrtf(warp_sum(e));
             warp_fft1024(re, im, tile, s_tw, lane);
-            if (a.zcache) {                                   // warp-uniform
+            if (a.zcache && t >= a.z_lo && t < a.z_hi) {      // warp-uniform
                 float2* zp = a.zcache + ((long long)ul * a.zpairs + (t >> 1)) * 1024 + lane;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) zp[32 * q] = make_float2(re[brev5(q)], im[brev5(q)]);
@@ -886,6 +887,7 @@ struct K1nArgs {
     int run, n_runs;
     float2* zcache;            // optional, as in K1Args
     int zpairs;
+    int z_lo, z_hi;
 };
 
 constexpr int k1n_smem_floats() { return kN + 2 * kN + kWarps * kExchFloats; }
@@ -923,7 +925,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
             float re[32], im[32];
             load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb);
             warp_fft1024(re, im, tile, s_tw, lane);
-            if (a.zcache) {
+            if (a.zcache && t >= a.z_lo && t < a.z_hi) {
                 float2* zp = a.zcache + ((long long)ul * a.zpairs + (t >> 1)) * 1024 + lane;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) zp[32 * q] = make_float2(re[brev5(q)], im[brev5(q)]);
