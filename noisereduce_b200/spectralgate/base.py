@@ -9,6 +9,18 @@ import numpy as np
 from .. import _cabi
 
 
+def _smoothing_filter(n_grad_freq, n_grad_time):
+    """The mask-smoothing filter of base.py:7-29 as an array: outer product of the two triangles
+    (n + 1 - |k|) / (n + 1), |k| <= n, normalised to unit sum.  Kept as the `_smoothing_filter` attribute for
+    callers that inspect it; the kernels apply the same taps as exact integers (n + 1 - |k|)."""
+    def tri(n):
+        k = np.arange(-n, n + 1, dtype=np.float64)
+        return (n + 1 - np.abs(k)) / (n + 1)
+
+    filt = np.outer(tri(n_grad_freq), tri(n_grad_time))
+    return filt / np.sum(filt)
+
+
 class SpectralGate:
     def __init__(
         self,
@@ -85,6 +97,7 @@ class SpectralGate:
         else:
             self.smooth_mask = True
             self._n_grad_freq, self._n_grad_time = n_grad_freq, n_grad_time
+            self._smoothing_filter = _smoothing_filter(n_grad_freq, n_grad_time)
 
     # -- parameters handed to the C ABI ------------------------------------------------------------
     def _gate_params(self):

@@ -45,6 +45,7 @@ class SpectralGateStationary(SpectralGate):
             else:
                 noise = y_noise
 
+        self._noise2d, self._clip_noise = noise, bool(clip_noise_stationary)
         params = self._gate_params()
         params.update(stationary=1, n_std_thresh=float(n_std_thresh_stationary),
                       clip_noise=1 if clip_noise_stationary else 0)
@@ -54,3 +55,10 @@ class SpectralGateStationary(SpectralGate):
         self._gate.noise_stats_host(self._samples_for_device(noise))
         self.mean_freq_noise, self.std_freq_noise = self._gate.noise_mean_std()
         self.noise_thresh = self._gate.noise_threshold()
+
+    @property
+    def y_noise(self):
+        """The collapsed noise clip the reference keeps as an attribute (stationary.py:61-64): channel mean in
+        the input dtype, clipped to chunk_size.  Computed on demand -- the thresholds come from the device."""
+        n = self._noise2d[:, : self._chunk_size] if self._clip_noise else self._noise2d
+        return np.mean(n, axis=0)

@@ -356,3 +356,25 @@ def test_general_geometry_dtypes_blend_and_ranges(lib, monkeypatch):
     cfg = O.GateConfig(sr=SR, stationary=True, n_fft=512, chunk_size=2500, padding=300)
     assert P.relinf(sg.get_traces(2600, 5900), O.reduce_noise(y, SR, cfg=cfg, start_frame=2600, end_frame=5900)) < GEN_TOL
     assert P.relinf(sg.get_traces(100, 2000), O.reduce_noise(y, SR, cfg=cfg, start_frame=100, end_frame=2000)) < GEN_TOL
+
+
+def test_operator_attributes_of_the_reference(lib, monkeypatch):
+    """Attributes user code reads off the reference's operator objects (base.py:54-97, stationary.py:47-81)."""
+    monkeypatch.setattr(_cabi, "_LIB", lib)
+    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
+    y = synth_small(C=2, n=6000)
+    sg = SpectralGateStationary(y=y, sr=SR, y_noise=None, n_std_thresh_stationary=1.5, chunk_size=2500,
+                                clip_noise_stationary=True, padding=400, n_fft=1024, win_length=None, hop_length=None,
+                                time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50, tmp_folder=None,
+                                prop_decrease=1.0, use_tqdm=False, n_jobs=1)
+    assert (sg.n_channels, sg.n_frames, sg.flat, sg.smooth_mask) == (2, 6000, False, True)
+    assert (sg._n_fft, sg._win_length, sg._hop_length) == (1024, 1024, 256)
+    assert sg._smoothing_filter.shape == (2 * 16 + 1, 2 * 3 + 1) and abs(sg._smoothing_filter.sum() - 1) < 1e-12
+    assert np.allclose(sg._smoothing_filter, O.smoothing_filter(16, 3), atol=1e-15)
+    yn = sg.y_noise
+    assert yn.dtype == np.float32 and yn.shape == (2500,) and np.array_equal(yn, np.mean(y[:, :2500], axis=0))
+    info = {}
+    O.reduce_noise(y, SR, cfg=O.GateConfig(sr=SR, stationary=True, chunk_size=2500, padding=400), info=info)
+    assert sg.noise_thresh.shape == sg.mean_freq_noise.shape == sg.std_freq_noise.shape == (513,)
+    assert np.abs(sg.noise_thresh - info["thresh"]).max() < P.THRESH_TOL_DB
+    assert np.abs(sg.mean_freq_noise - info["noise_mean"]).max() < P.THRESH_TOL_DB
