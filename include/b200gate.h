@@ -50,7 +50,7 @@ typedef struct b200gate_params {
     int32_t abi_version;        /* B200GATE_ABI_VERSION                                          */
     int32_t surface;            /* B200GATE_SURFACE_*                                            */
     int32_t stationary;         /* 1: stationary gate, 0: non-stationary gate                    */
-    int32_t n_fft;              /* any power of two in [16, 8192]                                 */
+    int32_t n_fft;              /* [8, 8192] if a power of two, else [8, 4096] (Bluestein)         */
     int32_t win_length;         /* 1 <= win_length <= n_fft                                      */
     int32_t hop_length;         /* 1 <= hop_length <= win_length.  n_fft=1024/win=1024/hop=256 (both gates, both
                                  * surfaces) and 2048/2048/512 (numpy surface, non-stationary) run the tuned FP32 kernels; every other

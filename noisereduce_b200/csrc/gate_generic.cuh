@@ -19,7 +19,8 @@ namespace b200 {
 
 struct GGeom {
     Geom g;                 // chunk table; g.T = (Lp + 2 (W/2) - W) / H + 1
-    int N, logN, W, F;      // n_fft, log2, frame length (win_length; n_fft on the torch surface), N/2 + 1
+    int N, logN, W, F;      // n_fft, log2 (power-of-two n_fft), frame length (win_length; n_fft on the torch surface), N/2 + 1
+    int M, logM;            // n_fft not a power of two: Bluestein length M = 2^logM >= 2 N - 1 (else 0)
     long long out_len;      // > 0: samples written per row (torch surface: (L / H) * H); 0: the chunk centre
 };
 
@@ -27,7 +28,9 @@ struct GTables {
     const double* wa;       // [W] analysis window / sum(w)
     const double* ws;       // [W] synthesis window * sum(w) / N
     const double* w2;       // [W] w^2 (overlap-add norm)
-    const double2* cs;      // [N] (cos, sin)(2 pi m / N)
+    const double2* cs;      // [N] (cos, sin)(2 pi m / N); Bluestein: [M] for the length-M transforms
+    const double2* chirp;   // Bluestein: [N] exp(-i pi n^2 / N)
+    const double2* bbr;     // Bluestein: [M] FFT_M of the conjugate chirp kernel, / M, in bit-reversed order
 };
 
 // In-place radix-2 DIT FFT of s[N] (input already in bit-reversed order); sgn = -1 forward, +1 inverse (unscaled).
@@ -52,6 +55,49 @@ __device__ __forceinline__ int gk_brev(int n, int logN) {
     for (int b = 0; b < logN; ++b) r |= ((n >> b) & 1) << (logN - 1 - b);
     return r;
 }
+// Radix-2 DIF, natural order in -> bit-reversed order out, forward sign.
+__device__ __forceinline__ void gk_fft_dif_smem(double2* s, int N, const double2* __restrict__ cs) {
+    for (int len = N; len >= 2; len >>= 1) {
+        const int half = len >> 1, stride = N / len;
+        for (int i = threadIdx.x; i < N / 2; i += blockDim.x) {
+            const int blk = i / half, o = i - blk * half;
+            const int ia = blk * len + o, ib = ia + half;
+            const double2 w = cs[o * stride];                          // exp(-i th) = (cos, -sin)
+            const double2 x = s[ia], y = s[ib];
+            const double dr = x.x - y.x, di = x.y - y.y;
+            s[ia] = make_double2(x.x + y.x, x.y + y.y);
+            s[ib] = make_double2(dr * w.x + di * w.y, di * w.x - dr * w.y);
+        }
+        __syncthreads();
+    }
+}
+
+// The length-N forward DFT both transforms are built on.
+//   power-of-two N : the caller stores element n at s[gk_slot(n)] (bit-reversed), gk_dft returns X in s[0..N).
+//   any other N    : Bluestein's chirp-z: the caller stores v[n] * chirp[n] at s[n] and zeros up to M; gk_dft leaves
+//                    the circular convolution with the conjugate chirp in s, and X[k] = s[k] * chirp[k].
+// gk_in / gk_out apply the chirp factors so the kernels read the same for both.
+__device__ __forceinline__ int gk_len(const GGeom& gg) { return gg.M ? gg.M : gg.N; }
+__device__ __forceinline__ int gk_slot(const GGeom& gg, int n) { return gg.M ? n : gk_brev(n, gg.logN); }
+__device__ __forceinline__ double2 gk_in(const GGeom& gg, const GTables& tb, int n, double2 v) {
+    if (!gg.M) return v;
+    const double2 c = tb.chirp[n];
+    return make_double2(v.x * c.x - v.y * c.y, v.x * c.y + v.y * c.x);
+}
+__device__ __forceinline__ double2 gk_out(const GGeom& gg, const GTables& tb, int k, double2 v) { return gk_in(gg, tb, k, v); }
+__device__ __forceinline__ void gk_dft(double2* s, const GGeom& gg, const GTables& tb) {
+    if (!gg.M) {
+        gk_fft_smem(s, gg.N, tb.cs, -1.0);
+        return;
+    }
+    gk_fft_dif_smem(s, gg.M, tb.cs);
+    for (int i = threadIdx.x; i < gg.M; i += blockDim.x) {
+        const double2 a = s[i], b = tb.bbr[i];
+        s[i] = make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    }
+    __syncthreads();
+    gk_fft_smem(s, gg.M, tb.cs, 1.0);
+}
 
 // ---- STFT: one CTA per (frame, unit) ---------------------------------------------------------------------
 template <typename T>
@@ -72,15 +118,17 @@ __global__ void __launch_bounds__(256) gk_stft(const GStftArgs<T> a) {
     const long long i1 = chunk * g.step - g.pad;
     const T* xrow = a.x + ch * g.in_stride;
     const long long base = (long long)t * g.H - W / 2;            // boundary='zeros': W/2 zeros either side
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const int len = gk_len(a.gg);
+    for (int n = threadIdx.x; n < len; n += blockDim.x) {
         double v = 0.0;
         if (n < W) v = chunk_sample_f64(xrow, base + n, i1, g.Lp, g.n_total) * a.tb.wa[n];
-        s[gk_brev(n, a.gg.logN)] = make_double2(v, 0.0);          // rfft(n=N): zero-padded at the end
+        const double2 z = n < N ? gk_in(a.gg, a.tb, n, make_double2(v, 0.0)) : make_double2(0.0, 0.0);
+        s[n < N ? gk_slot(a.gg, n) : n] = z;                      // rfft(n=N): zero-padded at the end
     }
     __syncthreads();
-    gk_fft_smem(s, N, a.tb.cs, -1.0);
+    gk_dft(s, a.gg, a.tb);
     double2* Xr = a.X + ((size_t)ul * g.T + t) * F;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) Xr[f] = s[f];
+    for (int f = threadIdx.x; f < F; f += blockDim.x) Xr[f] = gk_out(a.gg, a.tb, f, s[f]);
 }
 
 // ---- stationary decision: one thread per (unit, bin), two sweeps over the frames -----------------------
@@ -202,22 +250,27 @@ __global__ void __launch_bounds__(256) gk_istft(const GIstftArgs a) {
     const int N = a.gg.N, W = a.gg.W, F = a.gg.F;
     const int t = blockIdx.x, ul = blockIdx.y;
     const size_t row = ((size_t)ul * g.T + t) * F;
+    // inverse real DFT as conj(DFT(conj(Y))): only the real part is kept, so the outer conjugate drops out
+    const int len = gk_len(a.gg);
+    if (a.gg.M) {
+        for (int n = N + threadIdx.x; n < len; n += blockDim.x) s[n] = make_double2(0.0, 0.0);
+    }
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
         const double2 x = a.X[row + f];
         const double m = a.M[row + f];
-        double2 y = make_double2(x.x * m, x.y * m);
+        double2 y = make_double2(x.x * m, -x.y * m);                         // conj(X * mask)
         if (ul == a.dbg_ul) {
             a.dbg_spec[(size_t)t * F + f] = make_float2((float)x.x, (float)x.y);
             a.dbg_mask[(size_t)t * F + f] = (float)m;
         }
         if (f == 0 || 2 * f == N) y.y = 0.0;                                 // c2r ignores these imaginary parts
-        s[gk_brev(f, a.gg.logN)] = y;
-        if (f > 0 && 2 * f < N) s[gk_brev(N - f, a.gg.logN)] = make_double2(y.x, -y.y);
+        s[gk_slot(a.gg, f)] = gk_in(a.gg, a.tb, f, y);
+        if (f > 0 && 2 * f < N) s[gk_slot(a.gg, N - f)] = gk_in(a.gg, a.tb, N - f, make_double2(y.x, -y.y));
     }
     __syncthreads();
-    gk_fft_smem(s, N, a.tb.cs, 1.0);
+    gk_dft(s, a.gg, a.tb);
     double* fr = a.frames + ((size_t)ul * g.T + t) * W;
-    for (int n = threadIdx.x; n < W; n += blockDim.x) fr[n] = s[n].x * a.tb.ws[n];     // irfft(...)[:W] * sum(w) * w
+    for (int n = threadIdx.x; n < W; n += blockDim.x) fr[n] = gk_out(a.gg, a.tb, n, s[n]).x * a.tb.ws[n];   // irfft(...)[:W] * sum(w) * w
 }
 
 // ---- overlap-add + crop + cast: one thread per output sample of the chunk centre ------------------------------

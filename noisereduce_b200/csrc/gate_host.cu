@@ -57,6 +57,8 @@ struct b200gate_handle {
     // general-geometry family (gate_generic.cuh)
     bool generic = false;
     int g_logN = 0;
+    int g_M = 0, g_logM = 0;                       // Bluestein length for a non-power-of-two n_fft (0: radix-2 directly)
+    double2 *d_gchirp = nullptr, *d_gbbr = nullptr;
     int g_W = 0;                                   // frame length: win_length (numpy surface) / n_fft (torch surface)
     double* d_gtthr = nullptr;                     // torch surface: thresholds from xn, [tthr_units][F]
     double *d_gwa = nullptr, *d_gws = nullptr, *d_gw2 = nullptr, *d_gthr = nullptr;
@@ -319,12 +321,55 @@ int build_generic_tables(b200gate_handle* h) {
         ws[left + n] = torch_sem ? w[n] / (double)N : w[n] * sw / (double)N;               // irfft's 1/N (* sum(w) in scipy's istft)
         w2[left + n] = w[n] * w[n];
     }
-    std::vector<double2> cs(N);
-    for (int m = 0; m < N; ++m) {
-        const long double th = 2.0L * M_PIl * (long double)m / (long double)N;
+    // transform tables: radix-2 twiddles of n_fft itself, or -- n_fft not a power of two -- Bluestein's chirp-z
+    // through two length-M radix-2 transforms (M = 2^k >= 2 n_fft - 1)
+    const int L = h->g_M ? h->g_M : N;
+    std::vector<double2> cs(L);
+    for (int m = 0; m < L; ++m) {
+        const long double th = 2.0L * M_PIl * (long double)m / (long double)L;
         cs[m] = make_double2((double)cosl(th), (double)sinl(th));
     }
     int rc;
+    if (h->g_M) {
+        const int M = h->g_M, logM = h->g_logM;
+        std::vector<double2> chirp(N);
+        std::vector<long double> br(M, 0.0L), bi(M, 0.0L);
+        for (int n = 0; n < N; ++n) {
+            const long long q = ((long long)n * n) % (2LL * N);                  // n^2 mod 2N keeps the angle small
+            const long double th = M_PIl * (long double)q / (long double)N;
+            chirp[n] = make_double2((double)cosl(th), (double)(-sinl(th)));      // exp(-i pi n^2 / N)
+            br[n] = cosl(th); bi[n] = sinl(th);                                  // conjugate chirp, circular
+            if (n) { br[M - n] = br[n]; bi[M - n] = bi[n]; }
+        }
+        // forward FFT_M of the kernel in long double (iterative radix-2 DIT)
+        for (int i = 0; i < M; ++i) {
+            int r = 0;
+            for (int b = 0; b < logM; ++b) r |= ((i >> b) & 1) << (logM - 1 - b);
+            if (r > i) { std::swap(br[i], br[r]); std::swap(bi[i], bi[r]); }
+        }
+        for (int len = 2; len <= M; len <<= 1) {
+            const int half = len >> 1;
+            for (int blk = 0; blk < M; blk += len)
+                for (int o = 0; o < half; ++o) {
+                    const long double th = -2.0L * M_PIl * (long double)o / (long double)len;
+                    const long double wr = cosl(th), wi = sinl(th);
+                    const long double xr = br[blk + o], xi = bi[blk + o];
+                    const long double yr = br[blk + o + half] * wr - bi[blk + o + half] * wi;
+                    const long double yi = br[blk + o + half] * wi + bi[blk + o + half] * wr;
+                    br[blk + o] = xr + yr; bi[blk + o] = xi + yi;
+                    br[blk + o + half] = xr - yr; bi[blk + o + half] = xi - yi;
+                }
+        }
+        std::vector<double2> bbr(M);
+        for (int i = 0; i < M; ++i) {
+            int r = 0;
+            for (int b = 0; b < logM; ++b) r |= ((i >> b) & 1) << (logM - 1 - b);
+            bbr[i] = make_double2((double)(br[r] / (long double)M), (double)(bi[r] / (long double)M));   // bit-reversed, 1/M folded in
+        }
+        if (h->d_gchirp) { cudaFree(h->d_gchirp); h->d_gchirp = nullptr; }
+        if ((rc = upload(h, &h->d_gchirp, chirp))) return rc;
+        if ((rc = upload(h, &h->d_gbbr, bbr))) return rc;
+    }
     if ((rc = upload(h, &h->d_gwa, wa))) return rc;
     if ((rc = upload(h, &h->d_gws, ws))) return rc;
     if ((rc = upload(h, &h->d_gw2, w2))) return rc;
@@ -334,17 +379,19 @@ int build_generic_tables(b200gate_handle* h) {
 
 GTables generic_tables(const b200gate_handle* h) {
     GTables t{};
-    t.wa = h->d_gwa; t.ws = h->d_gws; t.w2 = h->d_gw2; t.cs = h->d_gcs;
+    t.wa = h->d_gwa; t.ws = h->d_gws; t.w2 = h->d_gw2; t.cs = h->d_gcs; t.chirp = h->d_gchirp; t.bbr = h->d_gbbr;
     return t;
 }
 
 GGeom generic_geom(const b200gate_handle* h, const Geom& g) {
     GGeom gg{};
     gg.g = g; gg.N = h->p.n_fft; gg.logN = h->g_logN; gg.W = h->g_W; gg.F = h->F; gg.out_len = 0;
+    gg.M = h->g_M; gg.logM = h->g_logM;
     return gg;
 }
 
-int generic_threads(int N) { return N >= 512 ? 256 : std::max(32, N / 2); }
+int generic_threads(int N) { return N >= 512 ? 256 : std::max(32, (N / 2 + 31) / 32 * 32); }
+int generic_fft_len(const b200gate_handle* h) { return h->g_M ? h->g_M : h->p.n_fft; }
 
 int generic_noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long long n, cudaStream_t st) {
     const int H = h->p.hop_length, W = h->p.win_length, N = h->p.n_fft, F = h->F;
@@ -361,7 +408,7 @@ int generic_noise_stats_from_mean(b200gate_handle* h, const double* d_yn, long l
     g.in_stride = n; g.out_stride = n; g.u0 = 0; g.n_units = 1;
     GStftArgs<double> a{};
     a.gg = generic_geom(h, g); a.tb = generic_tables(h); a.x = d_yn; a.X = d_X;
-    { auto kern_ = gk_stft<double>; B200_LAUNCH(kern_, dim3((unsigned)Tn, 1), dim3(generic_threads(N)), (size_t)N * sizeof(double2), st, a); }
+    { auto kern_ = gk_stft<double>; B200_LAUNCH(kern_, dim3((unsigned)Tn, 1), dim3(generic_threads(generic_fft_len(h))), (size_t)generic_fft_len(h) * sizeof(double2), st, a); }
     B200_LAUNCH(gk_noise_db, dim3(grid_1d(Tn * F, 256, 1 << 16)), dim3(256), 0, st, (const double2*)d_X, (long long)Tn * F, kEps64, d_db);
     B200_LAUNCH(k0_stats, dim3(F), dim3(256), 0, st, d_db, (int)Tn, F, h->p.top_db, h->p.std_ddof, h->p.n_std_thresh,
                 d_res, d_res + F, d_res + 2 * F);
@@ -451,11 +498,12 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     int logN = 0;
     while ((1 << logN) < p->n_fft) ++logN;
     if (want_generic) {
-        const bool pow2 = p->n_fft >= 16 && p->n_fft <= 8192 && (1 << logN) == p->n_fft;
-        if (!pow2 || p->win_length < 1 || p->win_length > p->n_fft || p->hop_length < 1 || p->hop_length > p->win_length)
+        const bool pow2 = (1 << logN) == p->n_fft;
+        const bool size_ok = p->n_fft >= 8 && p->n_fft <= (pow2 ? 8192 : 4096);
+        if (!size_ok || p->win_length < 1 || p->win_length > p->n_fft || p->hop_length < 1 || p->hop_length > p->win_length)
             return fail(nullptr, B200GATE_ERR_ARG,
                         "unsupported STFT geometry n_fft=%d win_length=%d hop_length=%d (%s gate, %s surface): n_fft must "
-                        "be a power of two in [16, 8192] with 1 <= hop_length <= win_length <= n_fft",
+                        "be in [8, 8192] if a power of two, else in [8, 4096], with 1 <= hop_length <= win_length <= n_fft",
                         p->n_fft, p->win_length, p->hop_length, p->stationary ? "stationary" : "non-stationary",
                         p->surface == B200GATE_SURFACE_NUMPY ? "numpy" : "torch");
     }
@@ -480,6 +528,10 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     if (p->reserve_sms > 0 && p->reserve_sms < h->num_sm) h->num_sm -= p->reserve_sms;   // leave room for NCCL
     h->generic = want_generic;
     h->g_logN = logN;
+    if (want_generic && (1 << logN) != p->n_fft) {              // Bluestein: M = 2^k >= 2 n_fft - 1
+        while ((1 << h->g_logM) < 2 * p->n_fft - 1) ++h->g_logM;
+        h->g_M = 1 << h->g_logM;
+    }
     h->F = want_generic ? p->n_fft / 2 + 1 : (p->n_fft == kN2 ? kF2 : kF);
     int rc = want_generic ? build_generic_tables(h) : build_static_tables(h);
     if (rc == B200GATE_OK) {
@@ -524,7 +576,7 @@ void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
                     h->d_wa64, h->d_cs64, h->d_tthr, h->d_maxabs, h->d_fscratch, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
-                    h->d_dbg_mask, h->d_dbg_bits, h->d_gwa, h->d_gws, h->d_gw2, h->d_gthr, h->d_gcs, h->d_gtthr};
+                    h->d_dbg_mask, h->d_dbg_bits, h->d_gwa, h->d_gws, h->d_gw2, h->d_gthr, h->d_gcs, h->d_gtthr, h->d_gchirp, h->d_gbbr};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -713,7 +765,7 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
         CK(h, cudaMalloc((void**)&h->d_gtthr, (size_t)Bn * F * sizeof(double)));
         GStftArgs<float> sa{};
         sa.gg = generic_geom(h, g); sa.tb = generic_tables(h); sa.x = x; sa.X = gX;
-        { auto kern_ = gk_stft<float>; B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)Bn), dim3(generic_threads(N)), (size_t)N * sizeof(double2), st, sa); }
+        { auto kern_ = gk_stft<float>; B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)Bn), dim3(generic_threads(generic_fft_len(h))), (size_t)generic_fft_len(h) * sizeof(double2), st, sa); }
         GTStatArgs ta{};
         ta.n_units = (int)Bn; ta.T = g.T; ta.F = F; ta.ddof = h->p.std_ddof; ta.eps = kEps64; ta.top_db = h->p.top_db;
         ta.n_std = h->p.n_std_thresh; ta.X = gX; ta.scratch = gD; ta.thr = h->d_gtthr;
@@ -746,7 +798,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                  int64_t out_stride, int is_device, void* stream) {
     if (!h || !in || !out || C <= 0 || N <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
     const bool torch_sem = h->p.surface == B200GATE_SURFACE_TORCH;
-    const int64_t No = torch_sem ? (N / h->p.hop_length) * h->p.hop_length : N;    // torchgate.py:255-262 length
+    // torch.istft(center=True) length: n_fft + hop (T - 1) minus n_fft/2 at both ends (torchgate.py:255-262)
+    const int64_t No = torch_sem ? (N / h->p.hop_length) * h->p.hop_length + (h->p.n_fft & 1) : N;
     // In a range mode only samples [o_lo, o_hi) of a row are addressed, so `out` may be a virtual base
     // (slab - o_lo) over rows as short as the range: the stride check below uses the range length.
     if (in_stride < N || (out_stride < No && (torch_sem || h->range_mode == 0)))
@@ -1057,8 +1110,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             double* gM = (double*)(h->d_ws_buf + goff_M);
             double* gTmp = (double*)(h->d_ws_buf + goff_tmp);
             double* gFr = (double*)(h->d_ws_buf + goff_fr);
-            const int thr_fft = generic_threads(NFFT);
-            const size_t smem_fft = (size_t)NFFT * sizeof(double2);
+            const int thr_fft = generic_threads(generic_fft_len(h));
+            const size_t smem_fft = (size_t)generic_fft_len(h) * sizeof(double2);
             const bool smooth = nf > 0 || nt > 0;
             if (dbg.ul >= 0) CK(h, cudaMemsetAsync(h->d_dbg_bits, 0, (size_t)g.T * FW * 4, st));
             cudaEventRecord(h->stage_ev[4 * bi + 0], st);

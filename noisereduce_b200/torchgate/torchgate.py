@@ -107,7 +107,7 @@ class TorchGate(torch.nn.Module):
         else:
             gate.torch_set_noise(None, 0, 0, 0, True, stream)
         B, L = xf.shape
-        Lo = (L // self.hop_length) * self.hop_length
+        Lo = (L // self.hop_length) * self.hop_length + (self.n_fft & 1)     # torch.istft(center=True) length
         y = torch.empty((B, Lo), dtype=torch.float32, device=x.device)
         gate.run_device(xf.data_ptr(), y.data_ptr(), np.float32, B, L, xf.stride(0), y.stride(0), stream)
         return y.to(dtype=x.dtype)                                              # torchgate.py:264

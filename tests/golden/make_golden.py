@@ -115,6 +115,11 @@ def main():
         stat_2048=nr.reduce_noise(y=y, sr=sr, stationary=True, n_fft=2048, **kw),
         nonstat_1024_hop300_f64=nr.reduce_noise(y=y.astype(np.float64), sr=sr, stationary=False, n_fft=1024,
                                                 hop_length=300, time_constant_s=0.5, **kw),
+        # n_fft not a power of two (Bluestein in the general family)
+        stat_400=nr.reduce_noise(y=y, sr=sr, stationary=True, n_fft=400, **kw),
+        thresh_400=stationary_thresh(y, sr, n_fft=400, **kw),
+        nonstat_441_odd=nr.reduce_noise(y=y, sr=sr, stationary=False, n_fft=441, time_constant_s=0.5, **kw),
+        stat_1000_600_150=nr.reduce_noise(y=y, sr=sr, stationary=True, n_fft=1000, win_length=600, hop_length=150, **kw),
     )
 
     # ---- TorchGate surface (reference on CPU) ------------------------------------------------
@@ -146,6 +151,8 @@ def main():
         stat_512_400_100_f64=TorchGate(sr=sr, n_fft=512, win_length=400, hop_length=100)(xg64).numpy(),
         nonstat_512_f64=TorchGate(sr=sr, nonstationary=True, n_fft=512)(xg64).numpy(),
         stat_2048_xn_f32=TorchGate(sr=sr, n_fft=2048, prop_decrease=0.8)(torch.from_numpy(xg), torch.from_numpy(xg[:1, :6000])).numpy(),
+        stat_400_f64=TorchGate(sr=sr, n_fft=400)(xg64).numpy(),
+        nonstat_441_f64=TorchGate(sr=sr, nonstationary=True, n_fft=441)(xg64).numpy(),
     )
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -237,7 +237,7 @@ def test_python_surface_on_simulator(lib, monkeypatch):
     with pytest.raises(ValueError, match="n_jobs must be 1"):
         nr.reduce_noise(y=y, sr=SR, stationary=True, use_torch=True, n_jobs=2)
     with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
-        nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=1000)             # not a power of two
+        nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=5000, time_mask_smooth_ms=200)   # beyond the Bluestein size limit
     with pytest.raises(_cabi.GateError, match="unsupported STFT geometry"):
         nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=512, win_length=600)
 
@@ -309,6 +309,9 @@ GEN_TOL = 2e-7      # float64 kernels; what is left is the float32 cast of the o
     dict(n_fft=128, win_length=100, hop_length=33),          # hop does not divide the window
     dict(n_fft=2048),                                        # stationary 2048 has no tuned kernel
     dict(n_fft=1024, path_flags=4),                          # tuned geometry forced onto the general family
+    dict(n_fft=400),                                         # not a power of two: Bluestein through M = 1024
+    dict(n_fft=441, win_length=441, hop_length=110),         # odd n_fft: no Nyquist bin
+    dict(n_fft=1000, win_length=600, hop_length=150),
 ], ids=lambda g: "-".join(f"{k}{v}" for k, v in g.items()))
 def test_general_geometry_family(lib, geo):
     """Any power-of-two n_fft, win_length <= n_fft, hop_length <= win_length (gate_generic.cuh): every stage

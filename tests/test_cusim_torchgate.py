@@ -59,7 +59,7 @@ def test_xn_and_dtypes_and_module_contract(lib):
 
 @pytest.mark.parametrize("geo", [
     dict(n_fft=512), dict(n_fft=512, win_length=400, hop_length=100), dict(n_fft=256, win_length=255, hop_length=50),
-    dict(n_fft=2048),
+    dict(n_fft=2048), dict(n_fft=400), dict(n_fft=441),
 ], ids=lambda g: "-".join(f"{k}{v}" for k, v in g.items()))
 def test_non_default_geometry_runs_on_the_general_family(lib, geo):
     """TorchGate off n_fft=1024/hop=256: float64 general family with torch.stft framing (gate_generic.cuh)."""

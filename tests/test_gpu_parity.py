@@ -178,9 +178,11 @@ def test_general_geometry_family_golden_and_stages(lib, golden_dir):
     outputs (tests/golden/synth_geometry.npz), stage taps against the oracle, and the tuned n_fft=1024
     kernels cross-checked against the general family on the same input."""
     import noisereduce_b200 as nr
-    from tests.test_oracle_golden import GEOMETRY_CASES, geometry_input
+    from tests.test_oracle_golden import GEOMETRY_CASES, NON_POW2_KEYS, geometry_input
     g = np.load(os.path.join(golden_dir, "synth_geometry.npz"))
     for key, (kw, dt) in GEOMETRY_CASES.items():
+        if key in NON_POW2_KEYS:
+            continue                                   # test_non_power_of_two_n_fft_golden
         y = geometry_input(dt)
         out = nr.reduce_noise(y=y, sr=16000, chunk_size=12000, padding=1500, **kw)
         assert out.dtype == g[key].dtype and out.shape == g[key].shape, key
@@ -317,12 +319,45 @@ def test_torchgate_general_geometry_golden(lib, golden_dir):
     import torch
     from noisereduce_b200.torchgate import TorchGate
     from tests.synth_host import synth_torchgate
-    from tests.test_oracle_golden import TG_GEOMETRY_CASES
+    from tests.test_oracle_golden import NON_POW2_KEYS, TG_GEOMETRY_CASES
     g = np.load(os.path.join(golden_dir, "torchgate_geometry.npz"))
     x = synth_torchgate()[:2, :12000]
     for key, (kw, xn_idx, dt) in TG_GEOMETRY_CASES.items():
+        if key in NON_POW2_KEYS:
+            continue
         xt = torch.from_numpy(x.astype(dt)).cuda()
         xn = None if xn_idx is None else xt[xn_idx]
         y = TorchGate(sr=16000, **kw)(xt, xn)
         assert y.dtype == xt.dtype and tuple(y.shape) == g[key].shape, key
         assert P.relinf(y.cpu().numpy(), g[key]) < 5e-5, key
+
+
+def test_non_power_of_two_n_fft_golden(lib, golden_dir):
+    """n_fft = 400 / 441 / 1000: Bluestein's chirp-z inside the general family (two length-M radix-2 transforms in
+    shared memory), both surfaces, against reference outputs; stage taps against the oracle."""
+    import torch
+    import noisereduce_b200 as nr
+    from noisereduce_b200.torchgate import TorchGate
+    from tests.synth_host import synth_torchgate
+    from tests.test_oracle_golden import GEOMETRY_CASES, NON_POW2_KEYS, TG_GEOMETRY_CASES, geometry_input
+    g = np.load(os.path.join(golden_dir, "synth_geometry.npz"))
+    for key, (kw, dt) in GEOMETRY_CASES.items():
+        if key in NON_POW2_KEYS:
+            out = nr.reduce_noise(y=geometry_input(dt), sr=16000, chunk_size=12000, padding=1500, **kw)
+            assert out.shape == g[key].shape and P.relinf(out, g[key]) < P.OUT_TOL_TIGHT, key
+    y = synth_small(C=2, n=30000)
+    for geo in (dict(n_fft=400), dict(n_fft=441, win_length=441, hop_length=110), dict(n_fft=3000, win_length=2000, hop_length=500)):
+        ms = 50 if geo["n_fft"] < 3000 else None
+        cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=12000, padding=1500, time_mask_smooth_ms=ms, **geo)
+        r = P.check_stationary(lib, y, cfg, tap_unit=(1, 1))
+        assert r["mask0_mismatch"] == 0 and r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
+        cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=12000, padding=1500, time_constant_s=0.3, time_mask_smooth_ms=ms, **geo)
+        r = P.check_nonstationary(lib, y, cfg, tap_unit=(2, 0))
+        assert r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
+    gt = np.load(os.path.join(golden_dir, "torchgate_geometry.npz"))
+    x = synth_torchgate()[:2, :12000]
+    for key, (kw, xn_idx, dt) in TG_GEOMETRY_CASES.items():
+        if key in NON_POW2_KEYS:
+            xt = torch.from_numpy(x.astype(dt)).cuda()
+            yt = TorchGate(sr=16000, **kw)(xt)
+            assert tuple(yt.shape) == gt[key].shape and P.relinf(yt.cpu().numpy(), gt[key]) < 5e-5, key

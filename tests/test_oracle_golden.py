@@ -224,6 +224,10 @@ GEOMETRY_CASES = {
     "stat_256_255_50_i16": (dict(stationary=True, n_fft=256, win_length=255, hop_length=50, prop_decrease=0.9), np.int16),
     "stat_2048": (dict(stationary=True, n_fft=2048), np.float32),
     "nonstat_1024_hop300_f64": (dict(stationary=False, n_fft=1024, hop_length=300, time_constant_s=0.5), np.float64),
+    # n_fft not a power of two
+    "stat_400": (dict(stationary=True, n_fft=400), np.float32),
+    "nonstat_441_odd": (dict(stationary=False, n_fft=441, time_constant_s=0.5), np.float32),
+    "stat_1000_600_150": (dict(stationary=True, n_fft=1000, win_length=600, hop_length=150), np.float32),
 }
 
 
@@ -252,10 +256,14 @@ def test_non_default_stft_geometries_match_reference(golden_dir):
     assert np.max(np.abs(info["thresh"] - g["thresh_512"])) < 1e-9
 
 
+NON_POW2_KEYS = ("stat_400", "nonstat_441_odd", "stat_1000_600_150", "stat_400_f64", "nonstat_441_f64")
+
 TG_GEOMETRY_CASES = {
     "stat_512_400_100_f64": (dict(n_fft=512, win_length=400, hop_length=100), None, np.float64),
     "nonstat_512_f64": (dict(nonstationary=True, n_fft=512), None, np.float64),
     "stat_2048_xn_f32": (dict(n_fft=2048, prop_decrease=0.8), (slice(0, 1), slice(0, 6000)), np.float32),
+    "stat_400_f64": (dict(n_fft=400), None, np.float64),
+    "nonstat_441_f64": (dict(nonstationary=True, n_fft=441), None, np.float64),
 }
 
 
