@@ -91,6 +91,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 // scipy boundary='zeros' outside [0, Lp)).  j: chunk-local index, i1: global index of j = 0.
 // The kernels read the caller's samples in their own dtype (float32 / int16 / float64) and convert on
 // load -- the device-side form of base.py:140's promotion -- and k2 casts on store (base.py:218-226).
+// u16 halves of a packed word -> float without the (quarter-rate) I2F unit: 2^23 + n as a float bit pattern, minus 2^23
+// (exact for n < 2^23): integer-pipe bit operations and one FADD instead.
+__device__ __forceinline__ float u16lo_to_float(unsigned pk) {
+    return __uint_as_float((pk & 0xFFFFu) | 0x4B000000u) - 8388608.0f;
+}
+__device__ __forceinline__ float u16hi_to_float(unsigned pk) {
+    return __uint_as_float((pk >> 16) | 0x4B000000u) - 8388608.0f;      // (the compiler emits one PRMT / LOP3)
+}
+
 template <typename T>
 __device__ __forceinline__ float ld_sample(const T* p) { return (float)__ldg(p); }
 template <typename T>
@@ -772,8 +781,8 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                                 mb = mkb[FMASK ? q : 0];
                             } else {
                                 const unsigned pk = __float_as_uint(mka[q]);
-                                ma = fmaf((float)(pk & 0xFFFFu), a.pD, eta * s_ef[k]);
-                                mb = fmaf((float)(pk >> 16), a.pD, etb * s_ef[k]);
+                                ma = fmaf(u16lo_to_float(pk), a.pD, eta * s_ef[k]);
+                                mb = fmaf(u16hi_to_float(pk), a.pD, etb * s_ef[k]);
                             }
                             if (!vb) mb = 0.f;
                             const float s = 0.5f * (ma + mb), d = 0.5f * (ma - mb);
