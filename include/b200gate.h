@@ -66,7 +66,9 @@ typedef struct b200gate_params {
     int32_t path_flags;         /* bit 0: use the experimental single-pass kernel (gate_fused.cuh; slower,
                                  * kept for A/B); bit 1: do not cache spectra between analysis and synthesis
                                  * (re-transform instead; saves 8 KB of workspace per frame pair); bit 2: run the
-                                 * float64 general-geometry family even for a tuned geometry (cross-check)  */
+                                 * float64 general-geometry family even for a tuned geometry (cross-check);
+                                 * bit 3 (experimental, unmeasured): k1 streams the next frame pair's float32
+                                 * sample rows into shared memory with cp.async                           */
     int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
     int64_t padding;
     double sr;

@@ -552,6 +552,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
                 cudaFuncSetAttribute(k2_synthesize<8, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
                 cudaFuncSetAttribute(k1n_magnitude<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
             });
+        cudaFuncSetAttribute(k1_analyze<8, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats_staged() * 4);
         cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k1n_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n2_smem_floats() * 4);
         cudaFuncSetAttribute(k2_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k22_smem_floats() * 4);
@@ -1243,6 +1244,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 a1.g = g; a1.tb = tb; a1.x = xb; a1.bits = d_bits; a1.rowmax = d_rowmax; a1.cnt = h->d_cnt; a1.dbg = dbg;
                 a1.zcache = d_zcache; a1.zpairs = zpairs;
                 a1.z_lo = tf_lo; a1.z_hi = tf_hi + 1;           // k2 walks pairs (2j, 2j+1) of frames [tf_lo, tf_hi)
+                a1.stage_rows = ((p.path_flags & 8) && kdt == B200GATE_F32) ? 1 : 0;
                 {
                     long long want = (long long)h->num_sm * B200_K1_MINBLOCKS * kWarps * 4;
                     long long run = ((long long)nu * g.T + want - 1) / want;
@@ -1252,8 +1254,15 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a1.n_runs = (g.T + a1.run - 1) / a1.run;
                 }
                 const long long items1 = (long long)nu * a1.n_runs;
-                B200_WITH_DTYPE(kdt, { auto kern_ = k1_analyze<8, T>;
-                    B200_LAUNCH(kern_, dim3(grid_1d(items1, kWarps, h->num_sm * B200_K1_MINBLOCKS)), dim3(kThreads), k1_smem_floats() * 4, st, a1); });
+                if (a1.stage_rows) {
+                    auto kern_ = k1_analyze<8, float, true>;
+                    B200_LAUNCH(kern_, dim3(grid_1d(items1, kWarps, h->num_sm * B200_K1_MINBLOCKS)), dim3(kThreads),
+                                k1_smem_floats_staged() * 4, st, a1);
+                } else {
+                    B200_WITH_DTYPE(kdt, { auto kern_ = k1_analyze<8, T>;
+                        B200_LAUNCH(kern_, dim3(grid_1d(items1, kWarps, h->num_sm * B200_K1_MINBLOCKS)), dim3(kThreads),
+                                    k1_smem_floats() * 4, st, a1); });
+                }
                 B200_LAUNCH(k_rowfloor, dim3(grid_1d((long long)nu * kFW, 256, 1 << 30)), dim3(256), 0, st, nu,
                             (const unsigned*)d_rowmax, (const float*)h->d_floor4, d_rowflag, h->d_cnt);
             }

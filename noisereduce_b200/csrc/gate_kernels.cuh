@@ -136,19 +136,9 @@ __device__ __forceinline__ bool pair_window_interior(long long base, long long i
 // the two frames as one complex signal.  Returns this lane's contribution to ||frame pair||^2.
 // (Measured and dropped: prefetch.global.L1 of the next pair's rows -- no effect -- and a register pre-load
 //  of them -- more bookkeeping than hidden latency; see profiles/r01_scaling_notes.md.)
-template <int HR, typename T>
-__device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32], const T* __restrict__ xrow,
-                                                 long long base, long long i1, long long Lp, long long n_total,
+template <int HR>
+__device__ __forceinline__ float pack_frame_pair(float (&re)[32], float (&im)[32], const float (&xr)[32 + HR],
                                                  const float* __restrict__ s_wa, int lane, bool vb) {
-    float xr[32 + HR];
-    if (pair_window_interior<HR>(base, i1, Lp, n_total)) {
-        const T* p = xrow + i1 + base + lane;
-#pragma unroll
-        for (int r = 0; r < 32 + HR; ++r) xr[r] = ld_sample(p + 32 * r);
-    } else {                                         // chunk / recording edges: zero-extended samples
-#pragma unroll
-        for (int r = 0; r < 32 + HR; ++r) xr[r] = chunk_sample(xrow, base + lane + 32 * r, i1, Lp, n_total);
-    }
     float e = 0.f;
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
@@ -167,6 +157,22 @@ __device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32
     return e;
 }
 
+template <int HR, typename T>
+__device__ __forceinline__ float load_frame_pair(float (&re)[32], float (&im)[32], const T* __restrict__ xrow,
+                                                 long long base, long long i1, long long Lp, long long n_total,
+                                                 const float* __restrict__ s_wa, int lane, bool vb) {
+    float xr[32 + HR];
+    if (pair_window_interior<HR>(base, i1, Lp, n_total)) {
+        const T* p = xrow + i1 + base + lane;
+#pragma unroll
+        for (int r = 0; r < 32 + HR; ++r) xr[r] = ld_sample(p + 32 * r);
+    } else {                                         // chunk / recording edges: zero-extended samples
+#pragma unroll
+        for (int r = 0; r < 32 + HR; ++r) xr[r] = chunk_sample(xrow, base + lane + 32 * r, i1, Lp, n_total);
+    }
+    return pack_frame_pair<HR>(re, im, xr, s_wa, lane, vb);
+}
+
 // Asynchronous global -> shared copies (LDGSTS): the next frame pair's cached spectrum is requested one whole
 // iteration before it is needed and costs no registers while in flight.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -175,6 +181,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 #else
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+#ifdef B200_CUSIM_BUILD
+    memcpy(smem_dst, gmem_src, 4);
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src));
 #endif
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
@@ -237,11 +251,15 @@ struct K1Args {
                                // frame pair, kept so that k2 need not transform the frames a second time
     int zpairs;                // ceil(T/2)
     int z_lo, z_hi;            // only frames [z_lo, z_hi) are read back by k2 (chunk centre + halo): the rest is not stored
+    int stage_rows;            // set for the k1_analyze<.., true> instantiation (path_flags bit 3, float32 rows): the NEXT
+                               // pair's sample rows stream into shared memory (cp.async) behind the current pair's transform
 };
 
 constexpr int k1_smem_floats() { return kN + 2 * kN + 2 * kFPad + kWarps * kExchFloats + kWarps * 2 * kFW + 8; }
+constexpr int kStageFloats = 32 * (32 + 8);          // one pair's rows: 40 x 32 samples
+constexpr int k1_smem_floats_staged() { return k1_smem_floats() + kWarps * kStageFloats; }
 
-template <int HR, typename T>
+template <int HR, typename T, bool STAGE = false>
 __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const K1Args a) {
     B200_DYN_SMEM(float, smem);
     float* s_wa = smem;
@@ -250,6 +268,7 @@ __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const 
     float* s_gco = s_thr4 + kFPad;
     float* s_tiles = s_gco + kFPad;
     unsigned* s_amb_all = reinterpret_cast<unsigned*>(s_tiles + kWarps * kExchFloats);
+    float* s_stage_all = reinterpret_cast<float*>(s_amb_all + kWarps * 2 * kFW + 8);    // only when a.stage_rows
     for (int i = threadIdx.x; i < kN; i += kThreads) {
         s_wa[i] = a.tb.wa[i];
         s_tw[i] = a.tb.tw[i];
@@ -282,11 +301,45 @@ __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const 
 #pragma unroll
         for (int q = 0; q < kFW; ++q) mx[q] = 0.f;
 
+        // staged rows: request pair t's 40 rows (float32, interior of the chunk and the recording) into this
+        // warp's 5 KB buffer; 16-byte copies when the first row is 16-byte aligned, else one word per lane and row
+        float* sbuf = s_stage_all + warp * kStageFloats;
+        auto stage_rows = [&](int tt) -> bool {
+            if (!STAGE || sizeof(T) != 4) return false;       // compile-time: the default instantiation carries none of this
+            const long long bb = (long long)tt * H - kN / 2;
+            if (!pair_window_interior<HR>(bb, i1, g.Lp, g.n_total)) return false;
+            const char* src = reinterpret_cast<const char*>(xrow + i1 + bb);
+            char* dst = reinterpret_cast<char*>(sbuf);
+            if ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {
+#pragma unroll
+                for (int j = 0; j < (32 + HR) / 4; ++j) cp_async16(dst + (lane + 32 * j) * 16, src + (lane + 32 * j) * 16);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32 + HR; ++r) cp_async4(dst + (lane + 32 * r) * 4, src + (lane + 32 * r) * 4);
+            }
+            cp_async_commit();
+            return true;
+        };
+        bool staged = STAGE && stage_rows(t0);
+
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
             float re[32], im[32];
-            float e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb);
+            float e;
+            if (STAGE && staged) {                            // warp-uniform
+                float xr[32 + HR];
+                cp_async_wait_all();
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 32 + HR; ++r) xr[r] = sbuf[32 * r + lane];
+                __syncwarp();
+                staged = (t + 2 < t1) && stage_rows(t + 2);   // the next pair streams in behind this pair's transform
+                e = pack_frame_pair<HR>(re, im, xr, s_wa, lane, vb);
+            } else {
+                if (STAGE) staged = (t + 2 < t1) && stage_rows(t + 2);
+                e = load_frame_pair<HR>(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa, lane, vb);
+            }
             const float S = sqrtf(warp_sum(e));
             warp_fft1024(re, im, tile, s_tw, lane);
             if (a.zcache && t >= a.z_lo && t < a.z_hi) {      // warp-uniform

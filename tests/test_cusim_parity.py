@@ -381,3 +381,17 @@ def test_operator_attributes_of_the_reference(lib, monkeypatch):
     assert sg.noise_thresh.shape == sg.mean_freq_noise.shape == sg.std_freq_noise.shape == (513,)
     assert np.abs(sg.noise_thresh - info["thresh"]).max() < P.THRESH_TOL_DB
     assert np.abs(sg.mean_freq_noise - info["noise_mean"]).max() < P.THRESH_TOL_DB
+
+
+def test_k1_staged_sample_rows_variant(lib):
+    """path_flags bit 3 (experimental): k1 streams the next pair's float32 rows into shared memory; 16-byte copies
+    when the rows are aligned, word copies otherwise; chunk / recording edges fall back to the direct loads."""
+    y = synth_small(C=2, n=12000)
+    for pad in (600, 601):                              # 601: every row starts off a 16-byte boundary
+        cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=5000, padding=pad)
+        for tap in ((1, 1), (2, 0), (0, 0)):
+            r = P.check_stationary(lib, y, cfg, tap_unit=tap, path_flags=8)
+            _assert_stationary(r)
+    yi = np.round(y * 20000).astype(np.int16)           # not float32: the flag is ignored
+    r = P.check_stationary(lib, yi, O.GateConfig(sr=SR, stationary=True, chunk_size=5000, padding=600), tap_unit=(1, 0), path_flags=8)
+    assert r["mask0_mismatch"] == 0 and r["out_max_lsb"] <= 1
