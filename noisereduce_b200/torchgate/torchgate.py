@@ -97,6 +97,12 @@ class TorchGate(torch.nn.Module):
             raise Exception(f"xn must be bigger than {self.win_length * 2}")
         if _lib is None and not x.is_cuda:
             raise RuntimeError("noisereduce_b200.TorchGate runs on CUDA tensors only (no CPU fallback)")
+        if torch.is_grad_enabled() and x.requires_grad:
+            # The reference builds its masks under no_grad but lets the gradient flow through
+            # stft -> (* mask) -> istft (torchgate.py:223-262).  The CUDA path has no backward kernel: refuse loudly
+            # rather than hand back a tensor that silently stops the gradient.
+            raise NotImplementedError(
+                "noisereduce_b200.TorchGate has no backward pass; call it under torch.no_grad() or on x.detach()")
         gate = self._get_gate(_lib)
         stream = torch.cuda.current_stream().cuda_stream if x.is_cuda else None
         xf = x.detach().to(torch.float32).contiguous()

@@ -55,6 +55,10 @@ def test_xn_and_dtypes_and_module_contract(lib):
         TorchGate(sr=16000, prop_decrease=1.5)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         tg(torch.zeros(1, 4096))                                           # product path: no CPU fallback
+    with pytest.raises(NotImplementedError, match="no backward pass"):
+        tg(torch.from_numpy(x).requires_grad_(True), _lib=lib)             # never a silently detached result
+    with torch.no_grad():
+        assert tg(torch.from_numpy(x).requires_grad_(True), _lib=lib).shape[0] == 2
 
 
 @pytest.mark.parametrize("geo", [
