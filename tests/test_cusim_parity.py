@@ -395,3 +395,41 @@ def test_k1_staged_sample_rows_variant(lib):
     yi = np.round(y * 20000).astype(np.int16)           # not float32: the flag is ignored
     r = P.check_stationary(lib, yi, O.GateConfig(sr=SR, stationary=True, chunk_size=5000, padding=600), tap_unit=(1, 0), path_flags=8)
     assert r["mask0_mismatch"] == 0 and r["out_max_lsb"] <= 1
+
+
+def test_c_abi_argument_and_state_errors(lib):
+    """Error behaviour of the C ABI (negative codes + b200gate_last_error), exercised through the binding."""
+    base = dict(surface=_cabi.SURFACE_NUMPY, stationary=1, n_fft=1024, win_length=1024, hop_length=256, n_grad_freq=5,
+                n_grad_time=3, chunk_size=3000, padding=400, sr=16000.0, prop_decrease=1.0, n_std_thresh=1.5, top_db=80.0,
+                clip_noise=1)
+    for bad, msg in ((dict(prop_decrease=1.5), "prop_decrease"), (dict(padding=-1), "padding"),
+                     (dict(n_grad_freq=100), "smoothing extents"), (dict(hop_length=2000), "unsupported STFT geometry"),
+                     (dict(win_length=0), "unsupported STFT geometry"), (dict(surface=7), "unknown surface"),
+                     (dict(abi_version=99), "ABI version")):
+        with pytest.raises(_cabi.GateError, match=msg):
+            _cabi.Gate(lib=lib, **{**base, **bad})
+    gate = _cabi.Gate(lib=lib, **base)
+    y = synth_small(C=2, n=7000)
+    with pytest.raises(_cabi.GateError, match="noise_stats first"):
+        gate.run_host(y)                                                 # stationary gate without thresholds
+    with pytest.raises(_cabi.GateError, match="expected 513 bins"):
+        gate.set_noise_threshold(np.zeros(100))
+    gate.noise_stats_host(y)
+    out = np.empty_like(y)
+    with pytest.raises(_cabi.GateError, match="row strides too small"):
+        gate._check(lib.dll.b200gate_run(gate._h, y.ctypes.data, out.ctypes.data, 0, 2, 7000, 6000, 7000, 0, None))
+    with pytest.raises(_cabi.GateError, match="bad argument"):
+        gate._check(lib.dll.b200gate_run(gate._h, y.ctypes.data, out.ctypes.data, 9, 2, 7000, 7000, 7000, 0, None))
+    with pytest.raises(_cabi.GateError, match="bad range"):
+        gate.set_range(3, 0, 0)
+    gate.set_range(2, 8000)
+    with pytest.raises(_cabi.GateError, match="beyond the recording"):
+        gate.run_host(y)
+    gate.set_range(1, 0, 1)
+    with pytest.raises(_cabi.GateError, match="shorter than the range"):
+        gate._check(lib.dll.b200gate_run(gate._h, y.ctypes.data, out.ctypes.data, 0, 2, 7000, 7000, 3000, 0, None))
+    gate.set_range(0)
+    assert P.relinf(gate.run_host(y), O.reduce_noise(y, SR, cfg=O.GateConfig(sr=SR, stationary=True, chunk_size=3000, padding=400,
+                                                                               freq_mask_smooth_hz=5 * 16000 / 512 + 1,
+                                                                               time_mask_smooth_ms=3 * 16 + 1))) < P.OUT_TOL
+    gate.close()
