@@ -494,7 +494,10 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
                        p->surface == B200GATE_SURFACE_NUMPY && !p->stationary;
     // everything else the reference accepts on the numpy surface runs on the general-geometry family
     // (path_flags bit 2 forces it for the tuned geometries too: the float64 cross-check of the fast kernels)
-    const bool want_generic = (!geo1k && !geo2k) || (p->path_flags & 4);
+    // ... and so does a smoothing filter beyond what the tuned integer kernels hold (16-bit mask numerators, 64 taps a side)
+    const bool big_filter = p->n_grad_freq > 64 || p->n_grad_time > 64 ||
+                            (long long)(p->n_grad_freq + 1) * (p->n_grad_freq + 1) * (p->n_grad_time + 1) * (p->n_grad_time + 1) > 65535;
+    const bool want_generic = (!geo1k && !geo2k) || (p->path_flags & 4) || big_filter;
     int logN = 0;
     while ((1 << logN) < p->n_fft) ++logN;
     if (want_generic) {
@@ -507,10 +510,8 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
                         p->n_fft, p->win_length, p->hop_length, p->stationary ? "stationary" : "non-stationary",
                         p->surface == B200GATE_SURFACE_NUMPY ? "numpy" : "torch");
     }
-    if (p->n_grad_freq < 0 || p->n_grad_time < 0 || p->n_grad_freq > 64 || p->n_grad_time > 64)
+    if (p->n_grad_freq < 0 || p->n_grad_time < 0 || p->n_grad_freq > 65535 || p->n_grad_time > 65535)
         return fail(nullptr, B200GATE_ERR_ARG, "smoothing extents out of range (%d, %d)", p->n_grad_freq, p->n_grad_time);
-    if ((long long)(p->n_grad_freq + 1) * (p->n_grad_freq + 1) * (p->n_grad_time + 1) * (p->n_grad_time + 1) > 65535)
-        return fail(nullptr, B200GATE_ERR_ARG, "smoothing filter too large for 16-bit mask numerators");
     if (p->padding < 0) return fail(nullptr, B200GATE_ERR_ARG, "padding must be >= 0");
     if (!(p->prop_decrease >= 0.0 && p->prop_decrease <= 1.0))
         return fail(nullptr, B200GATE_ERR_ARG, "prop_decrease must be in [0, 1]");

@@ -403,7 +403,7 @@ def test_c_abi_argument_and_state_errors(lib):
                 n_grad_time=3, chunk_size=3000, padding=400, sr=16000.0, prop_decrease=1.0, n_std_thresh=1.5, top_db=80.0,
                 clip_noise=1)
     for bad, msg in ((dict(prop_decrease=1.5), "prop_decrease"), (dict(padding=-1), "padding"),
-                     (dict(n_grad_freq=100), "smoothing extents"), (dict(hop_length=2000), "unsupported STFT geometry"),
+                     (dict(n_grad_freq=-1), "smoothing extents"), (dict(hop_length=2000), "unsupported STFT geometry"),
                      (dict(win_length=0), "unsupported STFT geometry"), (dict(surface=7), "unknown surface"),
                      (dict(abi_version=99), "ABI version")):
         with pytest.raises(_cabi.GateError, match=msg):
@@ -433,3 +433,15 @@ def test_c_abi_argument_and_state_errors(lib):
                                                                                freq_mask_smooth_hz=5 * 16000 / 512 + 1,
                                                                                time_mask_smooth_ms=3 * 16 + 1))) < P.OUT_TOL
     gate.close()
+
+
+def test_oversized_smoothing_filter_runs_on_the_general_family(lib):
+    """Default STFT geometry but a smoothing filter beyond the tuned integer kernels (more than 64 taps a side / 16-bit
+    numerators): the library routes the call to the float64 general family instead of refusing it."""
+    y = synth_small(C=1, n=30000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=None, padding=2000, time_mask_smooth_ms=1100)      # nt = 68
+    r = P.check_stationary(lib, y, cfg)
+    assert r["mask0_mismatch"] == 0 and r["mask_err"] < GEN_TOL and r["out_relinf"] < GEN_TOL
+    cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=None, padding=2000, freq_mask_smooth_hz=2100, time_constant_s=0.3)  # nf = 67
+    r = P.check_nonstationary(lib, y, cfg)
+    assert r["mask_err"] < GEN_TOL and r["out_relinf"] < GEN_TOL
