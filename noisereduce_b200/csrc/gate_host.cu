@@ -9,6 +9,7 @@
 #include "gate_generic.cuh"
 
 #include <math.h>
+#include <cmath>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -513,8 +514,10 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     if (p->n_grad_freq < 0 || p->n_grad_time < 0 || p->n_grad_freq > 65535 || p->n_grad_time > 65535)
         return fail(nullptr, B200GATE_ERR_ARG, "smoothing extents out of range (%d, %d)", p->n_grad_freq, p->n_grad_time);
     if (p->padding < 0) return fail(nullptr, B200GATE_ERR_ARG, "padding must be >= 0");
-    if (!(p->prop_decrease >= 0.0 && p->prop_decrease <= 1.0))
-        return fail(nullptr, B200GATE_ERR_ARG, "prop_decrease must be in [0, 1]");
+    // TorchGate asserts 0 <= prop_decrease <= 1 (torchgate.py:52); reduce_noise() takes any value (stationary.py:108)
+    if (!std::isfinite(p->prop_decrease) ||
+        (p->surface == B200GATE_SURFACE_TORCH && !(p->prop_decrease >= 0.0 && p->prop_decrease <= 1.0)))
+        return fail(nullptr, B200GATE_ERR_ARG, "prop_decrease must be finite (and in [0, 1] on the torch surface)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

@@ -402,7 +402,8 @@ def test_c_abi_argument_and_state_errors(lib):
     base = dict(surface=_cabi.SURFACE_NUMPY, stationary=1, n_fft=1024, win_length=1024, hop_length=256, n_grad_freq=5,
                 n_grad_time=3, chunk_size=3000, padding=400, sr=16000.0, prop_decrease=1.0, n_std_thresh=1.5, top_db=80.0,
                 clip_noise=1)
-    for bad, msg in ((dict(prop_decrease=1.5), "prop_decrease"), (dict(padding=-1), "padding"),
+    for bad, msg in ((dict(prop_decrease=float("nan")), "prop_decrease"), (dict(padding=-1), "padding"),
+                     (dict(prop_decrease=1.5, surface=_cabi.SURFACE_TORCH, chunk_size=0, padding=0), "prop_decrease"),
                      (dict(n_grad_freq=-1), "smoothing extents"), (dict(hop_length=2000), "unsupported STFT geometry"),
                      (dict(win_length=0), "unsupported STFT geometry"), (dict(surface=7), "unknown surface"),
                      (dict(abi_version=99), "ABI version")):
@@ -445,3 +446,16 @@ def test_oversized_smoothing_filter_runs_on_the_general_family(lib):
     cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=None, padding=2000, freq_mask_smooth_hz=2100, time_constant_s=0.3)  # nf = 67
     r = P.check_nonstationary(lib, y, cfg)
     assert r["mask_err"] < GEN_TOL and r["out_relinf"] < GEN_TOL
+
+
+def test_prop_decrease_outside_unit_interval_like_the_reference(lib):
+    """reduce_noise() does not validate prop_decrease (stationary.py:108-110): over-subtraction (> 1) and
+    negative values are plain arithmetic on the mask."""
+    y = synth_small(C=1, n=7000)
+    for p_ in (1.4, -0.3):
+        cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=3000, padding=400, prop_decrease=p_)
+        r = P.check_stationary(lib, y, cfg, tap_unit=(1, 0))
+        assert r["mask0_mismatch"] == 0 and r["mask_err"] < 2 * P.MASK_TOL and r["out_relinf"] < 2 * P.OUT_TOL_TIGHT
+        cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=3000, padding=400, prop_decrease=p_, time_constant_s=0.3)
+        r = P.check_nonstationary(lib, y, cfg, tap_unit=(1, 0))
+        assert r["mask_err"] < 2 * P.MASK_TOL_NONSTAT and r["out_relinf"] < 10 * P.OUT_TOL_TIGHT
