@@ -98,3 +98,17 @@ def check_nonstationary(lib, y, cfg: O.GateConfig, tap_unit=(0, 0), **extra):
     res["out_relinf"] = relinf(out, ref)
     gate.close()
     return res
+
+
+def reference_test_suite_scenarios(fish_int16, sr, n=None):
+    """The four numpy-path scenarios of the reference's test_reduction.py (:6-56), on its own asset: float64
+    `fish + noise * 10`, stationary with / without a 2-second noise clip, non-stationary, non-stationary in
+    30000-sample chunks.  Yields (name, y, kwargs)."""
+    from tests.synth_host import band_noise
+    data = fish_int16[: n] if n else fish_int16
+    noise = band_noise(len(data), sr) * 10
+    y = data + noise                                           # int16 + float64 -> float64, as in the reference's tests
+    yield "stationary_with_noise_clip", y, dict(stationary=True, y_noise=noise[: sr * 2])
+    yield "stationary_without_noise_clip", y, dict(stationary=True)
+    yield "nonstationary", y, dict(stationary=False)
+    yield "nonstationary_batches", y, dict(stationary=False, chunk_size=30000)

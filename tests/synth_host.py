@@ -23,3 +23,13 @@ def synth_torchgate(B=3, n=24000, sr=16000, seed=11):
     for b in range(B):
         x[b] += 0.2 * np.sin(2 * np.pi * (500 + 300 * b) * t) * ((t % 0.6) < 0.25)
     return x.astype(np.float32)
+
+
+def band_noise(n, sr, lo=2000.0, hi=12000.0, seed=3):
+    """Seeded band-limited noise for the scenarios of the reference's own test file (test_reduction.py builds its input
+    as `fish + band_limited_noise(2000, 12000) * 10`): random phases on the rfft bins inside [lo, hi], unit peak."""
+    rng = np.random.default_rng(seed)
+    f = np.fft.rfftfreq(n, 1.0 / sr)
+    spec = np.where((f >= lo) & (f <= hi), np.exp(2j * np.pi * rng.random(f.shape[0])), 0.0)
+    x = np.fft.irfft(spec, n)
+    return x / np.abs(x).max()

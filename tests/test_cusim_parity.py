@@ -459,3 +459,20 @@ def test_prop_decrease_outside_unit_interval_like_the_reference(lib):
         cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=3000, padding=400, prop_decrease=p_, time_constant_s=0.3)
         r = P.check_nonstationary(lib, y, cfg, tap_unit=(1, 0))
         assert r["mask_err"] < 2 * P.MASK_TOL_NONSTAT and r["out_relinf"] < 10 * P.OUT_TOL_TIGHT
+
+
+def test_reference_test_suite_scenarios_on_simulator(lib, monkeypatch, golden_dir):
+    """test_reduction.py:6-56 of the reference (its four numpy-path scenarios) on the first 50000 samples of its asset."""
+    import os
+    monkeypatch.setattr(_cabi, "_LIB", lib)
+    import noisereduce_b200 as nr
+    f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
+    sr = int(f["sr"])
+    for name, y, kw in P.reference_test_suite_scenarios(f["y"], sr, n=50000):
+        if name == "stationary_without_noise_clip":
+            continue                                   # same kernels as the first scenario; keeps the CPU suite short
+        out = nr.reduce_noise(y=y, sr=sr, **kw)
+        cfg_kw = {k: v for k, v in kw.items() if k != "y_noise"}
+        ref = O.reduce_noise(y, sr, y_noise=kw.get("y_noise"), cfg=O.GateConfig(sr=sr, **cfg_kw))
+        assert out.dtype == np.float64 and out.shape == y.shape, name
+        assert P.relinf(out, ref) < (P.OUT_TOL_TIGHT if kw["stationary"] else 10 * P.OUT_TOL_TIGHT), name

@@ -332,6 +332,19 @@ def test_torchgate_general_geometry_golden(lib, golden_dir):
         assert P.relinf(y.cpu().numpy(), g[key]) < 5e-5, key
 
 
+def test_reference_test_suite_scenarios(lib, golden_dir):
+    """test_reduction.py:6-56 of the reference, through reduce_noise() on the GPU, against the oracle."""
+    import noisereduce_b200 as nr
+    f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
+    sr = int(f["sr"])
+    for name, y, kw in P.reference_test_suite_scenarios(f["y"], sr):
+        out = nr.reduce_noise(y=y, sr=sr, **kw)
+        cfg_kw = {k: v for k, v in kw.items() if k != "y_noise"}
+        ref = O.reduce_noise(y, sr, y_noise=kw.get("y_noise"), cfg=O.GateConfig(sr=sr, **cfg_kw))
+        assert out.dtype == np.float64 and out.shape == y.shape, name
+        assert P.relinf(out, ref) < (P.OUT_TOL_TIGHT if kw["stationary"] else 10 * P.OUT_TOL_TIGHT), name
+
+
 def test_non_power_of_two_n_fft_golden(lib, golden_dir):
     """n_fft = 400 / 441 / 1000: Bluestein's chirp-z inside the general family (two length-M radix-2 transforms in
     shared memory), both surfaces, against reference outputs; stage taps against the oracle."""
