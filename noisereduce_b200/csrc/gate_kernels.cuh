@@ -614,14 +614,22 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPA
     };
     int tau = tau_s;
     for (; tau < t_begin + nt; ++tau) advance(nib(tau), nib(tau - aa), nib(tau - 2 * aa));
-    // steady state: NB output frames per barrier; all bit loads of a batch are issued up front
+    // steady state: NB output frames per barrier.  Of the three rows a frame needs, the two old ones (tau - aa,
+    // tau - 2 aa) were read by this thread a few iterations ago and hit L1; the NEW row comes from L2 / HBM, and its
+    // first use was where the kernel stalled (28 % of all stall samples, profiles/r01_r_sass_mix.txt).  The new rows
+    // of the NEXT batch are therefore requested one whole batch -- two barriers -- before they are needed.
+    auto in_range = [&](int t) -> bool { return active && t >= tau_s && t >= 0 && t < a.T; };
+    unsigned pre[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) pre[j] = (tau + j <= tau_e && in_range(tau + j)) ? __ldg(bp + (long long)(tau + j) * kFW) : 0u;
     for (; tau <= tau_e; tau += NB) {
         unsigned na[NB], nb[NB], nc[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const int tj = tau + j;
             const bool live = tj <= tau_e;
-            na[j] = live ? nib(tj) : 0u;
+            na[j] = (live && in_range(tj)) ? (((pre[j] >> sh) & 0xFu) | fl) : 0u;
+            pre[j] = (tj + NB <= tau_e && in_range(tj + NB)) ? __ldg(bp + (long long)(tj + NB) * kFW) : 0u;
             nb[j] = live ? nib(tj - aa) : 0u;
             nc[j] = live ? nib(tj - 2 * aa) : 0u;
         }
