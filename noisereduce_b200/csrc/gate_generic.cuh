@@ -131,72 +131,122 @@ __global__ void __launch_bounds__(256) gk_stft(const GStftArgs<T> a) {
     for (int f = threadIdx.x; f < F; f += blockDim.x) Xr[f] = gk_out(a.gg, a.tb, f, s[f]);
 }
 
-// ---- stationary decision: one thread per (unit, bin), two sweeps over the frames -----------------------
+// ---- stationary decision ---------------------------------------------------------------------------------
+// (1) gk_db_rowmax: dB of every bin (utils.py:15) and the per-(unit, bin) maximum over the frames -- a CTA covers a
+//     64-bin x 64-frame tile, reduces its column maxima in shared memory and merges them with one atomicMax per
+//     column on an order-preserving integer image of the double;  (2) gk_decide: element-wise floor, compare, blend.
+__device__ __forceinline__ unsigned long long gk_ord(double v) {          // monotone double -> uint64
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double gk_unord(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+struct GDbArgs {
+    int n_units, T, F;
+    double eps;
+    const double2* X;
+    double* M;                     // [n_units][T][F] dB
+    unsigned long long* rowmax;    // [n_units][F] gk_ord(max_t dB); zeroed by the host (0 = below every double)
+};
+__global__ void __launch_bounds__(256) gk_db_rowmax(const GDbArgs a) {
+    __shared__ double red[4][64];
+    const int fx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int f = blockIdx.x * 64 + fx;
+    const int t0 = blockIdx.y * 64;
+    const int ul = blockIdx.z;
+    double mx = -1.0e300;
+    if (f < a.F) {
+        const size_t base = (size_t)ul * a.T * a.F + f;
+        const int t1 = min(t0 + 64, a.T);
+        for (int t = t0 + ty; t < t1; t += 4) {
+            const double2 v = a.X[base + (size_t)t * a.F];
+            const double db = 20.0 * log10(hypot(v.x, v.y) + a.eps);         // utils.py:15
+            a.M[base + (size_t)t * a.F] = db;
+            mx = fmax(mx, db);
+        }
+    }
+    red[ty][fx] = mx;
+    __syncthreads();
+    if (ty == 0 && f < a.F) {
+        mx = fmax(fmax(red[0][fx], red[1][fx]), fmax(red[2][fx], red[3][fx]));
+        atomicMax(a.rowmax + (size_t)ul * a.F + f, gk_ord(mx));
+    }
+}
+
 struct GDecideArgs {
     int n_units, T, F;
-    double eps, top_db, p;
+    double top_db, p;
     const double* thr;      // [thr_units][F] dB (thr_units 1: shared by every unit)
     int thr_units;
-    const double2* X;
-    double* M;              // [n_units][T][F]: dB scratch, then mask0 * p + (1 - p)
+    const unsigned long long* rowmax;
+    double* M;              // dB in, mask0 * p + (1 - p) out
     int dbg_ul, FW;
     unsigned* dbg_bits;     // [T][FW] of the tapped unit (zeroed by the host)
 };
-__global__ void __launch_bounds__(128) gk_decide(const GDecideArgs a) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)a.n_units * a.F) return;
-    const int ul = (int)(i / a.F), f = (int)(i - (long long)ul * a.F);
-    const double2* X = a.X + (size_t)ul * a.T * a.F + f;
-    double* M = a.M + (size_t)ul * a.T * a.F + f;
-    double mx = -1.0e300;
-    for (int t = 0; t < a.T; ++t) {
-        const double2 v = X[(size_t)t * a.F];
-        const double db = 20.0 * log10(hypot(v.x, v.y) + a.eps);            // utils.py:15
-        M[(size_t)t * a.F] = db;
-        mx = fmax(mx, db);
-    }
-    const double fl = mx - a.top_db, th = a.thr[(size_t)(a.thr_units == 1 ? 0 : ul) * a.F + f];
-    for (int t = 0; t < a.T; ++t) {
-        const bool on = fmax(M[(size_t)t * a.F], fl) > th;                   // utils.py:16, stationary.py:99-106
-        M[(size_t)t * a.F] = (on ? 1.0 : 0.0) * a.p + (1.0 - a.p);           // stationary.py:108-110
+__global__ void __launch_bounds__(256) gk_decide(const GDecideArgs a) {
+    const long long total = (long long)a.n_units * a.T * a.F;
+    const long long TF = (long long)a.T * a.F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ul = (int)(i / TF);
+        const long long r = i - (long long)ul * TF;
+        const int t = (int)(r / a.F), f = (int)(r - (long long)t * a.F);
+        const double fl = gk_unord(a.rowmax[(size_t)ul * a.F + f]) - a.top_db;
+        const double th = a.thr[(size_t)(a.thr_units == 1 ? 0 : ul) * a.F + f];
+        const bool on = fmax(a.M[i], fl) > th;                               // utils.py:16, stationary.py:99-106
+        a.M[i] = (on ? 1.0 : 0.0) * a.p + (1.0 - a.p);                       // stationary.py:108-110
         if (ul == a.dbg_ul && on) atomicOr(a.dbg_bits + (size_t)t * a.FW + (f >> 5), 1u << (f & 31));
     }
 }
 
-// ---- non-stationary follower + sigmoid: one thread per (unit, bin) -------------------------------------
+// ---- non-stationary follower + sigmoid ------------------------------------------------------------------------
+// gk_abs (element-wise |X|) -> gk_follow (one thread per (unit, bin): the two one-pole sweeps, 2 FMAs per frame)
+// -> gk_sigmoid (element-wise mask).
+__global__ void __launch_bounds__(256) gk_abs(const double2* __restrict__ X, long long n, double* __restrict__ A) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 v = X[i];
+        A[i] = hypot(v.x, v.y);
+    }
+}
 struct GFollowArgs {
     int n_units, T, F;
-    double b, n_mult, slope, p;
-    int blend;              // 1: no smoothing follows -> apply prop_decrease here (nonstationary.py:82-84)
-    const double2* X;
-    double* M;              // |X|, then the sigmoid mask
-    double* tmp;            // forward sweep
+    double b;
+    const double* A;        // |X|
+    double* S;              // forward sweep, then the smoothed floor
 };
 __global__ void __launch_bounds__(128) gk_follow(const GFollowArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)a.n_units * a.F) return;
     const int ul = (int)(i / a.F), f = (int)(i - (long long)ul * a.F);
     const size_t o = (size_t)ul * a.T * a.F + f;
-    const double2* X = a.X + o;
-    double* M = a.M + o;
-    double* S = a.tmp + o;
+    const double* A = a.A + o;
+    double* S = a.S + o;
     const double b = a.b, c = 1.0 - a.b;
-    double s = 0.0;
+    double s = A[0];                                                         // lfilter_zi steady state: s[-1] = x[0]
     for (int t = 0; t < a.T; ++t) {
-        const double2 v = X[(size_t)t * a.F];
-        const double A = hypot(v.x, v.y);
-        if (t == 0) s = A;                                                   // lfilter_zi steady state: s[-1] = x[0]
-        s = b * A + c * s;
-        M[(size_t)t * a.F] = A;
+        s = b * A[(size_t)t * a.F] + c * s;
         S[(size_t)t * a.F] = s;
     }
     for (int t = a.T - 1; t >= 0; --t) {                                     // same sweep backwards, started at its last value
         s = b * S[(size_t)t * a.F] + c * s;
-        const double A = M[(size_t)t * a.F];
-        const double r = (A - s) / s;                                        // nonstationary.py:70
+        S[(size_t)t * a.F] = s;
+    }
+}
+struct GSigmoidArgs {
+    long long n;
+    double n_mult, slope, p;
+    int blend;              // 1: no smoothing follows -> apply prop_decrease here (nonstationary.py:82-84)
+    const double* S;
+    double* M;              // |X| in, mask out
+};
+__global__ void __launch_bounds__(256) gk_sigmoid(const GSigmoidArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        const double s = a.S[i];
+        const double r = (a.M[i] - s) / s;                                   // nonstationary.py:70
         double m = 1.0 / (1.0 + exp(-(r - a.n_mult) * a.slope));             // utils.py:4-8
         if (a.blend) m = m * a.p + (1.0 - a.p);
-        M[(size_t)t * a.F] = m;
+        a.M[i] = m;
     }
 }
 

@@ -947,7 +947,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t zunit = use_zcache ? (size_t)zpairs * 1024 * sizeof(float2) : 0;
     // general-geometry family: float64 spectrum, mask, scratch and synthesis frames of every unit
     const size_t g_tf = (size_t)g.T * (size_t)h->F, g_tw = (size_t)g.T * (size_t)h->g_W;
-    const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + (size_t)h->F * 8 + 5 * 256;
+    const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + 2 * (size_t)h->F * 8 + 6 * 256;
     const size_t per_unit = generic ? per_unit_generic : (use_fused ? 64 : per_unit_2pass + zunit);   // the fused kernel keeps no per-unit buffers
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 24.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
@@ -988,7 +988,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t goff_tmp = goff_M + al((size_t)ub * g_tf * 8);
     const size_t goff_fr = goff_tmp + al((size_t)ub * g_tf * 8);
     const size_t goff_thr = goff_fr + al((size_t)ub * g_tw * 8);          // torch surface: per-row thresholds
-    const size_t end_generic = goff_thr + al((size_t)ub * h->F * 8);
+    const size_t goff_rmax = goff_thr + al((size_t)ub * h->F * 8);         // per-(unit, bin) dB maxima (top_db floor)
+    const size_t end_generic = goff_rmax + al((size_t)ub * h->F * 8);
     const size_t end_base = generic ? end_generic : use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
     const size_t off_z = al(end_base);
     const size_t end_all = off_z + al((size_t)ub * zunit);
@@ -1125,11 +1126,18 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 sa.gg = gg; sa.tb = gt; sa.x = (const T*)xb; sa.X = gX;
                 auto kern_ = gk_stft<T>;
                 B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)nu), dim3(thr_fft), smem_fft, st, sa); });
+            const int gr_elem = grid_1d((long long)nu * g.T * F, 256, h->num_sm * 16);
             if (stat) {
+                unsigned long long* gRmax = (unsigned long long*)(h->d_ws_buf + goff_rmax);
+                CK(h, cudaMemsetAsync(gRmax, 0, (size_t)nu * F * 8, st));
+                GDbArgs ba{};
+                ba.n_units = nu; ba.T = g.T; ba.F = F; ba.eps = kEps64; ba.X = gX; ba.M = gM; ba.rowmax = gRmax;
+                B200_LAUNCH(gk_db_rowmax, dim3((unsigned)((F + 63) / 64), (unsigned)((g.T + 63) / 64), (unsigned)nu), dim3(256), 0, st, ba);
+                ++launches;
                 GDecideArgs da{};
-                da.n_units = nu; da.T = g.T; da.F = F; da.eps = kEps64; da.top_db = p.top_db; da.p = p.prop_decrease;
-                da.thr = h->d_gthr; da.thr_units = 1;
-                da.X = gX; da.M = gM; da.dbg_ul = dbg.ul; da.FW = FW; da.dbg_bits = h->d_dbg_bits;
+                da.n_units = nu; da.T = g.T; da.F = F; da.top_db = p.top_db; da.p = p.prop_decrease;
+                da.thr = h->d_gthr; da.thr_units = 1; da.rowmax = gRmax;
+                da.M = gM; da.dbg_ul = dbg.ul; da.FW = FW; da.dbg_bits = h->d_dbg_bits;
                 if (torch_sem) {                        // torchgate.py:127-165: per-row statistics (own frames or xn's)
                     if (h->tthr_units > 0) {
                         da.thr = h->tthr_units == 1 ? h->d_gtthr : h->d_gtthr + (size_t)u0 * F;
@@ -1145,7 +1153,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                         da.thr_units = nu;
                     }
                 }
-                B200_LAUNCH(gk_decide, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, da);
+                B200_LAUNCH(gk_decide, dim3(gr_elem), dim3(256), 0, st, da);
             } else if (torch_sem) {                     // torchgate.py:168-198: moving-mean follower
                 GMovArgs ma{};
                 ma.n_units = nu; ma.T = g.T; ma.F = F; ma.n = std::max(1, p.n_movemean); ma.n_thresh = p.thresh_n_mult;
@@ -1153,11 +1161,16 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 B200_LAUNCH(gk_movmean, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, ma);
             } else {
                 const double tfr = p.time_constant_s * p.sr / (double)p.hop_length;       // nonstationary.py:109-114
+                B200_LAUNCH(gk_abs, dim3(gr_elem), dim3(256), 0, st, (const double2*)gX, (long long)nu * g.T * F, gM);
                 GFollowArgs fa{};
                 fa.n_units = nu; fa.T = g.T; fa.F = F; fa.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
-                fa.n_mult = p.thresh_n_mult; fa.slope = p.sigmoid_slope; fa.p = p.prop_decrease; fa.blend = smooth ? 0 : 1;
-                fa.X = gX; fa.M = gM; fa.tmp = gTmp;
+                fa.A = gM; fa.S = gTmp;
                 B200_LAUNCH(gk_follow, dim3((unsigned)(((long long)nu * F + 127) / 128)), dim3(128), 0, st, fa);
+                GSigmoidArgs ga{};
+                ga.n = (long long)nu * g.T * F; ga.n_mult = p.thresh_n_mult; ga.slope = p.sigmoid_slope; ga.p = p.prop_decrease;
+                ga.blend = smooth ? 0 : 1; ga.S = gTmp; ga.M = gM;
+                B200_LAUNCH(gk_sigmoid, dim3(gr_elem), dim3(256), 0, st, ga);
+                launches += 2;
             }
             cudaEventRecord(h->stage_ev[4 * bi + 1], st);
             launches += 2;

@@ -173,52 +173,6 @@ def test_get_traces_subranges_golden(lib, golden_dir):
     assert P.relinf(o[:, 12000:24000], ref[:, 12000:24000]) < P.OUT_TOL
 
 
-def test_general_geometry_family_golden_and_stages(lib, golden_dir):
-    """STFT geometries off the default run on the float64 general family (gate_generic.cuh): reference
-    outputs (tests/golden/synth_geometry.npz), stage taps against the oracle, and the tuned n_fft=1024
-    kernels cross-checked against the general family on the same input."""
-    import noisereduce_b200 as nr
-    from tests.test_oracle_golden import GEOMETRY_CASES, NON_POW2_KEYS, geometry_input
-    g = np.load(os.path.join(golden_dir, "synth_geometry.npz"))
-    for key, (kw, dt) in GEOMETRY_CASES.items():
-        if key in NON_POW2_KEYS:
-            continue                                   # test_non_power_of_two_n_fft_golden
-        y = geometry_input(dt)
-        out = nr.reduce_noise(y=y, sr=16000, chunk_size=12000, padding=1500, **kw)
-        assert out.dtype == g[key].dtype and out.shape == g[key].shape, key
-        if dt == np.int16:
-            assert np.abs(out.astype(np.int64) - g[key].astype(np.int64)).max() <= 1, key
-        else:
-            assert P.relinf(out, g[key]) < P.OUT_TOL_TIGHT, key
-    y = synth_small(C=3, n=40000)
-    for geo in (dict(n_fft=512, win_length=400, hop_length=100), dict(n_fft=4096, win_length=2048, hop_length=512),
-                dict(n_fft=64, win_length=63, hop_length=20)):
-        cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=15000, padding=2000, freq_mask_smooth_hz=None,
-                           time_mask_smooth_ms=None if geo["n_fft"] == 4096 else 50, **geo)
-        if geo["n_fft"] == 64:
-            cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=15000, padding=2000, freq_mask_smooth_hz=1000,
-                               time_mask_smooth_ms=20, **geo)
-        r = P.check_stationary(lib, y, cfg, tap_unit=(1, 2))
-        assert r["mask0_mismatch"] == 0 and r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
-        cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=15000, padding=2000, time_constant_s=0.3,
-                           freq_mask_smooth_hz=cfg.freq_mask_smooth_hz, time_mask_smooth_ms=cfg.time_mask_smooth_ms, **geo)
-        r = P.check_nonstationary(lib, y, cfg, tap_unit=(2, 0))
-        assert r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
-    # the tuned FP32 kernels against the float64 family, same library, same thresholds
-    y = synth_small(C=4, n=200000)
-    a = nr.reduce_noise(y=y, sr=SR, stationary=True, chunk_size=60000, padding=3000)
-    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
-    args = dict(y_noise=None, n_std_thresh_stationary=1.5, clip_noise_stationary=True, n_fft=1024, win_length=None,
-                hop_length=None, time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50,
-                tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1, chunk_size=60000, padding=3000)
-    sg = SpectralGateStationary(y=y, sr=SR, **args)
-    import noisereduce_b200._cabi as cabi
-    gen = cabi.Gate(lib, **{**sg._gate_params(), "stationary": 1, "n_std_thresh": 1.5, "clip_noise": 1, "path_flags": 4})
-    gen.set_noise_threshold(sg.noise_thresh)
-    b = gen.run_host(np.ascontiguousarray(y))
-    assert P.relinf(a, b) < P.OUT_TOL_TIGHT
-
-
 def test_device_pointer_path_and_properties(lib):
     """Device-resident tensors through the same C call; linearity-in-scale and chunk independence."""
     import torch
@@ -314,6 +268,65 @@ def test_batching_slabs_and_config5_geometry(lib):
     assert out.dtype == np.int16 and np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1
 
 
+def test_reference_test_suite_scenarios(lib, golden_dir):
+    """test_reduction.py:6-56 of the reference, through reduce_noise() on the GPU, against the oracle."""
+    import noisereduce_b200 as nr
+    f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
+    sr = int(f["sr"])
+    for name, y, kw in P.reference_test_suite_scenarios(f["y"], sr):
+        out = nr.reduce_noise(y=y, sr=sr, **kw)
+        cfg_kw = {k: v for k, v in kw.items() if k != "y_noise"}
+        ref = O.reduce_noise(y, sr, y_noise=kw.get("y_noise"), cfg=O.GateConfig(sr=sr, **cfg_kw))
+        assert out.dtype == np.float64 and out.shape == y.shape, name
+        assert P.relinf(out, ref) < (P.OUT_TOL_TIGHT if kw["stationary"] else 10 * P.OUT_TOL_TIGHT), name
+
+
+def test_general_geometry_family_golden_and_stages(lib, golden_dir):
+    """STFT geometries off the default run on the float64 general family (gate_generic.cuh): reference
+    outputs (tests/golden/synth_geometry.npz), stage taps against the oracle, and the tuned n_fft=1024
+    kernels cross-checked against the general family on the same input."""
+    import noisereduce_b200 as nr
+    from tests.test_oracle_golden import GEOMETRY_CASES, NON_POW2_KEYS, geometry_input
+    g = np.load(os.path.join(golden_dir, "synth_geometry.npz"))
+    for key, (kw, dt) in GEOMETRY_CASES.items():
+        if key in NON_POW2_KEYS:
+            continue                                   # test_non_power_of_two_n_fft_golden
+        y = geometry_input(dt)
+        out = nr.reduce_noise(y=y, sr=16000, chunk_size=12000, padding=1500, **kw)
+        assert out.dtype == g[key].dtype and out.shape == g[key].shape, key
+        if dt == np.int16:
+            assert np.abs(out.astype(np.int64) - g[key].astype(np.int64)).max() <= 1, key
+        else:
+            assert P.relinf(out, g[key]) < P.OUT_TOL_TIGHT, key
+    y = synth_small(C=3, n=40000)
+    for geo in (dict(n_fft=512, win_length=400, hop_length=100), dict(n_fft=4096, win_length=2048, hop_length=512),
+                dict(n_fft=64, win_length=63, hop_length=20)):
+        cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=15000, padding=2000, freq_mask_smooth_hz=None,
+                           time_mask_smooth_ms=None if geo["n_fft"] == 4096 else 50, **geo)
+        if geo["n_fft"] == 64:
+            cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=15000, padding=2000, freq_mask_smooth_hz=1000,
+                               time_mask_smooth_ms=20, **geo)
+        r = P.check_stationary(lib, y, cfg, tap_unit=(1, 2))
+        assert r["mask0_mismatch"] == 0 and r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
+        cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=15000, padding=2000, time_constant_s=0.3,
+                           freq_mask_smooth_hz=cfg.freq_mask_smooth_hz, time_mask_smooth_ms=cfg.time_mask_smooth_ms, **geo)
+        r = P.check_nonstationary(lib, y, cfg, tap_unit=(2, 0))
+        assert r["spec_err"] < 2e-7 and r["mask_err"] < 2e-7 and r["out_relinf"] < 2e-7, (geo, r)
+    # the tuned FP32 kernels against the float64 family, same library, same thresholds
+    y = synth_small(C=4, n=200000)
+    a = nr.reduce_noise(y=y, sr=SR, stationary=True, chunk_size=60000, padding=3000)
+    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
+    args = dict(y_noise=None, n_std_thresh_stationary=1.5, clip_noise_stationary=True, n_fft=1024, win_length=None,
+                hop_length=None, time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50,
+                tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1, chunk_size=60000, padding=3000)
+    sg = SpectralGateStationary(y=y, sr=SR, **args)
+    import noisereduce_b200._cabi as cabi
+    gen = cabi.Gate(lib, **{**sg._gate_params(), "stationary": 1, "n_std_thresh": 1.5, "clip_noise": 1, "path_flags": 4})
+    gen.set_noise_threshold(sg.noise_thresh)
+    b = gen.run_host(np.ascontiguousarray(y))
+    assert P.relinf(a, b) < P.OUT_TOL_TIGHT
+
+
 def test_torchgate_general_geometry_golden(lib, golden_dir):
     """TorchGate off the default STFT geometry on the GPU (general family, torch framing) against reference outputs."""
     import torch
@@ -330,19 +343,6 @@ def test_torchgate_general_geometry_golden(lib, golden_dir):
         y = TorchGate(sr=16000, **kw)(xt, xn)
         assert y.dtype == xt.dtype and tuple(y.shape) == g[key].shape, key
         assert P.relinf(y.cpu().numpy(), g[key]) < 5e-5, key
-
-
-def test_reference_test_suite_scenarios(lib, golden_dir):
-    """test_reduction.py:6-56 of the reference, through reduce_noise() on the GPU, against the oracle."""
-    import noisereduce_b200 as nr
-    f = np.load(os.path.join(golden_dir, "fish_cfg1.npz"))
-    sr = int(f["sr"])
-    for name, y, kw in P.reference_test_suite_scenarios(f["y"], sr):
-        out = nr.reduce_noise(y=y, sr=sr, **kw)
-        cfg_kw = {k: v for k, v in kw.items() if k != "y_noise"}
-        ref = O.reduce_noise(y, sr, y_noise=kw.get("y_noise"), cfg=O.GateConfig(sr=sr, **cfg_kw))
-        assert out.dtype == np.float64 and out.shape == y.shape, name
-        assert P.relinf(out, ref) < (P.OUT_TOL_TIGHT if kw["stationary"] else 10 * P.OUT_TOL_TIGHT), name
 
 
 def test_non_power_of_two_n_fft_golden(lib, golden_dir):
