@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(os.path.dirname(HERE), "libb200gate.so")
 SOURCES = ["gate_host.cu"]
-DEPS = ["gate_host.cu", "gate_kernels.cuh", "warp_fft.cuh", "cuda_compat.h", os.path.join(ROOT, "include", "b200gate.h")]
+DEPS = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join(ROOT, "include", "b200gate.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

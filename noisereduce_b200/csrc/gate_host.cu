@@ -6,6 +6,7 @@
 #include "../../include/b200gate.h"
 #include "gate_kernels_2k.cuh"
 #include "gate_fused.cuh"
+#include "gate_synth.cuh"
 #include "gate_generic.cuh"
 
 #include <math.h>
@@ -72,7 +73,13 @@ struct b200gate_handle {
     void* d_raw = nullptr;                         // raw-dtype staging
     size_t raw_bytes = 0;
     Counters* d_cnt = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Counters* h_cnt = nullptr;                     // pinned: the run's exactness counters land here (stream-ordered copy)
+    unsigned* h_maxabs = nullptr;                  // pinned (fused path)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
+    // statistics of a device-pointer run are resolved lazily (b200gate_get_stats): the run itself never blocks the host
+    bool stats_pending = false;
+    size_t pend_batches = 0;
+    bool pend_fused = false;
     std::vector<cudaEvent_t> stage_ev;             // 4 per batch: analysis start, analysis end, smoothing end, synthesis end
     std::vector<cudaEvent_t> pipe_ev;              // 4 per batch: input landed, compute done, output landed, seam copied
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined host path
@@ -478,6 +485,33 @@ void launch_k1n(const Geom& g, const Tables& tb, const void* x, int kdt, float* 
                     k1n_smem_floats() * 4, st, a1); });
 }
 
+// Fill h->stats from the last run's stream-ordered counter copy and stage events (blocks until that run is done).
+int resolve_stats(b200gate_handle* h) {
+    if (!h->stats_pending) return B200GATE_OK;
+    h->stats_pending = false;
+    cudaError_t e = cudaEventSynchronize(h->ev_done);
+    if (e != cudaSuccess) return fail(h, B200GATE_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+    const Counters cnt = *h->h_cnt;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.bins_rechecked_fp64 = (int64_t)cnt.rechecked;
+    h->stats.bins_unresolved = (int64_t)cnt.unresolved;
+    h->stats.rowfloor_flags = (int64_t)cnt.floor_flags;
+    h->stats.rowfloor_ambiguous = (int64_t)cnt.floor_ambiguous;
+    h->stats.last_run_ms = ms;
+    for (size_t b = 0; b < h->pend_batches; ++b) {
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        cudaEventElapsedTime(&t1, h->stage_ev[4 * b + 0], h->stage_ev[4 * b + 1]);
+        cudaEventElapsedTime(&t2, h->stage_ev[4 * b + 1], h->stage_ev[4 * b + 2]);
+        cudaEventElapsedTime(&t3, h->stage_ev[4 * b + 2], h->stage_ev[4 * b + 3]);
+        if (h->pend_fused) { h->stats.fused_ms += t1; continue; }
+        h->stats.k1_ms += t1;
+        h->stats.smooth_ms += t2;
+        h->stats.k2_ms += t3;
+    }
+    return B200GATE_OK;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -546,6 +580,9 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     if (rc == B200GATE_OK) {
         cudaEventCreate(&h->ev0);
         cudaEventCreate(&h->ev1);
+        cudaEventCreate(&h->ev_done);
+        cudaMallocHost((void**)&h->h_cnt, sizeof(Counters));
+        cudaMallocHost((void**)&h->h_maxabs, sizeof(unsigned));
         cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
         cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
 #ifndef B200_CUSIM_BUILD
@@ -555,6 +592,9 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
                 cudaFuncSetAttribute(k2_synthesize<8, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
                 cudaFuncSetAttribute(k2_synthesize<8, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
                 cudaFuncSetAttribute(k1n_magnitude<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
+                cudaFuncSetAttribute(k2c_synthesize<8, kMaskU16, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c_smem_bytes<kMaskU16>());
+                cudaFuncSetAttribute(k2c_synthesize<8, kMaskU16Blend, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c_smem_bytes<kMaskU16Blend>());
+                cudaFuncSetAttribute(k2c_synthesize<8, kMaskF32, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c_smem_bytes<kMaskF32>());
             });
         cudaFuncSetAttribute(k1_analyze<8, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats_staged() * 4);
         cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -586,6 +626,9 @@ void b200gate_destroy(b200gate_handle* h) {
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->h_maxabs) cudaFreeHost(h->h_maxabs);
     for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -735,6 +778,8 @@ int b200gate_set_range(b200gate_handle* h, int32_t mode, int64_t a, int64_t b) {
 
 int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out) {
     if (!h || !out) return B200GATE_ERR_ARG;
+    const int rc = resolve_stats(const_cast<b200gate_handle*>(h));
+    if (rc) return rc;
     *out = h->stats;
     return B200GATE_OK;
 }
@@ -938,7 +983,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // single-pass fused kernel: stationary gate, n_fft 1024, filter extents the in-warp smoother handles
     const bool use_fused = stat && native && !generic && !h->force_two_pass && (p.path_flags & 1) &&
                            (2 * p.n_grad_freq + 1 <= 12) && (p.n_grad_time + 1 <= 14);
-    const size_t per_unit_2pass = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)g.T * kFPad * 2 + 64
+    const size_t per_unit_2pass = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)num_unit_stride(g.T) * 2 + 64
                                         : 2 * (size_t)g.T * FP * 4 + 64) +
                                   (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
     // spectrum cache: k1 / k1n keep the packed spectrum of every frame pair so k2 does not re-transform
@@ -976,7 +1021,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t off_rowmax = off_bits + al((size_t)ub * g.T * kFW * 4);
     const size_t off_rowflag = off_rowmax + al((size_t)ub * kFPad * 4);
     const size_t off_num = off_rowflag + al((size_t)ub * kFW * 4);
-    const size_t end_stat = off_num + al((size_t)ub * g.T * kFPad * 2);
+    const size_t end_stat = off_num + al((size_t)ub * num_unit_stride(g.T) * 2);
     const size_t off_m0 = al((size_t)ub * g.T * FP * 4);
     const size_t end_nonstat = off_m0 + al((size_t)ub * g.T * FP * 4);
     // torch surface, stationary: the stationary buffers follow the dB spectrogram
@@ -1303,6 +1348,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     const int groups = (nu + kSmoothUnits - 1) / kSmoothUnits;
                     int n_strips = std::max(1, std::min((tf_hi - tf_lo + 127) / 128, (h->num_sm * 4 + groups - 1) / groups));
                     pa.strip = (tf_hi - tf_lo + n_strips - 1) / n_strips;
+                    pa.strip = (pa.strip + kSmoothBatch - 1) / kSmoothBatch * kSmoothBatch;     // frame pairs (2j, 2j+1) leave together
                     n_strips = (tf_hi - tf_lo + pa.strip - 1) / pa.strip;
                     const dim3 grid(n_strips, groups);
                     if (ntaps <= 12) {
@@ -1333,9 +1379,21 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
                 }
                 const long long items2 = (long long)nu * a2.n_runs;
-                B200_WITH_DTYPE(kdt, { auto kern2 = k2_synthesize<8, false, T>;
-                    B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
-                                k2_smem_floats(g.H) * 4, st, a2); });
+                if (use_zcache) {                  // spectra kept by k1: bulk-staged synthesis (gate_synth.cuh)
+                    if (a2.one_minus_p != 0.f) {
+                        B200_WITH_DTYPE(kdt, { auto kern2 = k2c_synthesize<8, kMaskU16Blend, T>;
+                            B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
+                                        k2c_smem_bytes<kMaskU16Blend>(), st, a2); });
+                    } else {
+                        B200_WITH_DTYPE(kdt, { auto kern2 = k2c_synthesize<8, kMaskU16, T>;
+                            B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
+                                        k2c_smem_bytes<kMaskU16>(), st, a2); });
+                    }
+                } else {
+                    B200_WITH_DTYPE(kdt, { auto kern2 = k2_synthesize<8, false, T>;
+                        B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),
+                                    k2_smem_floats(g.H) * 4, st, a2); });
+                }
                 cudaEventRecord(h->stage_ev[4 * bi + 3], st);
                 launches += 2;
             }
@@ -1438,9 +1496,15 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                         a2.run = (int)run;
                         a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
                     }
-                    B200_WITH_DTYPE(kdt, { auto kern2 = k2_synthesize<8, true, T>;
-                        B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
-                                    k2_smem_floats(g.H) * 4, st, a2); });
+                    if (use_zcache) {
+                        B200_WITH_DTYPE(kdt, { auto kern2 = k2c_synthesize<8, kMaskF32, T>;
+                            B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
+                                        k2c_smem_bytes<kMaskF32>(), st, a2); });
+                    } else {
+                        B200_WITH_DTYPE(kdt, { auto kern2 = k2_synthesize<8, true, T>;
+                            B200_LAUNCH(kern2, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, resident)), dim3(kThreads),
+                                        k2_smem_floats(g.H) * 4, st, a2); });
+                    }
                     cudaEventRecord(h->stage_ev[4 * bi + 3], st);
                     launches += 2;
                 }
@@ -1509,44 +1573,35 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     }
     CK(h, cudaGetLastError());
 
-    // ---- stats (forces completion; device callers pay one sync for exactness bookkeeping) -----------
-    Counters cnt{};
-    unsigned maxabs_bits = 0;
-    CK(h, cudaMemcpyAsync(&cnt, h->d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-    if (use_fused) CK(h, cudaMemcpyAsync(&maxabs_bits, h->d_maxabs, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
+    // ---- stats: the counters travel to pinned host memory behind the kernels; a device-pointer run returns
+    // here with everything enqueued (b200gate_get_stats waits for it), host-pointer runs return finished -----
+    CK(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    if (use_fused) CK(h, cudaMemcpyAsync(h->h_maxabs, h->d_maxabs, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaEventRecord(h->ev_done, st));
+    h->stats.units = U;
+    h->stats.frames = U * g.T;
+    h->stats.kernel_launches = launches;
+    h->stats.fused_path = use_fused ? 1 : 0;
+    h->stats_pending = true;
+    h->pend_batches = n_batches;
+    h->pend_fused = use_fused;
     if (use_fused) {
+        CK(h, cudaStreamSynchronize(st));
         float mx;
-        memcpy(&mx, &maxabs_bits, 4);
+        memcpy(&mx, h->h_maxabs, 4);
         // |X[f,t]| <= max|x| (the scaled analysis window sums to 1): below the smallest floor no row can be lifted
         if (!((double)mx < 0.999 * h->min_floor_amp)) {
             h->force_two_pass = true;
+            h->stats_pending = false;
             const int rc2 = b200gate_run(h, in, out, dtype, C, N, in_stride, out_stride, is_device, stream);
             h->force_two_pass = false;
             h->stats.fused_fallbacks = 1;
             return rc2;
         }
     }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, evk0, evk1);
-    h->stats.units = U;
-    h->stats.frames = U * g.T;
-    h->stats.kernel_launches = launches;
-    h->stats.bins_rechecked_fp64 = (int64_t)cnt.rechecked;
-    h->stats.bins_unresolved = (int64_t)cnt.unresolved;
-    h->stats.rowfloor_flags = (int64_t)cnt.floor_flags;
-    h->stats.rowfloor_ambiguous = (int64_t)cnt.floor_ambiguous;
-    h->stats.last_run_ms = ms;
-    h->stats.fused_path = use_fused ? 1 : 0;
-    for (size_t b = 0; b < n_batches; ++b) {
-        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        cudaEventElapsedTime(&t1, h->stage_ev[4 * b + 0], h->stage_ev[4 * b + 1]);
-        cudaEventElapsedTime(&t2, h->stage_ev[4 * b + 1], h->stage_ev[4 * b + 2]);
-        cudaEventElapsedTime(&t3, h->stage_ev[4 * b + 2], h->stage_ev[4 * b + 3]);
-        if (use_fused) { h->stats.fused_ms += t1; continue; }
-        h->stats.k1_ms += t1;
-        h->stats.smooth_ms += t2;
-        h->stats.k2_ms += t3;
+    if (!direct) {                               // host buffers: the result must be in `out` on return
+        const int rc = resolve_stats(h);
+        if (rc) return rc;
     }
     h->stats.last_h2d_ms = h2d_ms;
     return B200GATE_OK;

@@ -75,6 +75,13 @@ struct DebugTap {
     float* mask;             // [T][F]
 };
 
+// Mask numerators are stored as uint16 pairs, element [pair j][bin k][frame 2j + {0, 1}], so that the synthesis
+// kernel fetches both frames of a pair with one 32-bit access; a unit owns ceil(T/2) pair rows of 2*FPad values.
+__host__ __device__ __forceinline__ long long num_index(int t, int k) {
+    return (((long long)(t >> 1) * kFPad + k) << 1) + (t & 1);
+}
+__host__ __device__ __forceinline__ long long num_unit_stride(int T) { return (long long)((T + 1) / 2) * (2 * kFPad); }
+
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -476,7 +483,7 @@ struct SmoothArgs {
     int TT;                    // output frames per tile
     const unsigned* bits;      // [n_units][T][FW]
     const unsigned* rowflag;   // [n_units][FW]
-    unsigned short* num;       // [n_units][T][FPad]
+    unsigned short* num;       // [n_units][ceil(T/2)][FPad][2]  (num_index)
 };
 
 __host__ __device__ inline int smooth_rows(int TT, int nt) { return TT + 2 * nt + 2 * (nt + 1); }
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(256) k_smooth_generic(const SmoothArgs a) {
             const unsigned short* cr = s_c + tt * cp + f;      // cr[nf + d] = c[f + d]
             for (int d = -nf; d <= nf; ++d) acc += (nf + 1 - (d < 0 ? -d : d)) * (int)cr[nf + d];
         }
-        a.num[((long long)ul * a.T + t0 + tt) * kFPad + f] = (unsigned short)acc;
+        a.num[(long long)ul * num_unit_stride(a.T) + num_index(t0 + tt, f)] = (unsigned short)acc;
     }
 }
 
@@ -592,7 +599,7 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPA
     const int w = i >> 3, sh = (i & 7) * 4;
     const unsigned fl = active ? ((a.rowflag[ul * kFW + w] >> sh) & 0xFu) : 0u;
     const unsigned* bp = a.bits + (long long)(active ? ul : 0) * a.T * kFW + w;
-    unsigned short* outp = a.num + (long long)(active ? ul : 0) * a.T * kFPad + 4 * i;
+    unsigned short* outp = a.num + (long long)(active ? ul : 0) * num_unit_stride(a.T) + 8 * i;
     unsigned taps[NTW];
 #pragma unroll
     for (int m = 0; m < NTW; ++m) taps[m] = a.taps[m];
@@ -643,16 +650,13 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPA
             row[nf + 4 * i + 3] = (unsigned char)(s2 >> 24);
         }
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const int t_out = tau + j - nt;
-            if (tau + j > tau_e) break;
+        // frequency direction; frames (t, t+1) of a pair leave together as one 16-byte store (num_index layout)
+        auto freq_taps = [&](int j, unsigned (&o)[4]) {
             const unsigned char* row = s_raw + ((par * NB + j) * kSmoothUnits + ug) * RB;
             const unsigned* rw = reinterpret_cast<const unsigned*>(row) + i;
             unsigned wv[NTW + 1];
 #pragma unroll
             for (int m = 0; m <= NTW; ++m) wv[m] = rw[m];
-            unsigned o[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 unsigned acc = 0u;
@@ -663,11 +667,21 @@ __global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPA
                 }
                 o[jj] = acc;
             }
+        };
+#pragma unroll
+        for (int j = 0; j < NB; j += 2) {
+            const int t_out = tau + j - nt;                   // even: strips start on even frames, NB is even
+            if (tau + j > tau_e) break;
+            unsigned oa[4], ob[4] = {0u, 0u, 0u, 0u};
+            freq_taps(j, oa);
+            if (tau + j + 1 <= tau_e) freq_taps(j + 1, ob);
             if (active) {
-                uint2 pk;
-                pk.x = o[0] | (o[1] << 16);
-                pk.y = o[2] | (o[3] << 16);
-                *reinterpret_cast<uint2*>(outp + (long long)t_out * kFPad) = pk;
+                uint4 pk;
+                pk.x = oa[0] | (ob[0] << 16);
+                pk.y = oa[1] | (ob[1] << 16);
+                pk.z = oa[2] | (ob[2] << 16);
+                pk.w = oa[3] | (ob[3] << 16);
+                *reinterpret_cast<uint4*>(outp + (long long)(t_out >> 1) * (2 * kFPad)) = pk;
             }
         }
         par ^= 1;
@@ -757,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
         const int t_last = min(he - 1, g.T - 1);
         const T* xrow = static_cast<const T*>(a.x) + (long long)c * g.in_stride;
         T* yrow = static_cast<T*>(a.y) + (long long)c * g.out_stride;
-        const unsigned short* mrow = FMASK ? nullptr : a.num + (long long)ul * g.T * kFPad;
+        const unsigned short* mrow = FMASK ? nullptr : a.num + (long long)ul * num_unit_stride(g.T);
         const float* frow = FMASK ? a.fmask + (long long)ul * g.T * kFPad : nullptr;
 
         float acc[32 + HR];
@@ -789,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                         mka[q] = frow[offA + k];
                         mkb[FMASK ? q : 0] = frow[offB + k];
                     } else {
-                        mka[q] = __uint_as_float((unsigned)mrow[offA + k] | ((unsigned)mrow[offB + k] << 16));
+                        mka[q] = __uint_as_float((unsigned)mrow[num_index(t, k)] | ((unsigned)mrow[num_index(vb ? t + 1 : t, k)] << 16));
                     }
                 }
                 float eta = 0.f, etb = 0.f;
@@ -805,8 +819,8 @@ __global__ void __launch_bounds__(kThreads, 3) k2_synthesize(const K2Args a) {
                             ma = frow[offA + k];
                             mb = frow[offB + k];
                         } else {
-                            ma = fmaf((float)mrow[offA + k], a.pD, eta * s_ef[k]);
-                            mb = fmaf((float)mrow[offB + k], a.pD, etb * s_ef[k]);
+                            ma = fmaf((float)mrow[num_index(t, k)], a.pD, eta * s_ef[k]);
+                            mb = fmaf((float)mrow[num_index(vb ? t + 1 : t, k)], a.pD, etb * s_ef[k]);
                         }
                         a.dbg.mask[(long long)t * kF + k] = ma;
                         if (vb) a.dbg.mask[(long long)(t + 1) * kF + k] = mb;

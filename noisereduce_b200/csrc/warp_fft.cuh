@@ -74,6 +74,14 @@ __device__ __forceinline__ f2 f2_mul_s(f2 a, float c) { f2 r; asm("mul.rn.f32x2 
 __device__ __forceinline__ f2 f2_fma_s(f2 a, float c, f2 acc) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(f2_pack(c, c)), "l"(acc)); return r; }
 #endif
 
+#ifdef B200_CUSIM_BUILD
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { return f2{a.lo * b.lo, a.hi * b.hi}; }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { return f2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+#else
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#endif
+
 #ifndef B200_PACKED_DFT
 #define B200_PACKED_DFT 1
 #endif
@@ -123,9 +131,8 @@ __device__ __forceinline__ void dft32_scalar(float (&re)[32], float (&im)[32]) {
 // Same network, natural slots in -> brev5 slots out.  Stage 1 (partners i, i+16) is scalar; its outputs are
 // paired (slot i, slot i+16) so that stages 2..5, which treat both halves identically (same partner offsets, same
 // twiddles), run on packed registers: 4 x 8 packed butterflies instead of 4 x 16 scalar ones.
-__device__ __forceinline__ void dft32_packed(float (&re)[32], float (&im)[32]) {
+__device__ __forceinline__ void dft32_packed_core(const float (&re)[32], const float (&im)[32], f2 (&Pr)[16], f2 (&Pi)[16]) {
     constexpr float kH = 0.70710678118654752440f;
-    f2 Pr[16], Pi[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const float ar = re[i], ai = im[i], br = re[i + 16], bi = im[i + 16];
@@ -173,6 +180,10 @@ __device__ __forceinline__ void dft32_packed(float (&re)[32], float (&im)[32]) {
             }
         }
     }
+}
+__device__ __forceinline__ void dft32_packed(float (&re)[32], float (&im)[32]) {
+    f2 Pr[16], Pi[16];
+    dft32_packed_core(re, im, Pr, Pi);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         f2_unpack(Pr[i], re[i], re[i + 16]);
@@ -229,6 +240,62 @@ __device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], f
     for (int pass = 0; pass < 2; ++pass) {
         dft32<false>(re, im);                                         // natural slots -> brev slots
         if (pass == 0) twiddle_transpose<true>(re, im, tile, tw, lane);   // brev slots -> natural slots
+    }
+}
+
+
+// ---- variant with the inter-pass twiddles applied on the packed pairs -----------------------------------------
+// After dft32_packed_core, register pair i holds slots (i, i+16) = frequencies (brev5(i), brev5(i) + 1).  The table
+// tw4[i*32 + lane] = (cos_lo, cos_hi, -sin_lo, -sin_hi) of those two frequencies' twiddles exp(-2 pi i lane q / 1024)
+// feeds packed multiplies: 5 packed instructions per pair instead of 8 scalar ones, 16 LDS.128 instead of 31 LDS.64.
+struct __align__(16) tw4_t { f2 wx, wy; };
+
+__device__ __forceinline__ void build_tw4(tw4_t* __restrict__ s_tw4, const float2* __restrict__ tw_global, int tid, int nthreads) {
+    for (int j = tid; j < 16 * 32; j += nthreads) {
+        const int i = j >> 5, l = j & 31;
+        const float2 a = tw_global[brev5(i) * 32 + l], b = tw_global[brev5(i + 16) * 32 + l];
+        tw4_t t;
+        t.wx = f2_pack(a.x, b.x);
+        t.wy = f2_pack(a.y, b.y);
+        s_tw4[j] = t;
+    }
+}
+
+__device__ __forceinline__ void warp_fft1024_ptw(float (&re)[32], float (&im)[32], float* __restrict__ tile,
+                                                 const tw4_t* __restrict__ tw4, int lane) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        f2 Pr[16], Pi[16];
+        dft32_packed_core(re, im, Pr, Pi);
+        if (pass == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const tw4_t w = tw4[i * 32 + lane];
+                const f2 a = Pr[i], b = Pi[i];
+                Pr[i] = f2_sub(f2_mul(a, w.wx), f2_mul(b, w.wy));
+                Pi[i] = f2_fma(a, w.wy, f2_mul(b, w.wx));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            f2_unpack(Pr[i], re[i], re[i + 16]);
+            f2_unpack(Pi[i], im[i], im[i + 16]);
+        }
+        if (pass == 0) {                       // brev slots -> natural slots through the 32x33 tile
+            float* row = tile + lane * 33;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) row[q] = re[brev5(q)];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) re[r] = tile[r * 33 + lane];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) row[q] = im[brev5(q)];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) im[r] = tile[r * 33 + lane];
+            __syncwarp();
+        }
     }
 }
 

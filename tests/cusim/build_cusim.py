@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "noisereduce_b200", "csrc")
 OUTDIR = os.path.join(HERE, "_build")
 OUT = os.path.join(OUTDIR, "libb200gate_cusim.so")
-DEPS = [os.path.join(CSRC, f) for f in ("gate_host.cu", "gate_kernels.cuh", "gate_kernels_2k.cuh", "gate_fused.cuh", "gate_generic.cuh", "warp_fft.cuh", "cuda_compat.h")] + \
+DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + \
        [os.path.join(HERE, f) for f in ("cusim.h", "cusim.cpp")] + [os.path.join(ROOT, "include", "b200gate.h")]
 
 
