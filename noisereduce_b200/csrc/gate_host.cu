@@ -7,6 +7,7 @@
 #include "gate_kernels_2k.cuh"
 #include "gate_fused.cuh"
 #include "gate_synth.cuh"
+#include "gate_dual.cuh"
 #include "gate_generic.cuh"
 
 #include <math.h>
@@ -42,6 +43,8 @@ struct b200gate_handle {
     double *d_thr2_64 = nullptr, *d_wa64 = nullptr;
     double2* d_cs64 = nullptr;
     float ws_to_w = 0.f;
+    float wa_max = 0.f;                            // max of the scaled analysis window (frame-energy bounds, gate_dual.cuh)
+    unsigned* d_need_rowmax = nullptr;             // device flag raised by k1d_analyze when the top_db floor is reachable
     float2 *d_wa2 = nullptr, *d_ws2 = nullptr, *d_w2k = nullptr, *d_invn2 = nullptr;   // n_fft = 2048 family
     double sum_w = 0.0;
     std::vector<float> user_window;                // torch surface: torch.hann_window values
@@ -203,6 +206,8 @@ int build_static_tables(b200gate_handle* h) {
         ws[n] = (float)(w[n] * sw / (double)N);
     }
     h->ws_to_w = (float)((double)N / sw);
+    h->wa_max = 0.f;
+    for (int n = 0; n < N; ++n) h->wa_max = std::max(h->wa_max, (float)fabs(w[n] / sw) * (1.0f + 1e-6f));
     for (int r = 0; r < H; ++r) {
         double s = 0.0;
         for (int i = 0; i * H + r < N; ++i) s += w[i * H + r] * w[i * H + r];
@@ -581,6 +586,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaEventCreate(&h->ev0);
         cudaEventCreate(&h->ev1);
         cudaEventCreate(&h->ev_done);
+        cudaMalloc((void**)&h->d_need_rowmax, sizeof(unsigned));
         cudaMallocHost((void**)&h->h_cnt, sizeof(Counters));
         cudaMallocHost((void**)&h->h_maxabs, sizeof(unsigned));
         cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
@@ -592,6 +598,9 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
                 cudaFuncSetAttribute(k2_synthesize<8, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
                 cudaFuncSetAttribute(k2_synthesize<8, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2_smem_floats(256) * 4);
                 cudaFuncSetAttribute(k1n_magnitude<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n_smem_floats() * 4);
+                cudaFuncSetAttribute(k1d_analyze<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1d_smem_bytes());
+                cudaFuncSetAttribute(k2d_synthesize<8, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2d_smem_bytes());
+                cudaFuncSetAttribute(k2d_synthesize<8, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2d_smem_bytes());
                 cudaFuncSetAttribute(k2c_synthesize<8, kMaskU16, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c_smem_bytes<kMaskU16>());
                 cudaFuncSetAttribute(k2c_synthesize<8, kMaskU16Blend, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c_smem_bytes<kMaskU16Blend>());
                 cudaFuncSetAttribute(k2c_synthesize<8, kMaskF32, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c_smem_bytes<kMaskF32>());
@@ -628,6 +637,7 @@ void b200gate_destroy(b200gate_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->d_need_rowmax) cudaFree(h->d_need_rowmax);
     if (h->h_maxabs) cudaFreeHost(h->h_maxabs);
     for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
@@ -990,6 +1000,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const int zpairs = (g.T + 1) / 2;
     const bool use_zcache = !use_fused && !two_k && !generic && !(p.path_flags & 2);
     const size_t zunit = use_zcache ? (size_t)zpairs * 1024 * sizeof(float2) : 0;
+    // dual kernels (gate_dual.cuh): two channels of a chunk per warp -- stationary numpy-surface gate, even channel count
+    const bool use_dual = use_zcache && stat && !torch_sem && native && (C % 2 == 0) && !(p.path_flags & 16);
     // general-geometry family: float64 spectrum, mask, scratch and synthesis frames of every unit
     const size_t g_tf = (size_t)g.T * (size_t)h->F, g_tw = (size_t)g.T * (size_t)h->g_W;
     const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + 2 * (size_t)h->F * 8 + 6 * 256;
@@ -997,6 +1009,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 24.0 * 1024 * 1024 * 1024;
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
+    if (use_dual) ub = std::max(2LL, ub & ~1LL);             // duals are units (2d, 2d+1) of a batch
     if (generic) ub = std::min(ub, 65535LL);                 // gk_* put the unit on gridDim.y
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
     if (pipelined) {
@@ -1316,6 +1329,30 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a1.n_runs = (g.T + a1.run - 1) / a1.run;
                 }
                 const long long items1 = (long long)nu * a1.n_runs;
+                if (use_dual) {
+                    // two channels per warp (gate_dual.cuh); the single-unit kernel below runs only if a frame could
+                    // reach the top_db floor (device flag), to supply the per-bin row maxima
+                    CK(h, cudaMemsetAsync(h->d_need_rowmax, 0, sizeof(unsigned), st));
+                    K1dArgs ad{};
+                    ad.g = g; ad.tb = tb; ad.x = xb; ad.bits = d_bits; ad.zd = (float4*)d_zcache; ad.zpairs = zpairs;
+                    ad.z_lo = tf_lo; ad.z_hi = tf_hi + 1; ad.cnt = h->d_cnt; ad.need_rowmax = h->d_need_rowmax;
+                    ad.min_floor4 = (float)(4.0 * h->min_floor_amp * h->min_floor_amp);
+                    ad.wa_max = h->wa_max; ad.dbg = dbg;
+                    {
+                        long long want = (long long)h->num_sm * kDualWarpsK1 * 4;
+                        long long run = ((long long)(nu / 2) * g.T + want - 1) / want;
+                        run = std::max(8LL, std::min(64LL, run));
+                        run += run & 1;
+                        ad.run = (int)run;
+                        ad.n_runs = (g.T + ad.run - 1) / ad.run;
+                    }
+                    B200_WITH_DTYPE(kdt, { auto kern_ = k1d_analyze<8, T>;
+                        B200_LAUNCH(kern_, dim3(grid_1d((long long)(nu / 2) * ad.n_runs, kDualWarpsK1, h->num_sm)),
+                                    dim3(kDualWarpsK1 * 32), k1d_smem_bytes(), st, ad); });
+                    ++launches;
+                    a1.guard = h->d_need_rowmax;
+                    a1.zcache = nullptr;
+                }
                 if (a1.stage_rows) {
                     auto kern_ = k1_analyze<8, float, true>;
                     B200_LAUNCH(kern_, dim3(grid_1d(items1, kWarps, h->num_sm * B200_K1_MINBLOCKS)), dim3(kThreads),
@@ -1379,7 +1416,30 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a2.n_runs = (int)((hops + a2.run - 1) / a2.run);
                 }
                 const long long items2 = (long long)nu * a2.n_runs;
-                if (use_zcache) {                  // spectra kept by k1: bulk-staged synthesis (gate_synth.cuh)
+                if (use_dual) {
+                    K2dArgs ad{};
+                    ad.g = g; ad.tb = tb; ad.y = yb; ad.num = d_num; ad.zd = (const float4*)d_zcache; ad.zpairs = zpairs;
+                    ad.pD = a2.pD; ad.one_minus_p = a2.one_minus_p; ad.nt = nt; ad.dbg = dbg;
+                    {
+                        const long long hops = h_hi - h_lo;
+                        long long want = (long long)h->num_sm * kDualWarpsK2 * 4;
+                        long long run = ((long long)(nu / 2) * hops + want - 1) / want;
+                        run = std::max(16LL, std::min(128LL, run));
+                        run += run & 1;
+                        ad.run = (int)run;
+                        ad.n_runs = (int)((hops + ad.run - 1) / ad.run);
+                    }
+                    const long long itemsd = (long long)(nu / 2) * ad.n_runs;
+                    if (ad.one_minus_p != 0.f) {
+                        B200_WITH_DTYPE(kdt, { auto kern2 = k2d_synthesize<8, true, T>;
+                            B200_LAUNCH(kern2, dim3(grid_1d(itemsd, kDualWarpsK2, h->num_sm)), dim3(kDualWarpsK2 * 32),
+                                        k2d_smem_bytes(), st, ad); });
+                    } else {
+                        B200_WITH_DTYPE(kdt, { auto kern2 = k2d_synthesize<8, false, T>;
+                            B200_LAUNCH(kern2, dim3(grid_1d(itemsd, kDualWarpsK2, h->num_sm)), dim3(kDualWarpsK2 * 32),
+                                        k2d_smem_bytes(), st, ad); });
+                    }
+                } else if (use_zcache) {           // spectra kept by k1: bulk-staged synthesis (gate_synth.cuh)
                     if (a2.one_minus_p != 0.f) {
                         B200_WITH_DTYPE(kdt, { auto kern2 = k2c_synthesize<8, kMaskU16Blend, T>;
                             B200_LAUNCH(kern2, dim3(grid_1d(items2, kWarps, resident)), dim3(kThreads),

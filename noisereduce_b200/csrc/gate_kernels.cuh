@@ -258,6 +258,8 @@ struct K1Args {
                                // frame pair, kept so that k2 need not transform the frames a second time
     int zpairs;                // ceil(T/2)
     int z_lo, z_hi;            // only frames [z_lo, z_hi) are read back by k2 (chunk centre + halo): the rest is not stored
+    const unsigned* guard;     // optional device flag: when given and zero the kernel returns at once (it is then the
+                               // row-maximum fallback behind k1d_analyze, gate_dual.cuh)
     int stage_rows;            // set for the k1_analyze<.., true> instantiation (path_flags bit 3, float32 rows): the NEXT
                                // pair's sample rows stream into shared memory (cp.async) behind the current pair's transform
 };
@@ -268,6 +270,7 @@ constexpr int k1_smem_floats_staged() { return k1_smem_floats() + kWarps * kStag
 
 template <int HR, typename T, bool STAGE = false>
 __global__ void __launch_bounds__(kThreads, B200_K1_MINBLOCKS) k1_analyze(const K1Args a) {
+    if (a.guard && *a.guard == 0u) return;
     B200_DYN_SMEM(float, smem);
     float* s_wa = smem;
     float2* s_tw = reinterpret_cast<float2*>(smem + kN);
@@ -1060,19 +1063,24 @@ __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
         for (int t = 0; t < a.T; ++t) M[(long long)t * FP] = 0.f;
         return;
     }
+    // The recurrence state stays in float64 (two FMAs per element: the filter pole 1 - b ~ 0.995 accumulates
+    // rounding over hundreds of frames); the follower ratio, exponential and reciprocal run in float32 (the
+    // float64 exp / divide of the first version made this kernel 3x longer than both FFT kernels together).
     const double b = a.b, omb = 1.0 - a.b;
+    const float n_mult = a.n_mult, slope = a.slope;
     double s = (double)A[0];
 #pragma unroll 8
     for (int t = 0; t < a.T; ++t) {
-        s = b * (double)A[(long long)t * FP] + omb * s;
+        s = fma(b, (double)A[(long long)t * FP], omb * s);
         M[(long long)t * FP] = (float)s;
     }
     s = (double)M[(long long)(a.T - 1) * FP];
 #pragma unroll 8
     for (int t = a.T - 1; t >= 0; --t) {
-        s = b * (double)M[(long long)t * FP] + omb * s;
-        const double r = ((double)A[(long long)t * FP] - s) / s;
-        M[(long long)t * FP] = (float)(1.0 / (1.0 + exp(-(r - (double)a.n_mult) * (double)a.slope)));
+        s = fma(b, (double)M[(long long)t * FP], omb * s);
+        const float num = (float)((double)A[(long long)t * FP] - s);      // |X| - S without float32 cancellation
+        const float r = num / (float)s;
+        M[(long long)t * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
     }
 }
 

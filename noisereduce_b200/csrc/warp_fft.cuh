@@ -299,4 +299,88 @@ __device__ __forceinline__ void warp_fft1024_ptw(float (&re)[32], float (&im)[32
     }
 }
 
+// =============================================================================================================
+// Dual transform: ONE warp runs TWO independent 1024-point FFTs, FFT A in the low half and FFT B in the high half
+// of every 64-bit register pair.  Every floating-point instruction of the butterfly network, the inter-pass
+// twiddles and the exchange is then a packed f32x2 / 64-bit one: the instruction count per transform drops by a
+// third against the single-transform network above (which can pack only stages 2..5), the two dependency chains
+// interleave, and values are born packed (64-bit loads, packed arithmetic), so no pack / unpack moves appear.
+// Constants need no duplication: the packed instructions take a scalar register broadcast to both halves (SASS
+// "FFMA2 R, R.F32x2, R.F32, R.F32"), so the single-transform twiddle table serves; the exchange tile holds 32 x 33
+// 64-bit elements.
+// =============================================================================================================
+constexpr int kExchDual = 32 * 33;              // f2 elements of one warp's dual exchange tile (8448 bytes)
+
+// natural slots in -> frequency q in slot brev5(q)
+__device__ __forceinline__ void dft32_dual(f2 (&re)[32], f2 (&im)[32]) {
+    constexpr float kH = 0.70710678118654752440f;
+#pragma unroll
+    for (int len = 32; len >= 2; len >>= 1) {
+        const int half = len >> 1, step = 32 / len;
+#pragma unroll
+        for (int blk = 0; blk < 32; blk += len) {
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const int ia = blk + i, ib = blk + i + half, m = i * step;
+                const f2 ar = re[ia], ai = im[ia], br = re[ib], bi = im[ib];
+                re[ia] = f2_add(ar, br);
+                im[ia] = f2_add(ai, bi);
+                if (m == 0) {
+                    re[ib] = f2_sub(ar, br);
+                    im[ib] = f2_sub(ai, bi);
+                } else if (m == 8) {                           // * (-i): (di, -dr)
+                    re[ib] = f2_sub(ai, bi);
+                    im[ib] = f2_sub(br, ar);
+                } else if (m == 4) {
+                    const f2 dr = f2_sub(ar, br), di = f2_sub(ai, bi);
+                    re[ib] = f2_mul_s(f2_add(dr, di), kH);
+                    im[ib] = f2_mul_s(f2_sub(di, dr), kH);
+                } else if (m == 12) {
+                    const f2 dr = f2_sub(ar, br), di = f2_sub(ai, bi);
+                    re[ib] = f2_mul_s(f2_sub(di, dr), kH);
+                    im[ib] = f2_mul_s(f2_add(dr, di), -kH);
+                } else {
+                    const f2 dr = f2_sub(ar, br), di = f2_sub(ai, bi);
+                    const float c = cos32(m), s = sin32(m);
+                    re[ib] = f2_fma_s(di, s, f2_mul_s(dr, c));
+                    im[ib] = f2_fma_s(dr, -s, f2_mul_s(di, c));
+                }
+            }
+        }
+    }
+}
+
+// Forward dual FFT: input point lane + 32 r in slot r, output X[lane + 32 q] in slot brev5(q).  One code instance
+// serves both radix-32 passes (2-trip runtime loop), as in warp_fft1024.
+__device__ __forceinline__ void warp_fft1024_dual(f2 (&re)[32], f2 (&im)[32], f2* __restrict__ tile,
+                                                  const float2* __restrict__ tw, int lane) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        dft32_dual(re, im);
+        if (pass == 0) {
+#pragma unroll
+            for (int q = 1; q < 32; ++q) {
+                const int s = brev5(q);
+                const float2 w = tw[q * 32 + lane];
+                const f2 a = re[s], b = im[s];
+                re[s] = f2_sub(f2_mul_s(a, w.x), f2_mul_s(b, w.y));
+                im[s] = f2_fma_s(a, w.y, f2_mul_s(b, w.x));
+            }
+            f2* row = tile + lane * 33;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) row[q] = re[brev5(q)];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) re[r] = tile[r * 33 + lane];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) row[q] = im[brev5(q)];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) im[r] = tile[r * 33 + lane];
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace b200
