@@ -150,6 +150,32 @@ int b200gate_set_range(b200gate_handle* h, int32_t mode, int64_t a, int64_t b);
 
 int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out);
 
+/* ---- multi-GPU (one process per GPU) ---------------------------------------------------
+ * The path's one collective -- the all-gather of the final waveform -- is done with NVLink stores issued by a kernel
+ * into buffers every peer has mapped (cudaIpc / CUDA VMM / torch symmetric memory), not with a library collective:
+ * the interface therefore takes plain device pointers (this rank's buffer and its mappings of the peers' buffers)
+ * instead of the ncclComm_t the survey sketched; NCCL / torch.distributed stays the caller's business (rendezvous,
+ * the chained channel mean of the stationary threshold -- b200gate_channel_sum).
+ *
+ * b200gate_run_sharded: denoise this rank's [C_local][N] channels (device pointers) group by group into rows
+ * [rank*C_local, (rank+1)*C_local) of `gathered_local` ([world*C_local][N], this rank's copy of the result) on
+ * `compute_stream`, and push every finished group into the same rows of each peer's copy on `comm_stream` while
+ * the next group is computed; a device-side barrier over the flag arrays (world uint32 each, zero-initialised,
+ * `epoch` strictly increasing per call) ends the step.  On return everything is enqueued; after `compute_stream`
+ * reaches this point `gathered_local` holds every rank's rows.  gathered_peers[r] / flags_peers[r] are this rank's
+ * mappings of rank r's buffers (entry [rank] is ignored / the local array).  push_ctas <= 0 picks a default. */
+int b200gate_run_sharded(b200gate_handle* h, const void* in_local, int dtype, int64_t C_local, int64_t N,
+                         int64_t in_stride, void* gathered_local, void* const* gathered_peers, void* flags_local,
+                         void* const* flags_peers, uint32_t epoch, int32_t rank, int32_t world, int32_t groups,
+                         int32_t push_ctas, void* compute_stream, void* comm_stream);
+/* The two building blocks, for callers with their own schedule (e.g. the slab ring of config 5): copy `rows` rows of
+ * `row_bytes` bytes (16-byte multiples, 16-byte aligned) from local memory into n_peers mapped buffers; and the
+ * epoch barrier described above. */
+int b200gate_peer_push(const void* src, void* const* peer_dst, int32_t n_peers, int64_t rows, int64_t row_bytes,
+                       int64_t src_stride_bytes, int64_t dst_stride_bytes, int32_t n_ctas, void* cuda_stream);
+int b200gate_peer_barrier(void* local_flags, void* const* peer_flags, int32_t rank, int32_t world, uint32_t epoch,
+                          void* cuda_stream);
+
 /* ---- parity-test taps (tests/ only; read back stage outputs of the last run) ---------------- */
 /* Select the (chunk, channel) unit whose stages the next run keeps.  chunk < 0 disables. */
 int b200gate_debug_select_unit(b200gate_handle* h, int64_t chunk, int64_t channel);

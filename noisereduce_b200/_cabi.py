@@ -27,6 +27,7 @@ EXPORTS = [
     "b200gate_torch_set_noise",
     "b200gate_run", "b200gate_set_range", "b200gate_get_stats", "b200gate_debug_select_unit", "b200gate_debug_dims",
     "b200gate_debug_read_bits", "b200gate_debug_read_mask", "b200gate_debug_read_spec",
+    "b200gate_run_sharded", "b200gate_peer_push", "b200gate_peer_barrier",
 ]
 
 
@@ -99,6 +100,24 @@ class GateLibrary:
         d.b200gate_debug_read_bits.argtypes = [vp, vp]
         d.b200gate_debug_read_mask.argtypes = [vp, vp]
         d.b200gate_debug_read_spec.argtypes = [vp, vp]
+        pvp = C.POINTER(vp)
+        d.b200gate_run_sharded.argtypes = [vp, vp, C.c_int, i64, i64, i64, vp, pvp, vp, pvp, C.c_uint32, i32, i32, i32, i32, vp, vp]
+        d.b200gate_peer_push.argtypes = [vp, pvp, i32, i64, i64, i64, i64, i32, vp]
+        d.b200gate_peer_barrier.argtypes = [vp, pvp, i32, i32, C.c_uint32, vp]
+
+
+def peer_push(lib, src_ptr, peer_ptrs, rows, row_bytes, src_stride_bytes, dst_stride_bytes, n_ctas, stream):
+    arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    rc = lib.dll.b200gate_peer_push(src_ptr, arr, len(peer_ptrs), rows, row_bytes, src_stride_bytes, dst_stride_bytes, n_ctas, stream)
+    if rc != 0:
+        raise GateError(rc, "b200gate_peer_push")
+
+
+def peer_barrier(lib, flags_local, flags_peers, rank, world, epoch, stream):
+    arr = (C.c_void_p * world)(*[int(p) if p else None for p in flags_peers])
+    rc = lib.dll.b200gate_peer_barrier(flags_local, arr, rank, world, epoch, stream)
+    if rc != 0:
+        raise GateError(rc, "b200gate_peer_barrier")
 
 
 _LIB: Optional[GateLibrary] = None
@@ -206,6 +225,16 @@ class Gate:
     def run_device(self, in_ptr, out_ptr, dtype, C_, N, in_stride, out_stride, stream=None):
         self._check(self.lib.dll.b200gate_run(
             self._h, in_ptr, out_ptr, dtype_code(dtype), C_, N, in_stride, out_stride, 1, stream))
+
+    def run_sharded(self, in_ptr, dtype, C_local, N, in_stride, gathered_local, gathered_peers, flags_local, flags_peers,
+                    epoch, rank, world, groups, push_ctas, compute_stream, comm_stream):
+        """b200gate_run_sharded: channel groups into this rank's slice of the gathered buffer + kernel-issued NVLink
+        pushes into every peer's copy + device-side epoch barrier (include/b200gate.h)."""
+        gp = (C.c_void_p * world)(*[int(p) if p else None for p in gathered_peers])
+        fp = (C.c_void_p * world)(*[int(p) if p else None for p in flags_peers])
+        self._check(self.lib.dll.b200gate_run_sharded(
+            self._h, in_ptr, dtype_code(dtype), C_local, N, in_stride, gathered_local, gp, flags_local, fp, epoch, rank, world,
+            groups, push_ctas, compute_stream, comm_stream))
 
     def set_range(self, mode: int, a: int = 0, b: int = 0):
         self._check(self.lib.dll.b200gate_set_range(self._h, mode, a, b))

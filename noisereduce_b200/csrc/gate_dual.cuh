@@ -18,8 +18,14 @@
 
 namespace b200 {
 
-constexpr int kDualWarpsK2 = 7;                 // one CTA per SM; 7 x (16 KB spectrum + masks + exchange tile) + tables = 226 KB
-constexpr int kDualWarpsK1 = 8;
+#ifndef B200_K2D_WARPS
+#define B200_K2D_WARPS 7
+#endif
+constexpr int kDualWarpsK2 = B200_K2D_WARPS;                 // one CTA per SM; 7 x (16 KB spectrum + masks + exchange tile) + tables = 226 KB
+#ifndef B200_K1D_WARPS
+#define B200_K1D_WARPS 8
+#endif
+constexpr int kDualWarpsK1 = B200_K1D_WARPS;
 
 // 64-bit / 128-bit shared and global accesses on packed pairs (the simulator's f2 is a two-float struct)
 struct __align__(16) f2x2 { f2 a, b; };
@@ -211,15 +217,16 @@ __global__ void __launch_bounds__(kDualWarpsK2 * 32, 1) k2d_synthesize(const K2d
                 for (int q = 0; q < 32; ++q) w[q] = s_ws[lane + 32 * q];
 #pragma unroll
                 for (int r = 0; r < HR; ++r) out[r] = f2_fma_s(im[brev5(r)], w[r], P[r]);
+                // (summation order as k2c_synthesize's accumulate-then-shift loop: frame b's row before frame a's)
 #pragma unroll
                 for (int r = 0; r < HR; ++r)
-                    out[HR + r] = f2_fma_s(re[brev5(r)], w[r], f2_fma_s(im[brev5(HR + r)], w[HR + r], P[HR + r]));
+                    out[HR + r] = f2_fma_s(im[brev5(HR + r)], w[HR + r], f2_fma_s(re[brev5(r)], w[r], P[HR + r]));
 #pragma unroll
                 for (int r = 0; r < HR; ++r)
-                    P[r] = f2_fma_s(re[brev5(HR + r)], w[HR + r], f2_fma_s(im[brev5(2 * HR + r)], w[2 * HR + r], P[2 * HR + r]));
+                    P[r] = f2_fma_s(im[brev5(2 * HR + r)], w[2 * HR + r], f2_fma_s(re[brev5(HR + r)], w[HR + r], P[2 * HR + r]));
 #pragma unroll
                 for (int r = 0; r < HR; ++r)
-                    P[HR + r] = f2_fma_s(re[brev5(2 * HR + r)], w[2 * HR + r], f2_mul_s(im[brev5(3 * HR + r)], w[3 * HR + r]));
+                    P[HR + r] = f2_fma_s(im[brev5(3 * HR + r)], w[3 * HR + r], f2_mul_s(re[brev5(2 * HR + r)], w[2 * HR + r]));
 #pragma unroll
                 for (int r = 0; r < HR; ++r) P[2 * HR + r] = f2_mul_s(re[brev5(3 * HR + r)], w[3 * HR + r]);
             } else {                                    // past the last frame: flush the state
@@ -300,13 +307,16 @@ struct K1dArgs {
 };
 
 constexpr int kK1dTableBytes = kN * 4 + kN * 8 + 2 * kFPad * 4;
-constexpr int kK1dRowBytes = 32 * (32 + 8) * 4;                               // one unit's 40 sample rows of a pair (float32)
+#ifndef B200_K1D_STAGE
+#define B200_K1D_STAGE 0              // float32 sample rows bulk-copied (TMA) one pair ahead
+#endif
+constexpr int kK1dRowBytes = B200_K1D_STAGE ? 32 * (32 + 8) * 4 : 0;           // one unit's 40 sample rows of a pair (float32)
 constexpr int kK1dWarpBytes = 2 * kK1dRowBytes + kExchDual * 8 + 4 * kFW * 4 + 16;
 constexpr int k1d_smem_bytes() { return kK1dTableBytes + kDualWarpsK1 * kK1dWarpBytes; }
 
 template <int HR, typename T>
 __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArgs a) {
-    constexpr bool kStage = sizeof(T) == 4;                // float32 rows are bulk-copied (TMA) one pair ahead
+    constexpr bool kStage = sizeof(T) == 4 && B200_K1D_STAGE;       // float32 rows are bulk-copied (TMA) one pair ahead
     B200_DYN_SMEM(unsigned char, smraw);
     float* s_wa = reinterpret_cast<float*>(smraw);
     float2* s_tw = reinterpret_cast<float2*>(smraw + kN * 4);

@@ -8,6 +8,7 @@
 #include "gate_fused.cuh"
 #include "gate_synth.cuh"
 #include "gate_dual.cuh"
+#include "gate_peer.cuh"
 #include "gate_generic.cuh"
 
 #include <math.h>
@@ -83,6 +84,7 @@ struct b200gate_handle {
     bool stats_pending = false;
     size_t pend_batches = 0;
     bool pend_fused = false;
+    std::vector<cudaEvent_t> group_ev;             // b200gate_run_sharded: one per channel group + 1
     std::vector<cudaEvent_t> stage_ev;             // 4 per batch: analysis start, analysis end, smoothing end, synthesis end
     std::vector<cudaEvent_t> pipe_ev;              // 4 per batch: input landed, compute done, output landed, seam copied
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined host path
@@ -607,6 +609,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
             });
         cudaFuncSetAttribute(k1_analyze<8, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats_staged() * 4);
         cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_smooth_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k1n_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n2_smem_floats() * 4);
         cudaFuncSetAttribute(k2_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k22_smem_floats() * 4);
         for (int dt = 0; dt < 3; ++dt)
@@ -636,6 +639,7 @@ void b200gate_destroy(b200gate_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (cudaEvent_t e : h->group_ev) cudaEventDestroy(e);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     if (h->d_need_rowmax) cudaFree(h->d_need_rowmax);
     if (h->h_maxabs) cudaFreeHost(h->h_maxabs);
@@ -1482,6 +1486,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     ia.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
                 }
                 ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
+                ia.regen = (ia.b < 0.5 && (double)g.T * -log1p(-ia.b) < 20.0 && !(p.path_flags & 64)) ? 1 : 0;
                 ia.mag = d_mag; ia.m0 = d_m0;
                 B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad2, 128, 1 << 30)), dim3(128), 0, st, ia);
                 launches += 2;
@@ -1493,8 +1498,14 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     sa.F = kF2; sa.FPad = kFPad2;
                     sa.p = (float)p.prop_decrease; sa.one_minus_p = (float)(1.0 - p.prop_decrease);
                     sa.m0 = d_m0; sa.m2 = d_mag;
-                    const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                    B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+                    if (smooths_smem_bytes(sa.FPad, nf, nt) <= 200 * 1024 && !(p.path_flags & 32)) {
+                        sa.TT = 256;                    // frames per strip (2 nt warm-up rows each)
+                        const int strips = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                        B200_LAUNCH(k_smooth_stream, dim3(strips, nu), dim3(sa.FPad / 4), smooths_smem_bytes(sa.FPad, nf, nt), st, sa);
+                    } else {
+                        const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                        B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+                    }
                     cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                     K22Args a2{};
                     a2.g = g; a2.tb = t2; a2.x = (const float*)xb; a2.y = (float*)yb; a2.fmask = d_mag; a2.dbg = dbg;
@@ -1527,6 +1538,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                         ia.b = (sqrt(1.0 + 4.0 * tfr * tfr) - 1.0) / (2.0 * tfr * tfr);
                     }
                     ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
+                ia.regen = (ia.b < 0.5 && (double)g.T * -log1p(-ia.b) < 20.0 && !(p.path_flags & 64)) ? 1 : 0;
                     ia.mag = d_mag; ia.m0 = d_m0;
                     B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
                 }
@@ -1540,8 +1552,14 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     sa.p = torch_sem ? 1.0f : (float)p.prop_decrease;
                     sa.one_minus_p = torch_sem ? 0.0f : (float)(1.0 - p.prop_decrease);
                     sa.m0 = d_m0; sa.m2 = d_mag;
-                    const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                    B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+                    if (smooths_smem_bytes(sa.FPad, nf, nt) <= 200 * 1024 && !(p.path_flags & 32)) {
+                        sa.TT = 256;                    // frames per strip (2 nt warm-up rows each)
+                        const int strips = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                        B200_LAUNCH(k_smooth_stream, dim3(strips, nu), dim3(sa.FPad / 4), smooths_smem_bytes(sa.FPad, nf, nt), st, sa);
+                    } else {
+                        const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+                        B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+                    }
                     cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                     K2Args a2{};
                     a2.g = g; a2.tb = tb; a2.x = xb; a2.y = yb; a2.fmask = d_mag; a2.zcache = d_zcache; a2.zpairs = zpairs;
@@ -1664,6 +1682,85 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         if (rc) return rc;
     }
     h->stats.last_h2d_ms = h2d_ms;
+    return B200GATE_OK;
+}
+
+
+// ---- multi-GPU: kernel-issued NVLink stores (gate_peer.cuh) ---------------------------------------------------------
+int b200gate_peer_push(const void* src, void* const* peer_dst, int32_t n_peers, int64_t rows, int64_t row_bytes,
+                       int64_t src_stride_bytes, int64_t dst_stride_bytes, int32_t n_ctas, void* stream) {
+    if (!src || !peer_dst || n_peers < 0 || n_peers > kMaxPeers || rows < 0 || row_bytes < 0) return B200GATE_ERR_ARG;
+    if (n_peers == 0 || rows == 0 || row_bytes == 0) return B200GATE_OK;
+    if ((row_bytes | src_stride_bytes | dst_stride_bytes | (int64_t)(uintptr_t)src) & 15) return B200GATE_ERR_ARG;
+    PushArgs a{};
+    a.src = (const uint4*)src;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_dst[p] || ((uintptr_t)peer_dst[p] & 15)) return B200GATE_ERR_ARG;
+        a.dst[p] = (uint4*)peer_dst[p];
+    }
+    a.n_dst = n_peers;
+    a.rows = rows; a.vec_per_row = row_bytes / 16; a.src_stride = src_stride_bytes / 16; a.dst_stride = dst_stride_bytes / 16;
+    const int ctas = n_ctas > 0 ? n_ctas : 16;
+    B200_LAUNCH(k_peer_push, dim3(ctas), dim3(512), 0, (cudaStream_t)stream, a);
+    return cudaGetLastError() == cudaSuccess ? B200GATE_OK : B200GATE_ERR_CUDA;
+}
+
+int b200gate_peer_barrier(void* local_flags, void* const* peer_flags, int32_t rank, int32_t world, uint32_t epoch, void* stream) {
+    if (!local_flags || !peer_flags || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return B200GATE_ERR_ARG;
+    BarrierArgs a{};
+    a.local_flags = (unsigned*)local_flags;
+    for (int p = 0; p < world; ++p) a.peer_flags[p] = (unsigned*)peer_flags[p];
+    a.rank = rank; a.world = world; a.epoch = epoch;
+    B200_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, (cudaStream_t)stream, a);
+    return cudaGetLastError() == cudaSuccess ? B200GATE_OK : B200GATE_ERR_CUDA;
+}
+
+int b200gate_run_sharded(b200gate_handle* h, const void* in_local, int dtype, int64_t C_local, int64_t N, int64_t in_stride,
+                         void* gathered_local, void* const* gathered_peers, void* flags_local, void* const* flags_peers,
+                         uint32_t epoch, int32_t rank, int32_t world, int32_t groups, int32_t push_ctas,
+                         void* compute_stream, void* comm_stream) {
+    if (!h || !in_local || !gathered_local || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || C_local <= 0)
+        return fail(h, B200GATE_ERR_ARG, "bad argument");
+    if (world > 1 && (!gathered_peers || !flags_local || !flags_peers || !comm_stream || comm_stream == compute_stream))
+        return fail(h, B200GATE_ERR_ARG, "a sharded run needs peer mappings, flag arrays and a separate communication stream");
+    const size_t es = dtype_size(dtype);
+    if (es == 0) return fail(h, B200GATE_ERR_ARG, "bad dtype");
+    cudaStream_t cs = (cudaStream_t)compute_stream, ms = (cudaStream_t)comm_stream;
+    if (groups < 1) groups = 1;
+    const int64_t gs = (C_local + groups - 1) / groups;
+    while (h->group_ev.size() < (size_t)groups + 1) {
+        cudaEvent_t e;
+        CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->group_ev.push_back(e);
+    }
+    // the previous step's pushes (other ranks') may still be landing in OUR buffer only before their barrier; ours are
+    // ordered by the communication stream itself.  Compute must not overwrite rows a previous push is still reading:
+    CK(h, cudaEventRecord(h->group_ev[groups], ms));
+    CK(h, cudaStreamWaitEvent(cs, h->group_ev[groups], 0));
+    char* mine = (char*)gathered_local + (size_t)rank * C_local * N * es;
+    int gi = 0;
+    for (int64_t g0 = 0; g0 < C_local; g0 += gs, ++gi) {
+        const int64_t g1 = std::min<int64_t>(C_local, g0 + gs);
+        const int rc = b200gate_run(h, (const char*)in_local + (size_t)g0 * in_stride * es, mine + (size_t)g0 * N * es, dtype,
+                                    g1 - g0, N, in_stride, N, 1, compute_stream);
+        if (rc) return rc;
+        if (world == 1) continue;
+        CK(h, cudaEventRecord(h->group_ev[gi], cs));
+        CK(h, cudaStreamWaitEvent(ms, h->group_ev[gi], 0));
+        void* dst[kMaxPeers];
+        int np = 0;
+        for (int p = 0; p < world; ++p)
+            if (p != rank) dst[np++] = (char*)gathered_peers[p] + ((size_t)rank * C_local + g0) * N * es;
+        const int rc2 = b200gate_peer_push(mine + (size_t)g0 * N * es, dst, np, g1 - g0, (int64_t)(N * es), (int64_t)(N * es),
+                                           (int64_t)(N * es), push_ctas, comm_stream);
+        if (rc2) return fail(h, rc2, "peer push failed (rows must be 16-byte multiples)");
+    }
+    if (world > 1) {
+        const int rc = b200gate_peer_barrier(flags_local, flags_peers, rank, world, epoch, comm_stream);
+        if (rc) return fail(h, rc, "peer barrier failed");
+        CK(h, cudaEventRecord(h->group_ev[groups], ms));
+        CK(h, cudaStreamWaitEvent(cs, h->group_ev[groups], 0));
+    }
     return B200GATE_OK;
 }
 

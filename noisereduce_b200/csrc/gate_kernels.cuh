@@ -1048,6 +1048,7 @@ struct IirArgs {
     int F, FPad;               // bins and padded row pitch (513/544 for n_fft 1024, 1025/1056 for 2048)
     double b;                  // nonstationary.py:114
     float n_mult, slope;       // thresh_n_mult_nonstationary, sigmoid_slope_nonstationary
+    int regen;                 // 1: regenerate the forward sweep in the backward pass instead of storing it
     const float* mag;          // [n_units][T][FPad]
     float* m0;                 // [n_units][T][FPad]: forward sweep, then overwritten by the sigmoid mask
 };
@@ -1069,6 +1070,26 @@ __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
     const double b = a.b, omb = 1.0 - a.b;
     const float n_mult = a.n_mult, slope = a.slope;
     double s = (double)A[0];
+    if (a.regen) {
+        // The forward sweep is not stored: the backward sweep regenerates it by the inverse recurrence
+        // fwd[t-1] = (fwd[t] - b x[t]) / (1 - b) in float64.  Its error grows by 1/(1 - b) per step; the host selects
+        // this variant only when (1 - b)^-T * 2^-53 stays far below float32 resolution (T ln(1/(1-b)) < 20), which
+        // holds for the reference's time constants (config 3: 6.9).  One read of |X| less, no forward write.
+#pragma unroll 8
+        for (int t = 0; t < a.T; ++t) s = fma(b, (double)A[(long long)t * FP], omb * s);
+        const double inv_omb = 1.0 / omb;
+        double f = s;                                          // fwd[T-1]
+#pragma unroll 8
+        for (int t = a.T - 1; t >= 0; --t) {
+            const double x = (double)A[(long long)t * FP];
+            s = fma(b, f, omb * s);
+            const float num = (float)(x - s);
+            const float r = num / (float)s;
+            M[(long long)t * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
+            f = fma(-b, x, f) * inv_omb;
+        }
+        return;
+    }
 #pragma unroll 8
     for (int t = 0; t < a.T; ++t) {
         s = fma(b, (double)A[(long long)t * FP], omb * s);
@@ -1131,6 +1152,69 @@ __global__ void __launch_bounds__(256) k_smooth_f(const SmoothFArgs a) {
             v = fmaf(acc * invD, a.p, a.one_minus_p);           // nonstationary.py:82-84
         }
         dst[(long long)(t0 + tt) * FP + f] = v;
+    }
+}
+
+// Streaming form of the same smoothing (the one that normally runs; k_smooth_f above is kept as its tile-based
+// cross-check).  A CTA walks a strip of frames of one unit; thread i owns bins i, i+G, i+2G, i+3G (G = FPad/4, so every
+// shared-memory access of a warp is 32 consecutive floats): the last 2 nt + 1 mask rows live in a ring of thread-private
+// columns (no barrier needed to refill it), the time-direction triangle is taken straight from the ring, the
+// frequency-direction triangle from one zero-haloed row -- two barriers per frame, every mask value read from HBM
+// once per strip and written once.
+inline size_t smooths_smem_bytes(int FPad, int nf, int nt) { return ((size_t)(2 * nt + 1) * FPad + FPad + 2 * nf + 8) * 4; }
+
+__global__ void __launch_bounds__(288) k_smooth_stream(const SmoothFArgs a) {
+    B200_DYN_SMEM(float, s_buf);
+    const int FP = a.FPad, FF = a.F, nt = a.nt, nf = a.nf, R = 2 * nt + 1;
+    const int G = blockDim.x, tid = threadIdx.x;
+    float* ring = s_buf;                     // [R][FP]
+    float* row = s_buf + (size_t)R * FP;     // [nf | FP | nf]
+    const int ul = blockIdx.y;
+    const int t_begin = a.tf_lo + blockIdx.x * a.TT;
+    if (t_begin >= a.tf_hi) return;
+    const int t_end = min(t_begin + a.TT, a.tf_hi);
+    const float* src = a.m0 + (long long)ul * a.T * FP;
+    float* dst = a.m2 + (long long)ul * a.T * FP;
+    for (int i = tid; i < FP + 2 * nf; i += G) row[i] = 0.f;
+    auto load_row = [&](int t, int slot) {
+        const bool in = t >= 0 && t < a.T;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int bin = tid + j * G;
+            ring[slot * FP + bin] = (in && bin < FF) ? src[(long long)t * FP + bin] : 0.f;
+        }
+    };
+    // ring slot of frame t: (t - t_begin + nt) mod R, so the newest row t + nt of step t sits at slot (t - t_begin + 2 nt) mod R
+    for (int k = 0; k < 2 * nt; ++k) load_row(t_begin - nt + k, k);
+    int newest = (2 * nt) % R;
+    const float invD = 1.0f / ((float)((nf + 1) * (nf + 1)) * (float)((nt + 1) * (nt + 1)));
+    __syncthreads();
+    for (int t = t_begin; t < t_end; ++t) {
+        load_row(t + nt, newest);
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        int slot = newest;                                  // frame t + nt; walking back to t - nt
+        for (int b = -nt; b <= nt; ++b) {
+            const float w = (float)(nt + 1 - (b < 0 ? -b : b));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = fmaf(w, ring[slot * FP + tid + j * G], c[j]);
+            slot = slot == 0 ? R - 1 : slot - 1;
+        }
+        newest = newest + 1 == R ? 0 : newest + 1;
+        __syncthreads();                                    // the previous frame's frequency pass has read `row`
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[nf + tid + j * G] = c[j];
+        __syncthreads();
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int d = -nf; d <= nf; ++d) {
+            const float w = (float)(nf + 1 - (d < 0 ? -d : d));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaf(w, row[nf + tid + j * G + d], o[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int bin = tid + j * G;
+            dst[(long long)t * FP + bin] = bin < FF ? fmaf(o[j] * invD, a.p, a.one_minus_p) : 0.f;      // nonstationary.py:82-84
+        }
     }
 }
 

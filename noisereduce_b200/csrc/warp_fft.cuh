@@ -363,8 +363,8 @@ __device__ __forceinline__ void warp_fft1024_dual(f2 (&re)[32], f2 (&im)[32], f2
                 const int s = brev5(q);
                 const float2 w = tw[q * 32 + lane];
                 const f2 a = re[s], b = im[s];
-                re[s] = f2_sub(f2_mul_s(a, w.x), f2_mul_s(b, w.y));
-                im[s] = f2_fma_s(a, w.y, f2_mul_s(b, w.x));
+                re[s] = f2_fma_s(b, -w.y, f2_mul_s(a, w.x));          // same operation order as twiddle_transpose: the dual and
+                im[s] = f2_fma_s(a, w.y, f2_mul_s(b, w.x));           // single-unit kernels give bit-identical results
             }
             f2* row = tile + lane * 33;
 #pragma unroll

@@ -22,19 +22,26 @@ def chained_noise_stats(dg, x_local: torch.Tensor, rank: int, world: int, group=
     n = N
     if p.clip_noise and p.chunk_size > 0 and n > p.chunk_size:
         n = int(p.chunk_size)
-    acc = torch.zeros(n, dtype=torch.float32, device=x_local.device)
+    # the reference's channel mean runs in the input dtype for float32 and in float64 for int16 / float64
+    # (stationary.py:61-64 through numpy's promotion); the running sum follows the same rule
+    if x_local.dtype not in (torch.float32, torch.int16, torch.float64):
+        raise TypeError("sharded noise statistics take float32 / int16 / float64 shards")
+    acc_t = torch.float32 if x_local.dtype == torch.float32 else torch.float64
+    np_in = {torch.float32: np.float32, torch.int16: np.int16, torch.float64: np.float64}[x_local.dtype]
+    np_acc = np.float32 if acc_t == torch.float32 else np.float64
+    acc = torch.zeros(n, dtype=acc_t, device=x_local.device)
     if rank > 0:
         dist.recv(acc, src=rank - 1, group=group)
     stream = torch.cuda.current_stream().cuda_stream if x_local.is_cuda else None
-    dg.gate.channel_sum_device(x_local.data_ptr(), np.float32, C, n, x_local.stride(0), acc.data_ptr(),
+    dg.gate.channel_sum_device(x_local.data_ptr(), np_in, C, n, x_local.stride(0), acc.data_ptr(),
                                init=(rank == 0), stream=stream)
     if x_local.is_cuda:
         torch.cuda.current_stream().synchronize()
     if rank < world - 1:
         dist.send(acc, dst=rank + 1, group=group)
-    mean = acc / np.float32(world * C) if rank == world - 1 else acc      # numpy: sum / count in float32
+    mean = acc / np_acc(world * C) if rank == world - 1 else acc      # numpy: sum / count in the accumulation dtype
     dist.broadcast(mean, src=world - 1, group=group)
-    dg.gate.noise_stats_collapsed_device(mean.data_ptr(), np.float32, n, stream=stream)
+    dg.gate.noise_stats_collapsed_device(mean.data_ptr(), np_acc, n, stream=stream)
     return mean
 
 
@@ -282,5 +289,92 @@ def _slab_ring_peer(dg, x_local, world, slab_chunks, consume, pg: PeerGather):
             pg.h.barrier(channel=1)                  # ... and have been consumed everywhere before the slot is reused
             slot_free[k] = torch.cuda.Event()
             slot_free[k].record(comm)
+    cur.wait_stream(comm)
+    return results
+
+
+# ---- kernel-issued NVLink stores: b200gate_run_sharded (include/b200gate.h, csrc/gate_peer.cuh) ---------------------
+class PeerStore:
+    """Symmetric-memory state of the fused gather: the gathered [world, C, N] result, a flag array for the device-side
+    epoch barrier, every peer's mapping of both, and the communication stream.  The library does the rest
+    (b200gate_run_sharded): gate kernels write this rank's rows into its slice of the local buffer, k_peer_push stores
+    every finished channel group into the peers' buffers over NVLink from a few SMs the gate leaves free
+    (DeviceGate(reserve_sms=...)), k_peer_barrier ends the step.  No NCCL kernels, no copy engines, no host syncs."""
+
+    def __init__(self, world: int, rank: int, shape, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.shape = world, rank, tuple(shape)
+        self.buf = symm.empty(self.shape, dtype=dtype, device=device)
+        self.h = symm.rendezvous(self.buf, grp)
+        self.flags = symm.empty((64,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.hf = symm.rendezvous(self.flags, grp)
+        self._views = [self.buf if r == rank else self.h.get_buffer(r, self.shape, dtype) for r in range(world)]
+        self._fviews = [self.flags if r == rank else self.hf.get_buffer(r, (64,), torch.int32) for r in range(world)]
+        self.peer_ptrs = [v.data_ptr() for v in self._views]
+        self.flag_ptrs = [v.data_ptr() for v in self._fviews]
+        self.comm = torch.cuda.Stream(device=device, priority=-1)
+        self.epoch = 0
+        torch.cuda.synchronize()
+        self.hf.barrier()                                   # every rank's flags are zero before the first epoch
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+
+def sharded_run_peer_store(dg, x_local: torch.Tensor, ps: PeerStore, groups: int = 8, push_ctas: int = 0):
+    """Channel-sharded step with the kernel-issued gather: ps.buf is the final [world, C, N] waveform on every rank
+    once the current stream reaches this point.  Thresholds must already be set (chained_noise_stats)."""
+    C, N = x_local.shape
+    cur = torch.cuda.current_stream()
+    dg.gate.run_sharded(x_local.data_ptr(), DeviceGateDtypes[x_local.dtype], C, N, x_local.stride(0), ps.buf.data_ptr(),
+                        ps.peer_ptrs, ps.flags.data_ptr(), ps.flag_ptrs, ps.next_epoch(), ps.rank, ps.world, groups,
+                        push_ctas, cur.cuda_stream, ps.comm.cuda_stream)
+    return ps.buf
+
+
+DeviceGateDtypes = {torch.float32: np.float32, torch.int16: np.int16, torch.float64: np.float64}
+
+
+def slab_ring_peer_store(dg, x_local, world, slab_chunks, consume, ps: PeerStore, push_ctas: int = 0):
+    """Config-5 slab ring on the kernel-issued gather: ps.buf is [2, world, C, slab]; slab s is denoised into
+    ps.buf[s & 1, rank], pushed into every peer's copy by k_peer_push behind the next slab's kernels, published by the
+    epoch barrier, consumed, and released by a second barrier before its slot is reused."""
+    from . import _cabi
+    C, N = x_local.shape
+    cs = int(dg.gate.params.chunk_size)
+    n_chunks = (N - 1) // cs + 1
+    cur = torch.cuda.current_stream()
+    comm = ps.comm
+    lib = dg.gate.lib
+    es = x_local.element_size()
+    slab_len = ps.buf.shape[-1]
+    slot_free = [None, None]
+    results = []
+    peers = [r for r in range(world) if r != ps.rank]
+    for si, first in enumerate(range(0, n_chunks, slab_chunks)):
+        last = min(n_chunks - 1, first + slab_chunks - 1)
+        k = si & 1
+        if slot_free[k] is not None:
+            cur.wait_event(slot_free[k])
+        mine = ps.buf[k, ps.rank]
+        view = dg.run_chunks(x_local, mine, first, last)
+        n_s = view.shape[1]
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        comm.wait_event(ev)
+        off = ((k * world + ps.rank) * C) * slab_len * es
+        if peers:
+            _cabi.peer_push(lib, mine.data_ptr(), [ps.peer_ptrs[r] + off for r in peers], C, n_s * es, slab_len * es,
+                            slab_len * es, push_ctas, comm.cuda_stream)
+            _cabi.peer_barrier(lib, ps.flags.data_ptr(), ps.flag_ptrs, ps.rank, world, ps.next_epoch(), comm.cuda_stream)
+        with torch.cuda.stream(comm):
+            results.append(consume(ps.buf[k, :, :, :n_s], first * cs, si) if consume is not None else None)
+        if peers:
+            _cabi.peer_barrier(lib, ps.flags.data_ptr(), ps.flag_ptrs, ps.rank, world, ps.next_epoch(), comm.cuda_stream)
+        slot_free[k] = torch.cuda.Event()
+        slot_free[k].record(comm)
     cur.wait_stream(comm)
     return results

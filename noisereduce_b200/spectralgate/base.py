@@ -41,7 +41,7 @@ class SpectralGate:
     ):
         self.sr = sr
         self.flat = False
-        y = np.array(y)
+        y = np.asarray(y)              # (the reference copies with np.array; nothing here writes to the caller's samples)
         # reshape data to (#channels, #frames)                      (base.py:54-62)
         if len(y.shape) == 1:
             self.y = np.expand_dims(y, 0)
@@ -72,6 +72,7 @@ class SpectralGate:
         else:
             self._generate_mask_smoothing_filter(freq_mask_smooth_hz, time_mask_smooth_ms)
         self._gate = None
+        self._unit_gate = None
 
     def _generate_mask_smoothing_filter(self, freq_mask_smooth_hz, time_mask_smooth_ms):
         """base.py:99-128 -- same integer arithmetic and the same ValueErrors.  Only the extents are
@@ -131,6 +132,44 @@ class SpectralGate:
             with np.errstate(invalid="ignore"):
                 out = out.astype(self._dtype)                  # base.py:218-226
         return out
+
+    # -- the reference's per-chunk plugin point (base.py:130-160) ----------------------------------------
+    def _read_chunk(self, i1, i2):
+        """base.py:130-142: the span [i1, i2) of every channel as float64, zeros outside the recording."""
+        lo, hi = max(i1, 0), min(i2, self.n_frames)
+        chunk = np.zeros((self.n_channels, i2 - i1))
+        chunk[:, lo - i1: hi - i1] = self.y[:, lo:hi]
+        return chunk
+
+    def filter_chunk(self, start_frame, end_frame):
+        """base.py:144-150: pad by `padding` on both sides, filter, return the centre."""
+        i1, i2 = start_frame - self.padding, end_frame + self.padding
+        filtered = self._do_filter(self._read_chunk(i1, i2))
+        return filtered[:, start_frame - i1: end_frame - i1]
+
+    def _get_filtered_chunk(self, ind):
+        """base.py:152-156."""
+        return self.filter_chunk(start_frame=ind * self._chunk_size, end_frame=(ind + 1) * self._chunk_size)
+
+    def _unit_gate_params(self):
+        """Parameters of the gate that filters ONE already padded chunk (chunk_size <= 0 and padding = 0 make the
+        library treat its whole input as the single unit of stationary.py:83-127 / nonstationary.py:47-97)."""
+        raise NotImplementedError
+
+    def _do_filter(self, chunk):
+        """base.py:158-160 / stationary.py:129 / nonstationary.py:99: filter one padded chunk [C, Lp]; the result has
+        the chunk's shape and dtype, its first (Lp // hop) * hop columns filled.  One library call on a second handle
+        that shares this gate's statistics."""
+        chunk = np.asarray(chunk)
+        if self._unit_gate is None:
+            self._unit_gate = _cabi.Gate(**self._unit_gate_params())
+            self._prepare_unit_gate(self._unit_gate)
+        x = self._samples_for_device(chunk)
+        out = self._unit_gate.run_host(x)
+        return out if out.dtype == chunk.dtype else out.astype(chunk.dtype)
+
+    def _prepare_unit_gate(self, gate):
+        pass
 
     def get_traces(self, start_frame=None, end_frame=None):
         """base.py:167-226.  With both bounds None this is the whole recording (what reduce_noise

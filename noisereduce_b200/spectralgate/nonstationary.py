@@ -35,4 +35,10 @@ class SpectralGateNonStationary(SpectralGate):
         params.update(stationary=0, time_constant_s=float(time_constant_s),
                       thresh_n_mult=float(thresh_n_mult_nonstationary),
                       sigmoid_slope=float(sigmoid_slope_nonstationary))
+        self._params = params
         self._gate = _cabi.Gate(**params)
+
+    def _unit_gate_params(self):
+        p = dict(self._params)
+        p.update(chunk_size=0, padding=0)
+        return p

@@ -49,12 +49,21 @@ class SpectralGateStationary(SpectralGate):
         params = self._gate_params()
         params.update(stationary=1, n_std_thresh=float(n_std_thresh_stationary),
                       clip_noise=1 if clip_noise_stationary else 0)
+        self._params = params
         self._gate = _cabi.Gate(**params)
         # stationary.py:61-81 on the device: channel mean in the input dtype, clip, STFT, dB with the
         # 80 dB floor, per-bin mean / std over time, threshold
         self._gate.noise_stats_host(self._samples_for_device(noise))
         self.mean_freq_noise, self.std_freq_noise = self._gate.noise_mean_std()
         self.noise_thresh = self._gate.noise_threshold()
+
+    def _unit_gate_params(self):
+        p = dict(self._params)
+        p.update(chunk_size=0, padding=0)
+        return p
+
+    def _prepare_unit_gate(self, gate):
+        gate.set_noise_threshold(self.noise_thresh)          # the thresholds of the whole recording (stationary.py:79-81)
 
     @property
     def y_noise(self):

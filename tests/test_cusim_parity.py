@@ -242,6 +242,73 @@ def test_python_surface_on_simulator(lib, monkeypatch):
         nr.reduce_noise(y=y, sr=SR, stationary=True, n_fft=512, win_length=600)
 
 
+def test_do_filter_plugin_point_on_simulator(lib, monkeypatch):
+    """The reference's per-chunk operator interface (base.py:130-160): _read_chunk / filter_chunk /
+    _get_filtered_chunk / _do_filter(chunk) on the mirror classes, against the oracle's per-unit gate."""
+    monkeypatch.setattr(_cabi, "_LIB", lib)
+    from noisereduce_b200.spectralgate.stationary import SpectralGateStationary
+    from noisereduce_b200.spectralgate.nonstationary import SpectralGateNonStationary
+    y = synth_small(C=2, n=9000)
+    kw = dict(chunk_size=3000, padding=400)
+    common = dict(n_fft=1024, win_length=None, hop_length=None, time_constant_s=0.3, freq_mask_smooth_hz=500,
+                  time_mask_smooth_ms=50, tmp_folder=None, prop_decrease=1.0, use_tqdm=False, n_jobs=1, **kw)
+    sg = SpectralGateStationary(y=y, sr=SR, y_noise=None, n_std_thresh_stationary=1.5, clip_noise_stationary=True, **common)
+    cfg = O.GateConfig(sr=SR, stationary=True, **kw)
+    info = {}
+    full = O.reduce_noise(y, SR, cfg=cfg, info=info, return_float64=True)
+    chunk = sg._read_chunk(3000 - 400, 6000 + 400)
+    assert chunk.dtype == np.float64 and chunk.shape == (2, 3800)
+    assert np.array_equal(chunk, O.read_chunk(y, 2600, 6400))
+    filt = sg._do_filter(chunk)
+    assert filt.shape == chunk.shape and filt.dtype == chunk.dtype
+    for c in range(2):
+        ref = O.gate_stationary_unit(chunk[c], sg.noise_thresh, cfg, info["filt"])
+        assert P.relinf(filt[c], ref) < P.OUT_TOL
+    assert P.relinf(sg._get_filtered_chunk(1), full[:, 3000:6000]) < P.OUT_TOL
+    assert P.relinf(sg.filter_chunk(6000, 9000), full[:, 6000:9000]) < P.OUT_TOL
+    # the last columns past (Lp // hop) * hop stay zero, as stationary.py:126 leaves them
+    assert np.all(filt[:, (3800 // 256) * 256:] == 0)
+    ns = SpectralGateNonStationary(y=y, sr=SR, thresh_n_mult_nonstationary=2, sigmoid_slope_nonstationary=10, **common)
+    cfg_ns = O.GateConfig(sr=SR, stationary=False, time_constant_s=0.3, **kw)
+    info = {}
+    full = O.reduce_noise(y, SR, cfg=cfg_ns, info=info, return_float64=True)
+    filt = ns._do_filter(chunk)
+    for c in range(2):
+        assert P.relinf(filt[c], O.gate_nonstationary_unit(chunk[c], cfg_ns, info["filt"])) < P.OUT_TOL
+    assert P.relinf(ns._get_filtered_chunk(0), full[:, 0:3000]) < P.OUT_TOL
+
+
+def test_run_sharded_peer_stores_on_simulator(lib):
+    """b200gate_run_sharded (kernel-issued gather): two 'ranks' in one process share host buffers as their peer
+    mappings; each writes its channel groups into its own copy and pushes them into the other's; both copies must end
+    up equal to the single-gate result, flags carry the epoch."""
+    import torch
+    from noisereduce_b200.device import DeviceGate
+    y = torch.from_numpy(synth_small(C=4, n=7000))
+    kw = dict(chunk_size=3000, padding=400)
+    ref_gate = DeviceGate(sr=SR, stationary=True, lib=lib, **kw)
+    ref_gate.noise_stats(y)
+    thr = ref_gate.gate.noise_threshold()
+    want = ref_gate.run(y).numpy()
+    world, Cl, N = 2, 2, y.shape[1]
+    gathered = [np.full((world * Cl, N), np.nan, np.float32) for _ in range(world)]
+    flags = [np.zeros(64, np.uint32) for _ in range(world)]
+    for rank in range(world):
+        dg = DeviceGate(sr=SR, stationary=True, lib=lib, **kw)
+        dg.gate.set_noise_threshold(thr)
+        x_local = y[rank * Cl: (rank + 1) * Cl].contiguous()
+        dg.gate.run_sharded(x_local.data_ptr(), np.float32, Cl, N, N, gathered[rank].ctypes.data,
+                            [g.ctypes.data for g in gathered], flags[rank].ctypes.data, [f.ctypes.data for f in flags],
+                            7, rank, world, 2, 2, None, 1)
+    for g in gathered:
+        assert np.array_equal(g, want)
+    assert flags[0][1] == 7 and flags[1][0] == 7
+    # argument checks: rows that are not 16-byte multiples cannot be pushed
+    odd = np.zeros((2, 7001), np.float32)
+    with pytest.raises(_cabi.GateError):
+        _cabi.peer_push(lib, odd.ctypes.data, [gathered[0].ctypes.data], 2, 7001 * 4, 7001 * 4, 7001 * 4, 1, None)
+
+
 def test_get_traces_subranges_on_simulator(lib, monkeypatch):
     """SpectralGate.get_traces(start_frame, end_frame) runs only the reference's units (base.py:167-226):
     a chunk sub-range of the grid (host rows -> slab pipeline; int16 -> staged window), and the single
