@@ -131,6 +131,14 @@ int b200gate_set_window(b200gate_handle* h, const float* window, int32_t win_len
 int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int64_t Bn, int64_t Ln,
                              int64_t stride, int is_device, void* cuda_stream);
 
+/* Torch surface only: apply the MASKS OF THE LAST b200gate_run (same [C][N]) to another signal: analysis of `in`, the
+ * stored masks, synthesis.  The gate is linear in its input once the masks are fixed and its operator is
+ * out = OLA(w B_mask(w frame(in))) / env with a symmetric B_mask, so this call on g / env, times env, is the adjoint:
+ * the backward pass of TorchGate.forward (torchgate.py:223-262 builds the masks under no_grad and lets the gradient flow
+ * through stft -> * mask -> istft).  Needs the tuned n_fft = 1024 geometry and a forward that fitted one workspace batch. */
+int b200gate_torch_apply_masks(b200gate_handle* h, const void* in, void* out, int dtype, int64_t C, int64_t N,
+                               int64_t in_stride, int64_t out_stride, int is_device, void* cuda_stream);
+
 /* The operator.  in/out: [C][N] samples of `dtype` with row strides in elements; host or device
  * pointers (is_device).  out may not alias in.  For the torch surface out holds [C][(N/hop)*hop].
  * Returns after the work is enqueued for device pointers; for host pointers it returns after the

@@ -27,7 +27,7 @@ EXPORTS = [
     "b200gate_torch_set_noise",
     "b200gate_run", "b200gate_set_range", "b200gate_get_stats", "b200gate_debug_select_unit", "b200gate_debug_dims",
     "b200gate_debug_read_bits", "b200gate_debug_read_mask", "b200gate_debug_read_spec",
-    "b200gate_run_sharded", "b200gate_peer_push", "b200gate_peer_barrier",
+    "b200gate_run_sharded", "b200gate_peer_push", "b200gate_peer_barrier", "b200gate_torch_apply_masks",
 ]
 
 
@@ -93,6 +93,7 @@ class GateLibrary:
         d.b200gate_set_window.argtypes = [vp, C.POINTER(C.c_float), i32]
         d.b200gate_torch_set_noise.argtypes = [vp, vp, C.c_int, i64, i64, i64, C.c_int, vp]
         d.b200gate_run.argtypes = [vp, vp, vp, C.c_int, i64, i64, i64, i64, C.c_int, vp]
+        d.b200gate_torch_apply_masks.argtypes = [vp, vp, vp, C.c_int, i64, i64, i64, i64, C.c_int, vp]
         d.b200gate_set_range.argtypes = [vp, i32, i64, i64]
         d.b200gate_get_stats.argtypes = [vp, C.POINTER(Stats)]
         d.b200gate_debug_select_unit.argtypes = [vp, i64, i64]
@@ -191,8 +192,8 @@ class Gate:
         w = np.ascontiguousarray(window_f32, dtype=np.float32)
         self._check(self.lib.dll.b200gate_set_window(self._h, w.ctypes.data_as(C.POINTER(C.c_float)), w.shape[0]))
 
-    def torch_set_noise(self, ptr, Bn, Ln, stride, is_device=True, stream=None):
-        self._check(self.lib.dll.b200gate_torch_set_noise(self._h, ptr, F32, Bn, Ln, stride, 1 if is_device else 0, stream))
+    def torch_set_noise(self, ptr, Bn, Ln, stride, is_device=True, stream=None, dtype=np.float32):
+        self._check(self.lib.dll.b200gate_torch_set_noise(self._h, ptr, dtype_code(dtype), Bn, Ln, stride, 1 if is_device else 0, stream))
 
     def set_noise_threshold(self, thresh_db):
         t = np.ascontiguousarray(thresh_db, dtype=np.float64)
@@ -235,6 +236,10 @@ class Gate:
         self._check(self.lib.dll.b200gate_run_sharded(
             self._h, in_ptr, dtype_code(dtype), C_local, N, in_stride, gathered_local, gp, flags_local, fp, epoch, rank, world,
             groups, push_ctas, compute_stream, comm_stream))
+
+    def torch_apply_masks_device(self, in_ptr, out_ptr, dtype, C_, N, in_stride, out_stride, stream=None):
+        self._check(self.lib.dll.b200gate_torch_apply_masks(
+            self._h, in_ptr, out_ptr, dtype_code(dtype), C_, N, in_stride, out_stride, 1, stream))
 
     def set_range(self, mode: int, a: int = 0, b: int = 0):
         self._check(self.lib.dll.b200gate_set_range(self._h, mode, a, b))

@@ -81,6 +81,10 @@ struct b200gate_handle {
     unsigned* h_maxabs = nullptr;                  // pinned (fused path)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
     // statistics of a device-pointer run are resolved lazily (b200gate_get_stats): the run itself never blocks the host
+    // torch surface: the masks of the last forward stay in the workspace so that the adjoint (= the same synthesis
+    // with the same masks, TorchGate.backward) can reuse them -- b200gate_torch_apply_masks
+    bool masks_valid = false, reuse_masks = false;
+    long long masks_C = 0, masks_N = 0;
     bool stats_pending = false;
     size_t pend_batches = 0;
     bool pend_fused = false;
@@ -803,14 +807,17 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
     if (!h) return B200GATE_ERR_ARG;
     if (h->p.surface != B200GATE_SURFACE_TORCH) return fail(h, B200GATE_ERR_STATE, "torch surface only");
     if (!xn) { h->tthr_units = 0; return B200GATE_OK; }
-    if (Bn <= 0 || Ln <= 0 || dtype != B200GATE_F32) return fail(h, B200GATE_ERR_ARG, "xn must be float32 [Bn][Ln]");
+    const bool f64 = dtype == B200GATE_F64 && h->generic;            // float64 noise clips: general family only
+    if (Bn <= 0 || Ln <= 0 || (dtype != B200GATE_F32 && !f64))
+        return fail(h, B200GATE_ERR_ARG, "xn must be float32 [Bn][Ln] (float64 on the general-geometry family)");
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t xes = f64 ? 8 : 4;
     const float* x = (const float*)xn;
     Scratch s_tmp;
     long long xs = stride;
     if (!is_device) {
-        CK(h, s_tmp.alloc((size_t)Bn * Ln * 4));
-        CK(h, cudaMemcpy2DAsync(s_tmp.p, (size_t)Ln * 4, xn, (size_t)stride * 4, (size_t)Ln * 4, (size_t)Bn, cudaMemcpyHostToDevice, st));
+        CK(h, s_tmp.alloc((size_t)Bn * Ln * xes));
+        CK(h, cudaMemcpy2DAsync(s_tmp.p, (size_t)Ln * xes, xn, (size_t)stride * xes, (size_t)Ln * xes, (size_t)Bn, cudaMemcpyHostToDevice, st));
         x = s_tmp.as<float>(); xs = Ln;
     }
     Geom g{};
@@ -827,9 +834,17 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
         if (h->d_gtthr) cudaFree(h->d_gtthr);
         h->d_gtthr = nullptr;
         CK(h, cudaMalloc((void**)&h->d_gtthr, (size_t)Bn * F * sizeof(double)));
-        GStftArgs<float> sa{};
-        sa.gg = generic_geom(h, g); sa.tb = generic_tables(h); sa.x = x; sa.X = gX;
-        { auto kern_ = gk_stft<float>; B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)Bn), dim3(generic_threads(generic_fft_len(h))), (size_t)generic_fft_len(h) * sizeof(double2), st, sa); }
+        if (f64) {
+            GStftArgs<double> sa{};
+            sa.gg = generic_geom(h, g); sa.tb = generic_tables(h); sa.x = (const double*)(const void*)x; sa.X = gX;
+            auto kern_ = gk_stft<double>;
+            B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)Bn), dim3(generic_threads(generic_fft_len(h))), (size_t)generic_fft_len(h) * sizeof(double2), st, sa);
+        } else {
+            GStftArgs<float> sa{};
+            sa.gg = generic_geom(h, g); sa.tb = generic_tables(h); sa.x = x; sa.X = gX;
+            auto kern_ = gk_stft<float>;
+            B200_LAUNCH(kern_, dim3((unsigned)g.T, (unsigned)Bn), dim3(generic_threads(generic_fft_len(h))), (size_t)generic_fft_len(h) * sizeof(double2), st, sa);
+        }
         GTStatArgs ta{};
         ta.n_units = (int)Bn; ta.T = g.T; ta.F = F; ta.ddof = h->p.std_ddof; ta.eps = kEps64; ta.top_db = h->p.top_db;
         ta.n_std = h->p.n_std_thresh; ta.X = gX; ta.scratch = gD; ta.thr = h->d_gtthr;
@@ -878,6 +893,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t es = dtype_size(dtype);
     h->stats = b200gate_stats{};
     long long launches = 0;
+    if (!h->reuse_masks) h->masks_valid = false;
 
     // ---- which part of the recording (base.py:167-226; b200gate_set_range) -----------------------------
     // range_mode 2: the reference's single padded chunk [0, a) inside a longer recording (base.py:222)
@@ -908,7 +924,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // float32 / int16 / float64 rows directly and cast on store (base.py:140, :218-226).  The 2048 family and
     // the torch surface run on float32 rows (other dtypes are converted at the edge).
     const bool generic = h->generic;
-    const bool native = !torch_sem && (p.n_fft == kN || generic);
+    // (the general family is templated on the sample type on both surfaces: float64 TorchGate input stays float64)
+    const bool native = (!torch_sem && p.n_fft == kN) || generic;
     const int kdt = native ? dtype : B200GATE_F32;            // dtype the kernels see
     const size_t kes = dtype_size(kdt);
     const void* x = nullptr;
@@ -1297,7 +1314,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if (torch_sem) {
                 // TorchGate: |X| -> dB, per-row statistics over the row's own frames (or xn's), compare
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, kdt, d_tdb, dbg, resident, st, d_zcache, tf_lo, tf_hi + 1);
+                launch_k1n(g, tb, xb, kdt, h->reuse_masks ? nullptr : d_tdb, dbg, resident, st, d_zcache, tf_lo, tf_hi + 1);
+                if (!h->reuse_masks) {
                 TStatArgs ta{};
                 ta.n_units = nu; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64;
                 ta.top_db = (float)p.top_db; ta.n_std = (float)p.n_std_thresh; ta.ddof = p.std_ddof;
@@ -1315,6 +1333,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 B200_LAUNCH(k_tgate_bits, dim3((unsigned)(((long long)nu * kFPad + 127) / 128)), dim3(128), 0, st, ba);
                 CK(h, cudaMemsetAsync(d_rowflag, 0, (size_t)nu * kFW * 4, st));
                 ++launches;
+                }
             } else {
                 CK(h, cudaMemsetAsync(d_rowmax, 0, (size_t)nu * kFPad * 4, st));
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
@@ -1378,7 +1397,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 sa.n_units = nu; sa.T = g.T; sa.nf = nf; sa.nt = nt; sa.tf_lo = tf_lo; sa.tf_hi = tf_hi; sa.TT = 32;
                 sa.bits = d_bits; sa.rowflag = d_rowflag; sa.num = d_num;
                 const int ntaps = 2 * nf + 1;
-                if (nt + 1 <= 14 && ntaps <= 36) {
+                if (h->reuse_masks) {
+                    // the numerators of the last forward are still in d_num
+                } else if (nt + 1 <= 14 && ntaps <= 36) {
                     SmoothPArgs pa{};
                     pa.n_units = nu; pa.T = g.T; pa.nf = nf; pa.nt = nt; pa.tf_lo = tf_lo; pa.tf_hi = tf_hi;
                     pa.bits = d_bits; pa.rowflag = d_rowflag; pa.num = d_num;
@@ -1523,9 +1544,11 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
             } else {
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-                launch_k1n(g, tb, xb, kdt, d_mag, dbg, resident, st, d_zcache, tf_lo, tf_hi + 1);
+                launch_k1n(g, tb, xb, kdt, h->reuse_masks ? nullptr : d_mag, dbg, resident, st, d_zcache, tf_lo, tf_hi + 1);
                 cudaEventRecord(h->stage_ev[4 * bi + 1], st);
-                if (torch_sem) {
+                if (h->reuse_masks) {
+                    // the final masks of the last forward are still in d_mag
+                } else if (torch_sem) {
                     TMovArgs ma{};
                     ma.n_units = nu; ma.T = g.T; ma.n_movemean = p.n_movemean; ma.n_thresh = (float)p.thresh_n_mult;
                     ma.inv_temp = (float)p.sigmoid_slope; ma.p = (float)p.prop_decrease; ma.mag = d_mag; ma.m0 = d_m0;
@@ -1552,7 +1575,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     sa.p = torch_sem ? 1.0f : (float)p.prop_decrease;
                     sa.one_minus_p = torch_sem ? 0.0f : (float)(1.0 - p.prop_decrease);
                     sa.m0 = d_m0; sa.m2 = d_mag;
-                    if (smooths_smem_bytes(sa.FPad, nf, nt) <= 200 * 1024 && !(p.path_flags & 32)) {
+                    if (h->reuse_masks) {
+                        // masks of the last forward
+                    } else if (smooths_smem_bytes(sa.FPad, nf, nt) <= 200 * 1024 && !(p.path_flags & 32)) {
                         sa.TT = 256;                    // frames per strip (2 nt warm-up rows each)
                         const int strips = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
                         B200_LAUNCH(k_smooth_stream, dim3(strips, nu), dim3(sa.FPad / 4), smooths_smem_bytes(sa.FPad, nf, nt), st, sa);
@@ -1661,6 +1686,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     h->stats.kernel_launches = launches;
     h->stats.fused_path = use_fused ? 1 : 0;
     h->stats_pending = true;
+    if (torch_sem && !generic && !two_k && n_batches == 1 && !h->reuse_masks) {
+        h->masks_valid = true; h->masks_C = C; h->masks_N = N;
+    }
     h->pend_batches = n_batches;
     h->pend_fused = use_fused;
     if (use_fused) {
@@ -1685,6 +1713,19 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     return B200GATE_OK;
 }
 
+
+int b200gate_torch_apply_masks(b200gate_handle* h, const void* in, void* out, int dtype, int64_t C, int64_t N, int64_t in_stride,
+                               int64_t out_stride, int is_device, void* stream) {
+    if (!h) return B200GATE_ERR_ARG;
+    if (h->p.surface != B200GATE_SURFACE_TORCH) return fail(h, B200GATE_ERR_STATE, "torch surface only");
+    if (!h->masks_valid || h->masks_C != C || h->masks_N != N)
+        return fail(h, B200GATE_ERR_STATE, "no masks of a matching forward are kept (run b200gate_run on [%lld][%lld] first; "
+                    "tuned n_fft=1024 geometry, one workspace batch)", (long long)C, (long long)N);
+    h->reuse_masks = true;
+    const int rc = b200gate_run(h, in, out, dtype, C, N, in_stride, out_stride, is_device, stream);
+    h->reuse_masks = false;
+    return rc;
+}
 
 // ---- multi-GPU: kernel-issued NVLink stores (gate_peer.cuh) ---------------------------------------------------------
 int b200gate_peer_push(const void* src, void* const* peer_dst, int32_t n_peers, int64_t rows, int64_t row_bytes,

@@ -1017,6 +1017,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
 #pragma unroll
                 for (int q = 0; q < 32; ++q) zp[32 * q] = make_float2(re[brev5(q)], im[brev5(q)]);
             }
+            if (!a.mag && a.dbg.ul != ul) continue;        // spectra only
             float* dstA = a.mag + ((long long)ul * g.T + t) * kFPad;
 #pragma unroll
             for (int q = 0; q < kFW; ++q) {
@@ -1031,8 +1032,10 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude(const K1nArgs a) {
                 const bool valid = (q < 16) || (lane == 0);
                 const float ma = valid ? 0.5f * sqrtf(fmaf(ar, ar, ai * ai)) : 0.f;
                 const float mb = valid ? 0.5f * sqrtf(fmaf(br, br, bi * bi)) : 0.f;
-                dstA[k] = ma;
-                if (vb) dstA[kFPad + k] = mb;
+                if (a.mag) {                               // (null: spectra only -- b200gate_torch_apply_masks)
+                    dstA[k] = ma;
+                    if (vb) dstA[kFPad + k] = mb;
+                }
                 if (a.dbg.ul == ul && valid && k < kF) {
                     float* sp = a.dbg.spec + ((long long)t * kF + k) * 2;
                     sp[0] = 0.5f * ar; sp[1] = 0.5f * ai;

@@ -30,12 +30,24 @@ def reduce_noise(
 
     y : np.ndarray, shape (# frames,) or (# channels, # frames); the result has the same shape and
     dtype.  ``n_jobs``, ``tmp_folder`` and ``use_tqdm`` are accepted and ignored: the chunk loop they
-    steer in the reference runs as one GPU grid here.  ``use_torch=True`` selects the same CUDA
-    backend (the reference's torch route is its own GPU port, not a different algorithm family);
-    the reference's argument check for it is kept.  There is no CPU path.
+    steer in the reference runs as one GPU grid here.  ``use_torch=True`` takes the reference's torch route
+    (noisereduce.py:121-143 -> StreamedTorchGate): every padded chunk through TorchGate -- a different gate from
+    the numpy one (torch.stft framing, per-chunk self statistics, top_db 40, moving-mean follower; see
+    spectralgate/streamed_torch_gate.py) -- on ``device``, which must be a CUDA device.  There is no CPU path.
     """
-    if use_torch and n_jobs != 1:                               # noisereduce.py:115-118
-        raise ValueError("n_jobs must be 1 when using torch version of spectral gating.")
+    if use_torch:
+        if n_jobs != 1:                                         # noisereduce.py:115-118
+            raise ValueError("n_jobs must be 1 when using torch version of spectral gating.")
+        from .spectralgate.streamed_torch_gate import StreamedTorchGate
+        sg = StreamedTorchGate(                                 # (n_std_thresh_stationary is not forwarded, as in the reference)
+            y=y, sr=sr, stationary=stationary, y_noise=y_noise, prop_decrease=prop_decrease,
+            time_constant_s=time_constant_s, freq_mask_smooth_hz=freq_mask_smooth_hz,
+            time_mask_smooth_ms=time_mask_smooth_ms, thresh_n_mult_nonstationary=thresh_n_mult_nonstationary,
+            sigmoid_slope_nonstationary=sigmoid_slope_nonstationary, tmp_folder=tmp_folder, chunk_size=chunk_size,
+            padding=padding, n_fft=n_fft, win_length=win_length, hop_length=hop_length,
+            clip_noise_stationary=clip_noise_stationary, use_tqdm=use_tqdm, n_jobs=n_jobs, device=device,
+        )
+        return sg.get_traces()
     if stationary:
         sg = SpectralGateStationary(
             y=y, sr=sr, y_noise=y_noise, prop_decrease=prop_decrease,
