@@ -263,9 +263,21 @@ def same_run_parity(np, torch, dg, x, out, n_chunks=48):
     filt = O.smoothing_filter(nf, nt)
     chans = [c for c in (0, 31, 63) if c < C]
     chunks = [k for k in (0, 1, n_chunks - 1) if k < n_chunks]
-    worst, flips_own, flips_inj, bins = 0.0, 0, 0, 0
     ymax = float(out.abs().max().item())
     scratch = torch.empty_like(out[:2])
+    refs = {}
+
+    def compare(tag):
+        worst = 0.0
+        for ch in chans:
+            for ck in chunks:
+                o_lo, o_hi = ck * cs, min((ck + 1) * cs, n)
+                i1 = ck * cs - pad
+                got = out[ch, o_lo:o_hi].cpu().numpy().astype(np.float64)
+                worst = max(worst, float(np.abs(got - refs[(ch, ck)][0][o_lo - i1: o_hi - i1]).max()) / max(ymax, 1e-30))
+        return worst
+
+    flips_own = flips_inj = bins = 0
     for ch in chans:
         for ck in chunks:
             i1, i2 = ck * cs - pad, (ck + 1) * cs + pad
@@ -274,30 +286,39 @@ def same_run_parity(np, torch, dg, x, out, n_chunks=48):
             xc[lo - i1: hi - i1] = x[ch, lo:hi].cpu().numpy()
             taps = O.Taps()
             yref = O.gate_stationary_unit(xc.astype(np.float64), thresh, cfg, filt, taps)
-            o_lo, o_hi = ck * cs, min((ck + 1) * cs, n)
-            got = out[ch, o_lo:o_hi].cpu().numpy().astype(np.float64)
-            ref = yref[o_lo - i1: o_hi - i1]
-            worst = max(worst, float(np.abs(got - ref).max()) / max(ymax, 1e-30))
-            # mask decisions of this unit: tap a 2-channel run (the dual kernels need an even channel count)
-            c0 = ch - (ch & 1)
-            for inject in (False, True):
-                if inject:
-                    dg.gate.set_noise_threshold(thresh)
+            refs[(ch, ck)] = (yref, taps.mask0)
+            bins += taps.mask0.size
+    out_own = compare("own")                       # `out` still holds the timed result (library's own thresholds)
+    # mask decisions: tap a 2-channel run per unit (the dual kernels pair channels), own and injected thresholds
+    for inject in (False, True):
+        if inject:
+            dg.gate.set_noise_threshold(thresh)
+        for ch in chans:
+            for ck in chunks:
+                c0 = ch - (ch & 1)
                 dg.gate.debug_select_unit(ck, ch - c0)
                 dg.run(x[c0: c0 + 2], scratch)
                 d = dg.gate.debug_read()
-                nb = int(np.count_nonzero(d["mask0"] != taps.mask0))
+                nb = int(np.count_nonzero(d["mask0"] != refs[(ch, ck)][1]))
                 if inject:
                     flips_inj += nb
                 else:
                     flips_own += nb
-                    bins += taps.mask0.size
-            dg.gate.debug_select_unit(-1, 0)
-            dg.gate.set_noise_threshold(own)
-    return {"out_relinf": worst, "mask_flips_own_thresholds": flips_own, "mask_flips_injected_thresholds": flips_inj,
+        dg.gate.debug_select_unit(-1, 0)
+    # the whole workload once more with the reference's thresholds injected: decisions then agree bit for bit
+    dg.run(x, out)
+    torch.cuda.synchronize()
+    out_inj = compare("injected")
+    dg.gate.set_noise_threshold(own)
+    return {"out_relinf": out_inj, "out_relinf_own_thresholds": out_own,
+            "mask_flips_injected_thresholds": flips_inj, "mask_flips_own_thresholds": flips_own,
             "bins": bins, "units": len(chans) * len(chunks),
             "thresholds_max_abs_diff_db": float(np.abs(own - thresh).max()),
-            "subsets": "channels {0,31,63} x chunks {0,1,47} of the timed tensor; oracle float64; thresholds of the full 64-ch clip"}
+            "subsets": "channels {0,31,63} x chunks {0,1,47} of the timed tensor; oracle float64; thresholds of the full 64-ch clip",
+            "note": "the reference transforms a float32 noise clip in float32 (scipy keeps the input precision), this library in "
+                    "float64: the thresholds differ by ~1e-5 dB and a bin whose level sits inside that gap decides differently "
+                    "(own-threshold flips, each a local waveform difference); with the reference's thresholds injected "
+                    "(b200gate_set_noise_threshold) every decision is bit-equal and the waveform agrees to float32 rounding"}
 
 
 def main():

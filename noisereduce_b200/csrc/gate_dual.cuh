@@ -307,16 +307,11 @@ struct K1dArgs {
 };
 
 constexpr int kK1dTableBytes = kN * 4 + kN * 8 + 2 * kFPad * 4;
-#ifndef B200_K1D_STAGE
-#define B200_K1D_STAGE 0              // float32 sample rows bulk-copied (TMA) one pair ahead
-#endif
-constexpr int kK1dRowBytes = B200_K1D_STAGE ? 32 * (32 + 8) * 4 : 0;           // one unit's 40 sample rows of a pair (float32)
-constexpr int kK1dWarpBytes = 2 * kK1dRowBytes + kExchDual * 8 + 4 * kFW * 4 + 16;
+constexpr int kK1dWarpBytes = kN * 16 + kExchDual * 8 + 4 * kFW * 4 + 16;     // dual spectrum, exchange tile, guard-band words
 constexpr int k1d_smem_bytes() { return kK1dTableBytes + kDualWarpsK1 * kK1dWarpBytes; }
 
 template <int HR, typename T>
 __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArgs a) {
-    constexpr bool kStage = sizeof(T) == 4 && B200_K1D_STAGE;       // float32 rows are bulk-copied (TMA) one pair ahead
     B200_DYN_SMEM(unsigned char, smraw);
     float* s_wa = reinterpret_cast<float*>(smraw);
     float2* s_tw = reinterpret_cast<float2*>(smraw + kN * 4);
@@ -324,11 +319,9 @@ __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArg
     float* s_gco = s_thr4 + kFPad;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = smraw + kK1dTableBytes + warp * kK1dWarpBytes;
-    const float* sA = reinterpret_cast<const float*>(wbase);
-    const float* sB = reinterpret_cast<const float*>(wbase + kK1dRowBytes);
-    f2* tile = reinterpret_cast<f2*>(wbase + 2 * kK1dRowBytes);
-    unsigned* s_amb = reinterpret_cast<unsigned*>(wbase + 2 * kK1dRowBytes + kExchDual * 8);      // [4][FW]
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(wbase + 2 * kK1dRowBytes + kExchDual * 8 + 4 * kFW * 4);
+    f2x2* zs = reinterpret_cast<f2x2*>(wbase);                                    // [1024] the pair's dual spectrum
+    f2* tile = reinterpret_cast<f2*>(wbase + kN * 16);
+    unsigned* s_amb = reinterpret_cast<unsigned*>(wbase + kN * 16 + kExchDual * 8);      // [4][FW]
     const int nthr = kDualWarpsK1 * 32;
     for (int i = threadIdx.x; i < kN; i += nthr) {
         s_wa[i] = a.tb.wa[i];
@@ -338,14 +331,10 @@ __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArg
         s_thr4[i] = a.tb.thr4[i];
         s_gco[i] = a.tb.gco[i];
     }
-    if (lane == 0) mbar_init(bar, 1);
-    mbar_init_fence();
     __syncthreads();
-    unsigned phase = 0;
 
     const Geom& g = a.g;
     const int H = g.H;
-    const int pl = (32 - lane) & 31;                 // partner lane holding the mirrored bins
     const int n_duals = g.n_units >> 1;
     const long long n_items = (long long)n_duals * a.n_runs;
 
@@ -363,40 +352,14 @@ __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArg
         const int t1 = min(t0 + a.run, g.T);
         float emax = 0.f;                                   // largest frame-energy bound of this run (row floor test)
 
-        // request pair tt's 40 rows of both units (interior of the chunk and the recording, 16-byte aligned)
-        auto stage_rows = [&](int tt) -> bool {
-            if (!kStage) return false;
-            const long long bb = (long long)tt * H - kN / 2;
-            if (!pair_window_interior<HR>(bb, i1, g.Lp, g.n_total)) return false;
-            const T* srcA = xrowA + i1 + bb;
-            const T* srcB = xrowB + i1 + bb;
-            if (((reinterpret_cast<unsigned long long>(srcA) | reinterpret_cast<unsigned long long>(srcB)) & 15ull) != 0) return false;
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_expect_tx(bar, 2u * kK1dRowBytes);
-                bulk_g2s(wbase, srcA, kK1dRowBytes, bar);
-                bulk_g2s(wbase + kK1dRowBytes, srcB, kK1dRowBytes, bar);
-            }
-            return true;
-        };
-        bool staged = stage_rows(t0);
-
         for (int t = t0; t < t1; t += 2) {
             const bool vb = (t + 1 < t1);
             const long long base = (long long)t * H - kN / 2;
-            f2 re[32], im[32];
             float S_A, S_B;
             {
-                f2 xr[32 + HR];
-                if (staged) {                                  // warp-uniform
-                    mbar_wait(bar, phase);
-                    phase ^= 1u;
-#pragma unroll
-                    for (int r = 0; r < 32 + HR; ++r) xr[r] = f2_pack(sA[32 * r + lane], sB[32 * r + lane]);
-                    __syncwarp();
-                    staged = (t + 2 < t1) && stage_rows(t + 2);
-                } else {
+                f2 re[32], im[32];
+                {
+                    f2 xr[32 + HR];
                     if (pair_window_interior<HR>(base, i1, g.Lp, g.n_total)) {
                         const T* pA = xrowA + i1 + base + lane;
                         const T* pB = xrowB + i1 + base + lane;
@@ -408,92 +371,87 @@ __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArg
                             xr[r] = f2_pack(chunk_sample(xrowA, base + lane + 32 * r, i1, g.Lp, g.n_total),
                                             chunk_sample(xrowB, base + lane + 32 * r, i1, g.Lp, g.n_total));
                     }
-                    staged = (t + 2 < t1) && stage_rows(t + 2);
+                    f2 e2 = f2_dup(0.f);
+#pragma unroll
+                    for (int r = 0; r < 32 + HR; ++r) e2 = f2_fma(xr[r], xr[r], e2);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) e2 = f2_add(e2, __shfl_xor_sync(0xffffffffu, e2, o));
+                    // every frame's windowed energy <= wa_max^2 * (energy of the pair's 40 rows): S bounds ||frame pair||_2
+                    const float eA = f2_lo(e2) * a.wa_max * a.wa_max, eB = f2_hi(e2) * a.wa_max * a.wa_max;
+                    S_A = sqrtf(2.0f * eA);
+                    S_B = sqrtf(2.0f * eB);
+                    emax = fmaxf(emax, fmaxf(eA, eB));
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float w = s_wa[lane + 32 * r];
+                        re[r] = f2_mul_s(xr[r], w);
+                        im[r] = f2_mul_s(xr[r + HR], vb ? w : 0.f);      // odd frame count: the pair's second frame does not exist
+                    }
                 }
-                f2 e2 = f2_dup(0.f);
-#pragma unroll
-                for (int r = 0; r < 32 + HR; ++r) e2 = f2_fma(xr[r], xr[r], e2);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) e2 = f2_add(e2, __shfl_xor_sync(0xffffffffu, e2, o));
-                // every frame's windowed energy <= wa_max^2 * (energy of the pair's 40 rows): S bounds ||frame pair||_2
-                const float eA = f2_lo(e2) * a.wa_max * a.wa_max, eB = f2_hi(e2) * a.wa_max * a.wa_max;
-                S_A = sqrtf(2.0f * eA);
-                S_B = sqrtf(2.0f * eB);
-                emax = fmaxf(emax, fmaxf(eA, eB));
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const float w = s_wa[lane + 32 * r];
-                    re[r] = f2_mul_s(xr[r], w);
-                    im[r] = f2_mul_s(xr[r + HR], vb ? w : 0.f);      // odd frame count: the pair's second frame does not exist
-                }
-            }
-            warp_fft1024_dual(re, im, tile, s_tw, lane);
-            if (t >= a.z_lo && t < a.z_hi) {                  // warp-uniform
-                f2x2* zp = reinterpret_cast<f2x2*>(a.zd) + ((long long)dl * a.zpairs + (t >> 1)) * 1024 + lane;
+                warp_fft1024_dual(re, im, tile, s_tw, lane);
+                // the spectrum goes to shared memory once: the decisions below read bins and their mirrors from there by flat
+                // index (no shuffles, no lane-0 special case), and ONE bulk copy (TMA store) takes it to the dual cache
+                bulk_wait_read_all();                         // (the previous pair's store has read zs)
+                __syncwarp();
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     f2x2 v;
                     v.a = re[brev5(q)];
                     v.b = im[brev5(q)];
-                    zp[32 * q] = v;
+                    zs[32 * q + lane] = v;
                 }
             }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (t >= a.z_lo && t < a.z_hi && lane == 0)       // warp-uniform condition
+                bulk_s2g(reinterpret_cast<f2x2*>(a.zd) + ((long long)dl * a.zpairs + (t >> 1)) * 1024, zs, kN * 16);
 
             unsigned wAa = 0u, wAb = 0u, wBa = 0u, wBb = 0u;      // lane q keeps word q of (unit, frame)
             unsigned anyamb = 0u;
-#pragma unroll
-            for (int q = 0; q < kFW; ++q) {
-                const int sAq = brev5(q), sP = brev5(31 - q), s0 = brev5((32 - q) & 31);
-                const f2 zr = re[sAq], zi = im[sAq];
-                f2 pr = __shfl_sync(0xffffffffu, re[sP], pl);
-                f2 pi = __shfl_sync(0xffffffffu, im[sP], pl);
-                if (lane == 0) { pr = re[s0]; pi = im[s0]; }
+            const f2 S2 = f2_pack(S_A, S_B);
+            // decisions of bin k of (unit A, unit B) x (frame a, frame b); a missing frame b compares against +inf
+            auto decide = [&](int q, int k, bool valid) {
+                const f2x2 own = zs[k];
+                const f2x2 par = zs[(kN - k) & (kN - 1)];
                 // 2 X_a = Z + conj(Zp),  2 X_b = (Z - conj(Zp)) / i
-                const f2 ar = f2_add(zr, pr), ai = f2_sub(zi, pi);
-                const f2 br = f2_add(zi, pi), bi = f2_sub(pr, zr);
+                const f2 ar = f2_add(own.a, par.a), ai = f2_sub(own.b, par.b);
+                const f2 br = f2_add(own.b, par.b), bi = f2_sub(par.a, own.a);
                 const f2 PA = f2_fma(ar, ar, f2_mul(ai, ai));
                 const f2 PB = f2_fma(br, br, f2_mul(bi, bi));
-                const int k = lane + 32 * q;
-                const bool valid = (q < 16) || (lane == 0);
-                const float th = s_thr4[k], gc = s_gco[k];
-                const float tb = th * 8.0e-7f;
-                const float ggA = fmaf(gc, S_A, tb), ggB = fmaf(gc, S_B, tb);
-                const float dAa = f2_lo(PA) - th, dAb = f2_lo(PB) - th, dBa = f2_hi(PA) - th, dBb = f2_hi(PB) - th;
-                const unsigned bAa = __ballot_sync(0xffffffffu, valid && (dAa > 0.f));
-                const unsigned bAb = __ballot_sync(0xffffffffu, valid && vb && (dAb > 0.f));
-                const unsigned bBa = __ballot_sync(0xffffffffu, valid && (dBa > 0.f));
-                const unsigned bBb = __ballot_sync(0xffffffffu, valid && vb && (dBb > 0.f));
+                const float th = valid ? s_thr4[k] : INFINITY;                 // (invalid lanes of the N/2 slot: never set, never ambiguous)
+                const float thb = vb ? th : INFINITY;
+                // guard band of (unit A, unit B); -1 on the invalid lanes of the N/2 slot (never ambiguous: their "bins" do not exist)
+                const f2 gg = f2_fma_s(S2, valid ? s_gco[k] : 0.f, f2_dup(valid ? th * 8.0e-7f : -1.0f));
+                const f2 dA = f2_add(PA, f2_dup(-th)), dB = f2_add(PB, f2_dup(-thb));
+                const float dAa = f2_lo(dA), dBa = f2_hi(dA), dAb = f2_lo(dB), dBb = f2_hi(dB);
+                const float ggA = f2_lo(gg), ggB = f2_hi(gg);
+                const unsigned bAa = __ballot_sync(0xffffffffu, dAa > 0.f);
+                const unsigned bAb = __ballot_sync(0xffffffffu, dAb > 0.f);
+                const unsigned bBa = __ballot_sync(0xffffffffu, dBa > 0.f);
+                const unsigned bBb = __ballot_sync(0xffffffffu, dBb > 0.f);
                 if (lane == q) { wAa = bAa; wAb = bAb; wBa = bBa; wBb = bBb; }
-                const bool mAa = valid && fabsf(dAa) <= ggA, mAb = valid && vb && fabsf(dAb) <= ggA;
-                const bool mBa = valid && fabsf(dBa) <= ggB, mBb = valid && vb && fabsf(dBb) <= ggB;
+                const bool mAa = fabsf(dAa) <= ggA, mAb = fabsf(dAb) <= ggA;     // (|-inf| <= gg is false; inf - inf = NaN compares false)
+                const bool mBa = fabsf(dBa) <= ggB, mBb = fabsf(dBb) <= ggB;
                 if (__any_sync(0xffffffffu, mAa || mAb || mBa || mBb)) {      // rare: remember the bins inside the guard band
                     const unsigned x0 = __ballot_sync(0xffffffffu, mAa), x1 = __ballot_sync(0xffffffffu, mAb);
                     const unsigned x2 = __ballot_sync(0xffffffffu, mBa), x3 = __ballot_sync(0xffffffffu, mBb);
                     anyamb |= 1u << q;
                     if (lane == 0) { s_amb[q] = x0; s_amb[kFW + q] = x1; s_amb[2 * kFW + q] = x2; s_amb[3 * kFW + q] = x3; }
                 }
-            }
+            };
+#pragma unroll 2
+            for (int q = 0; q < 16; ++q) decide(q, 32 * q + lane, true);
+            decide(16, 512 + lane, lane == 0);                 // bin N/2 (lane 0); the other lanes' slots hold mirrored bins
             if (a.dbg.ul == ulA || a.dbg.ul == ulA + 1) {    // parity tap (tests): the FP32 STFT itself
                 const bool hi = a.dbg.ul == ulA + 1;
 #pragma unroll 1
-                for (int q = 0; q < kFW; ++q) {
-                    float zr = 0.f, zi = 0.f, pr = 0.f, pi = 0.f;
-#pragma unroll
-                    for (int qq = 0; qq < kFW; ++qq)
-                        if (qq == q) {
-                            const f2 zr2 = re[brev5(qq)], zi2 = im[brev5(qq)];
-                            f2 pr2 = __shfl_sync(0xffffffffu, re[brev5(31 - qq)], pl);
-                            f2 pi2 = __shfl_sync(0xffffffffu, im[brev5(31 - qq)], pl);
-                            if (lane == 0) { pr2 = re[brev5((32 - qq) & 31)]; pi2 = im[brev5((32 - qq) & 31)]; }
-                            zr = hi ? f2_hi(zr2) : f2_lo(zr2); zi = hi ? f2_hi(zi2) : f2_lo(zi2);
-                            pr = hi ? f2_hi(pr2) : f2_lo(pr2); pi = hi ? f2_hi(pi2) : f2_lo(pi2);
-                        }
-                    const int k = lane + 32 * q;
-                    if (((q < 16) || lane == 0) && k < kF) {
-                        float* sp = a.dbg.spec + ((long long)t * kF + k) * 2;
-                        sp[0] = 0.5f * (zr + pr); sp[1] = 0.5f * (zi - pi);
-                        if (vb) { sp[2 * kF] = 0.5f * (zi + pi); sp[2 * kF + 1] = 0.5f * (pr - zr); }
-                    }
+                for (int k = lane; k < kF; k += 32) {
+                    const f2x2 own = zs[k], par = zs[(kN - k) & (kN - 1)];
+                    const float zr = hi ? f2_hi(own.a) : f2_lo(own.a), zi = hi ? f2_hi(own.b) : f2_lo(own.b);
+                    const float pr = hi ? f2_hi(par.a) : f2_lo(par.a), pi = hi ? f2_hi(par.b) : f2_lo(par.b);
+                    float* sp = a.dbg.spec + ((long long)t * kF + k) * 2;
+                    sp[0] = 0.5f * (zr + pr); sp[1] = 0.5f * (zi - pi);
+                    if (vb) { sp[2 * kF] = 0.5f * (zi + pi); sp[2 * kF + 1] = 0.5f * (pr - zr); }
                 }
             }
             if (anyamb) {                             // warp-uniform, rare: redo those bins in float64
@@ -512,8 +470,11 @@ __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArg
                             ++nre;
                             if (r == 0) { ++nun; continue; }
                             if (lane == q) {
-                                unsigned& wd = uf == 0 ? wAa : uf == 1 ? wAb : uf == 2 ? wBa : wBb;
-                                wd = (r == 2) ? (wd | (1u << src)) : (wd & ~(1u << src));
+                                const unsigned bit = 1u << src;
+                                if (uf == 0) wAa = (r == 2) ? (wAa | bit) : (wAa & ~bit);
+                                else if (uf == 1) wAb = (r == 2) ? (wAb | bit) : (wAb & ~bit);
+                                else if (uf == 2) wBa = (r == 2) ? (wBa | bit) : (wBa & ~bit);
+                                else wBb = (r == 2) ? (wBb | bit) : (wBb & ~bit);
                             }
                         }
                     }
@@ -535,6 +496,7 @@ __global__ void __launch_bounds__(kDualWarpsK1 * 32, 1) k1d_analyze(const K1dArg
         // |X|^2 <= N * (frame energy): could any bin of this run have reached its top_db floor?
         if (4.0f * (float)kN * emax >= 0.999f * a.min_floor4 && lane == 0) atomicOr(a.need_rowmax, 1u);
     }
+    bulk_wait_read_all();                                     // no bulk store may outlive the CTA's shared memory
 }
 
 }  // namespace b200

@@ -77,6 +77,22 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
+// shared -> global bulk copy (TMA store engine) of `bytes` (16-byte multiple, both sides 16-byte aligned); completion is
+// tracked by bulk groups: commit, then wait_group.read before the shared source is overwritten
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+#ifdef B200_CUSIM_BUILD
+    memcpy(gmem_dst, smem_src, bytes);
+#else
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_wait_read_all() {
+#ifndef B200_CUSIM_BUILD
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
 #ifdef B200_CUSIM_BUILD
     const unsigned long long v = ((unsigned long long)b << 32) | a;
