@@ -306,12 +306,18 @@ def same_run_parity(np, torch, dg, x, out, n_chunks=48):
                     flips_own += nb
         dg.gate.debug_select_unit(-1, 0)
     # the whole workload once more with the reference's thresholds injected: decisions then agree bit for bit
+    own_rows = out[:8].clone()                   # (8 of the 64 channels, all 48 chunks, of the own-threshold result)
     dg.run(x, out)
     torch.cuda.synchronize()
     out_inj = compare("injected")
+    dfull = (out[:8] - own_rows).abs()
+    full_diff = {"channels": 8, "samples": int(dfull.numel()), "samples_differing": int((dfull > 0).sum().item()),
+                 "max_abs_over_ymax": float(dfull.max().item()) / max(ymax, 1e-30)}
+    del own_rows, dfull
     dg.gate.set_noise_threshold(own)
     return {"out_relinf": out_inj, "out_relinf_own_thresholds": out_own,
             "mask_flips_injected_thresholds": flips_inj, "mask_flips_own_thresholds": flips_own,
+            "own_vs_injected_thresholds_8ch": full_diff,
             "bins": bins, "units": len(chans) * len(chunks),
             "thresholds_max_abs_diff_db": float(np.abs(own - thresh).max()),
             "subsets": "channels {0,31,63} x chunks {0,1,47} of the timed tensor; oracle float64; thresholds of the full 64-ch clip",
@@ -382,7 +388,7 @@ def main():
     #   nccl   all-gather kernels per channel group on a side stream
     transport = os.environ.get("B200GATE_GATHER", "store") if world > 1 else None
     reserve = int(os.environ.get("B200GATE_RESERVE_SMS", "12"))
-    push_ctas = int(os.environ.get("B200GATE_PUSH_CTAS", str(3 * reserve)))
+    push_ctas = int(os.environ.get("B200GATE_PUSH_CTAS", str(reserve)))       # one SM-filling CTA per reserved SM
     groups = int(os.environ.get("B200GATE_GROUPS", "8"))
     ps = pg = None
     if world > 1 and transport in ("store", "peer"):
@@ -556,10 +562,6 @@ def main():
         "exactness": {k: stats[k] for k in ("bins_rechecked_fp64", "bins_unresolved", "rowfloor_flags", "rowfloor_ambiguous")},
     }
     if n_gpus == 1 and not args.no_extras:
-        try:
-            line["parity"] = same_run_parity(np, torch, dg, x, out)
-        except Exception as exc:
-            line["parity"] = {"error": repr(exc)[:200]}
         # ---- the user-facing call on a pageable numpy array ---------------------------------------------
         try:
             import noisereduce_b200 as nrb
@@ -575,6 +577,10 @@ def main():
             del res, ynp
         except Exception as exc:
             line["e2e_numpy"] = {"value": None, "error": repr(exc)[:200]}
+        try:
+            line["parity"] = same_run_parity(np, torch, dg, x, out)
+        except Exception as exc:
+            line["parity"] = {"error": repr(exc)[:200]}
         # ---- BASELINE configs 3 and 4 -----------------------------------------------------------------
         extra = {}
         try:

@@ -171,7 +171,8 @@ int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out);
  * the next group is computed; a device-side barrier over the flag arrays (world uint32 each, zero-initialised,
  * `epoch` strictly increasing per call) ends the step.  On return everything is enqueued; after `compute_stream`
  * reaches this point `gathered_local` holds every rank's rows.  gathered_peers[r] / flags_peers[r] are this rank's
- * mappings of rank r's buffers (entry [rank] is ignored / the local array).  push_ctas <= 0 picks a default. */
+ * mappings of rank r's buffers (entry [rank] is ignored / the local array).  push_ctas = the number of SMs the copy kernel
+ * occupies (each of its CTAs fills one SM; create the handle with reserve_sms >= push_ctas); <= 0 picks 12. */
 int b200gate_run_sharded(b200gate_handle* h, const void* in_local, int dtype, int64_t C_local, int64_t N,
                          int64_t in_stride, void* gathered_local, void* const* gathered_peers, void* flags_local,
                          void* const* flags_peers, uint32_t epoch, int32_t rank, int32_t world, int32_t groups,

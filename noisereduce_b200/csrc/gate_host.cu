@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace b200;
@@ -28,7 +29,7 @@ namespace {
 const double kEps64 = 2.220446049250313e-16;       // np.finfo(np.float64).eps (spectralgate/utils.py:11)
 const double kEps32 = 5.9604644775390625e-08;      // 2^-24, FP32 unit roundoff
 const double kKappa = 16.0;                        // guard band: |dX| <= kappa * eps32 * ||frame pair||_2
-std::string g_create_error;
+thread_local std::string g_create_error;          // one handle per thread: a failed create reports through the calling thread
 
 }  // namespace
 
@@ -92,6 +93,10 @@ struct b200gate_handle {
     std::vector<cudaEvent_t> stage_ev;             // 4 per batch: analysis start, analysis end, smoothing end, synthesis end
     std::vector<cudaEvent_t> pipe_ev;              // 4 per batch: input landed, compute done, output landed, seam copied
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // pipelined host path
+    void* hp_in[2] = {nullptr, nullptr};           // pinned staging slabs for pageable host rows (pipelined path)
+    void* hp_out[2] = {nullptr, nullptr};
+    size_t hp_in_bytes[2] = {0, 0}, hp_out_bytes[2] = {0, 0};
+    int host_threads = 16;
     void* d_slab_in[2] = {nullptr, nullptr};       // caller-dtype slabs
     void* d_slab_out[2] = {nullptr, nullptr};
     size_t slab_in_bytes[2] = {0, 0}, slab_out_bytes[2] = {0, 0};
@@ -496,6 +501,41 @@ void launch_k1n(const Geom& g, const Tables& tb, const void* x, int kdt, float* 
                     k1n_smem_floats() * 4, st, a1); });
 }
 
+// Pageable host memory: cudaMemcpyAsync from / to it is neither asynchronous nor fast (the driver bounces it through a small
+// pinned buffer at ~10 GB/s), and pinning a caller's 7 GB array in place costs a second (measured: cudaHostRegister 8.5 GB/s).
+// The slab pipeline therefore stages pageable rows through its own pinned slabs with a handful of host threads
+// (measured 60-70 GB/s with 8-16 threads), which keeps PCIe busy.
+bool host_pointer_is_pinned(const void* p) {
+#ifdef B200_CUSIM_BUILD
+    (void)p;
+    return false;                                  // simulator: exercise the staging path
+#else
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+#endif
+}
+void parallel_rows_copy(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, int nthreads) {
+    if (rows == 0 || width == 0) return;
+    // split every row into pieces of >= 1 MB so that few long rows still spread over all threads
+    const size_t piece = std::max<size_t>(1 << 20, (width * rows / (size_t)std::max(1, nthreads) + 4095) / 4096 * 4096);
+    const size_t per_row = (width + piece - 1) / piece;
+    const size_t n_pieces = per_row * rows;
+    const int nt = (int)std::min<size_t>((size_t)std::max(1, nthreads), n_pieces);
+    auto work = [&](int id) {
+        for (size_t k = (size_t)id; k < n_pieces; k += (size_t)nt) {
+            const size_t r = k / per_row, off = (k - r * per_row) * piece;
+            memcpy((char*)dst + r * dpitch + off, (const char*)src + r * spitch + off, std::min(piece, width - off));
+        }
+    };
+    if (nt == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)nt - 1);
+    for (int i = 1; i < nt; ++i) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+}
+
 // Fill h->stats from the last run's stream-ordered counter copy and stage events (blocks until that run is done).
 int resolve_stats(b200gate_handle* h) {
     if (!h->stats_pending) return B200GATE_OK;
@@ -584,19 +624,19 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     h->F = want_generic ? p->n_fft / 2 + 1 : (p->n_fft == kN2 ? kF2 : kF);
     int rc = want_generic ? build_generic_tables(h) : build_static_tables(h);
     if (rc == B200GATE_OK) {
-        cudaMalloc((void**)&h->d_maxabs, sizeof(unsigned));
-        e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
-        if (e != cudaSuccess) rc = fail(h, B200GATE_ERR_CUDA, "cudaMalloc counters: %s", cudaGetErrorString(e));
+        e = cudaMalloc((void**)&h->d_maxabs, sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_need_rowmax, sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_cnt, sizeof(Counters));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_maxabs, sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->ev_done);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
+        if (e != cudaSuccess) rc = fail(h, B200GATE_ERR_CUDA, "handle resources: %s", cudaGetErrorString(e));
     }
     if (rc == B200GATE_OK) {
-        cudaEventCreate(&h->ev0);
-        cudaEventCreate(&h->ev1);
-        cudaEventCreate(&h->ev_done);
-        cudaMalloc((void**)&h->d_need_rowmax, sizeof(unsigned));
-        cudaMallocHost((void**)&h->h_cnt, sizeof(Counters));
-        cudaMallocHost((void**)&h->h_maxabs, sizeof(unsigned));
-        cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
 #ifndef B200_CUSIM_BUILD
         for (int dt = 0; dt < 3; ++dt)
             B200_WITH_DTYPE(dt, {
@@ -645,6 +685,7 @@ void b200gate_destroy(b200gate_handle* h) {
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     for (cudaEvent_t e : h->group_ev) cudaEventDestroy(e);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    for (int i = 0; i < 2; ++i) { if (h->hp_in[i]) cudaFreeHost(h->hp_in[i]); if (h->hp_out[i]) cudaFreeHost(h->hp_out[i]); }
     if (h->d_need_rowmax) cudaFree(h->d_need_rowmax);
     if (h->h_maxabs) cudaFreeHost(h->h_maxabs);
     for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
@@ -1027,12 +1068,30 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t g_tf = (size_t)g.T * (size_t)h->F, g_tw = (size_t)g.T * (size_t)h->g_W;
     const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + 2 * (size_t)h->F * 8 + 6 * 256;
     const size_t per_unit = generic ? per_unit_generic : (use_fused ? 64 : per_unit_2pass + zunit);   // the fused kernel keeps no per-unit buffers
-    double limit = p.workspace_limit_bytes > 0 ? p.workspace_limit_bytes : 24.0 * 1024 * 1024 * 1024;
+    // default workspace: up to 24 GiB, never more than 70 % of what is free now (plus what this handle already holds)
+    double limit = p.workspace_limit_bytes;
+    if (!(limit > 0)) {
+        limit = 24.0 * 1024 * 1024 * 1024;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            limit = std::min(limit, 0.7 * ((double)free_b + (double)h->ws_bytes));
+    }
     long long ub = (long long)std::max(1.0, floor(limit / (double)per_unit));
     ub = std::min(ub, U);
     if (use_dual) ub = std::max(2LL, ub & ~1LL);             // duals are units (2d, 2d+1) of a batch
     if (generic) ub = std::min(ub, 65535LL);                 // gk_* put the unit on gridDim.y
+    // reserve the workspace now; if the device cannot give it (the caller's own tensors may fill HBM), halve the batch
+    for (;;) {
+        const size_t est = (size_t)ub * per_unit + ((size_t)8 << 20);
+        if (ensure(h, (void**)&h->d_ws_buf, &h->ws_bytes, est) == B200GATE_OK) break;
+        cudaGetLastError();
+        long long nub = ub / 2;
+        if (use_dual) nub &= ~1LL;
+        if (nub < (use_dual ? 2 : 1)) return B200GATE_ERR_NOMEM;     // (message set by ensure)
+        ub = nub;
+    }
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
+    bool stage_in = false, stage_out = false;
     if (pipelined) {
         // ~256 MB of input per slab (measured on B200 + PCIe Gen5: 160-320 MB best, profiles/r01_e2e_slab_sweep.md), whole chunks, within the workspace limit
         long long slab_bytes = 256LL << 20;
@@ -1048,6 +1107,23 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             if ((rc = ensure(h, (void**)&h->d_slab_in[i], &h->slab_in_bytes[i], (size_t)C * slab_w * es))) return rc;
             if ((rc = ensure(h, (void**)&h->d_slab_out[i], &h->slab_out_bytes[i], (size_t)C * slab_ow * es))) return rc;
         }
+        stage_in = !host_pointer_is_pinned(in);
+        stage_out = !host_pointer_is_pinned(out);
+        for (int i = 0; i < 2; ++i) {                  // pinned staging slabs for pageable caller memory
+            if (stage_in && h->hp_in_bytes[i] < (size_t)C * slab_w * es) {
+                if (h->hp_in[i]) cudaFreeHost(h->hp_in[i]);
+                h->hp_in[i] = nullptr; h->hp_in_bytes[i] = 0;
+                CK(h, cudaMallocHost(&h->hp_in[i], (size_t)C * slab_w * es));
+                h->hp_in_bytes[i] = (size_t)C * slab_w * es;
+            }
+            if (stage_out && h->hp_out_bytes[i] < (size_t)C * slab_ow * es) {
+                if (h->hp_out[i]) cudaFreeHost(h->hp_out[i]);
+                h->hp_out[i] = nullptr; h->hp_out_bytes[i] = 0;
+                CK(h, cudaMallocHost(&h->hp_out[i], (size_t)C * slab_ow * es));
+                h->hp_out_bytes[i] = (size_t)C * slab_ow * es;
+            }
+        }
+        if (const char* e = getenv("B200GATE_HOST_THREADS")) h->host_threads = std::max(1, atoi(e));
     }
     // carve the workspace into 256-byte aligned sub-buffers (vector stores need natural alignment)
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -1142,6 +1218,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     }
     size_t bi = 0;
     int nu_prev = 0;
+    long long prev_o0 = 0, prev_o1 = 0;
     cudaEventRecord(evk0, st);
     for (long long u0 = 0; u0 < U; u0 += ub, ++bi) {
         const int nu = (int)std::min(ub, U - u0);
@@ -1160,10 +1237,20 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             // [pw1, w1) over PCIe, so every sample crosses the bus once.
             const long long pw1 = bi == 0 ? w0 : std::min<long long>(N, c0 * g.step + g.pad);
             if (bi >= 1) CK(h, cudaStreamWaitEvent(h->s_h2d, h->pipe_ev[4 * (bi - 1) + 3], 0));   // slab buffer free
-            if (w1 > pw1)
-                CK(h, cudaMemcpy2DAsync((char*)h->d_slab_in[ib] + (size_t)(pw1 - w0) * es, (size_t)slab_w * es,
-                                        (const char*)in + (size_t)pw1 * es, (size_t)in_stride * es, (size_t)(w1 - pw1) * es,
-                                        (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
+            if (w1 > pw1) {
+                const void* src = (const char*)in + (size_t)pw1 * es;
+                size_t spitch = (size_t)in_stride * es;
+                if (stage_in) {
+                    // pageable rows: host threads copy them into this slab's pinned staging buffer (free once the H2D of
+                    // slab bi-2 has completed), the copy engine takes them from there
+                    if (bi >= 2) CK(h, cudaEventSynchronize(h->pipe_ev[4 * (bi - 2) + 0]));
+                    parallel_rows_copy(h->hp_in[ib], (size_t)(w1 - pw1) * es, src, spitch, (size_t)(w1 - pw1) * es, (size_t)C, h->host_threads);
+                    src = h->hp_in[ib];
+                    spitch = (size_t)(w1 - pw1) * es;
+                }
+                CK(h, cudaMemcpy2DAsync((char*)h->d_slab_in[ib] + (size_t)(pw1 - w0) * es, (size_t)slab_w * es, src, spitch,
+                                        (size_t)(w1 - pw1) * es, (size_t)C, cudaMemcpyHostToDevice, h->s_h2d));
+            }
             CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 0], h->s_h2d));
             if (bi >= 1 && pw1 > w0) {
                 const long long pw0 = std::max(0LL, (c0 - nu_prev / C) * g.step - g.pad);           // previous window start
@@ -1359,6 +1446,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     K1dArgs ad{};
                     ad.g = g; ad.tb = tb; ad.x = xb; ad.bits = d_bits; ad.zd = (float4*)d_zcache; ad.zpairs = zpairs;
                     ad.z_lo = tf_lo; ad.z_hi = tf_hi + 1; ad.cnt = h->d_cnt; ad.need_rowmax = h->d_need_rowmax;
+                    if (getenv("B200GATE_DBG_NOCACHE_STORE")) ad.z_hi = 0;        // timing experiment only: results are wrong
                     ad.min_floor4 = (float)(4.0 * h->min_floor_amp * h->min_floor_amp);
                     ad.wa_max = h->wa_max; ad.dbg = dbg;
                     {
@@ -1631,9 +1719,24 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             const void* d2h_src = h->d_slab_out[ib];
             CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 1], st));
             CK(h, cudaStreamWaitEvent(h->s_d2h, h->pipe_ev[4 * bi + 1], 0));
-            CK(h, cudaMemcpy2DAsync((char*)out + (size_t)o0 * es, (size_t)out_stride * es, d2h_src, (size_t)slab_ow * es,
-                                    (size_t)(o1 - o0) * es, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
-            CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 2], h->s_d2h));
+            if (stage_out) {
+                // pageable result rows: D2H into this slab's pinned staging buffer (its previous content, slab bi-2, was
+                // copied out by the host below), then the host threads move slab bi-1 -- whose D2H has had a whole slab of
+                // kernel time -- into the caller's array
+                CK(h, cudaMemcpy2DAsync(h->hp_out[ib], (size_t)(o1 - o0) * es, d2h_src, (size_t)slab_ow * es,
+                                        (size_t)(o1 - o0) * es, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
+                CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 2], h->s_d2h));
+                if (bi >= 1) {
+                    CK(h, cudaEventSynchronize(h->pipe_ev[4 * (bi - 1) + 2]));
+                    parallel_rows_copy((char*)out + (size_t)prev_o0 * es, (size_t)out_stride * es, h->hp_out[ib ^ 1],
+                                       (size_t)(prev_o1 - prev_o0) * es, (size_t)(prev_o1 - prev_o0) * es, (size_t)C, h->host_threads);
+                }
+                prev_o0 = o0; prev_o1 = o1;
+            } else {
+                CK(h, cudaMemcpy2DAsync((char*)out + (size_t)o0 * es, (size_t)out_stride * es, d2h_src, (size_t)slab_ow * es,
+                                        (size_t)(o1 - o0) * es, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
+                CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 2], h->s_d2h));
+            }
             nu_prev = nu;
         }
     }
@@ -1641,6 +1744,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     if (pipelined) {
         CK(h, cudaStreamSynchronize(h->s_d2h));
         CK(h, cudaStreamSynchronize(h->s_h2d));
+        if (stage_out && bi >= 1)                      // the last slab's rows
+            parallel_rows_copy((char*)out + (size_t)prev_o0 * es, (size_t)out_stride * es, h->hp_out[(bi - 1) & 1],
+                               (size_t)(prev_o1 - prev_o0) * es, (size_t)(prev_o1 - prev_o0) * es, (size_t)C, h->host_threads);
         if (getenv("B200GATE_TRACE")) {                       // slab timeline (ms since the first launch) on stderr
             CK(h, cudaStreamSynchronize(st));
             for (size_t b = 0; b < n_batches; ++b) {
@@ -1741,8 +1847,10 @@ int b200gate_peer_push(const void* src, void* const* peer_dst, int32_t n_peers, 
     }
     a.n_dst = n_peers;
     a.rows = rows; a.vec_per_row = row_bytes / 16; a.src_stride = src_stride_bytes / 16; a.dst_stride = dst_stride_bytes / 16;
-    const int ctas = n_ctas > 0 ? n_ctas : 16;
-    B200_LAUNCH(k_peer_push, dim3(ctas), dim3(512), 0, (cudaStream_t)stream, a);
+    const int ctas = n_ctas > 0 ? n_ctas : 12;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_peer_push, cudaFuncAttributeMaxDynamicSharedMemorySize, kPushSmemBytes); attr_set = true; }
+    B200_LAUNCH(k_peer_push, dim3(ctas), dim3(kPushThreads), kPushSmemBytes, (cudaStream_t)stream, a);
     return cudaGetLastError() == cudaSuccess ? B200GATE_OK : B200GATE_ERR_CUDA;
 }
 

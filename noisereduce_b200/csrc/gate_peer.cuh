@@ -24,31 +24,33 @@ struct PushArgs {
     long long src_stride, dst_stride;   // row pitches in vectors
 };
 
-__global__ void __launch_bounds__(512) k_peer_push(const PushArgs a) {
-    const long long total = a.rows * a.vec_per_row;
+// One k_peer_push CTA owns a whole SM (1024 threads + a dynamic shared-memory request no other CTA fits beside): the
+// hardware block scheduler otherwise spreads small copy CTAs over as many SMs as it can, and every SM holding one cannot
+// take a gate CTA (k1d / k2d need an SM's whole register file) -- measured: any co-running small-CTA copy kernel, ours or
+// NCCL's, doubled k1d's time.  R fat CTAs block exactly R SMs; the gate kernels' grids are sized for the rest.
+constexpr int kPushThreads = 1024;
+constexpr int kPushSmemBytes = 200 * 1024;
+constexpr int kPushUnroll = 12;              // 16-byte vectors in flight per thread (128 bytes): the copy is latency bound
+
+__global__ void __launch_bounds__(kPushThreads, 1) k_peer_push(const PushArgs a) {
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * step) {
-        uint4 v[4];
-        long long so[4], doff[4];
-        bool ok[4];
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long r = 0; r < a.rows; ++r) {
+        const uint4* s = a.src + r * a.src_stride;
+        const long long drow = r * a.dst_stride;
+        for (long long c = first; c < a.vec_per_row; c += kPushUnroll * step) {
+            uint4 v[kPushUnroll];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long j = i + u * step;
-            ok[u] = j < total;
-            const long long r = ok[u] ? j / a.vec_per_row : 0;
-            const long long c = ok[u] ? j - r * a.vec_per_row : 0;
-            so[u] = r * a.src_stride + c;
-            doff[u] = r * a.dst_stride + c;
-        }
+            for (int u = 0; u < kPushUnroll; ++u)
+                if (c + u * step < a.vec_per_row) v[u] = s[c + u * step];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (ok[u]) v[u] = a.src[so[u]];
+            for (int p = 0; p < kMaxPeers; ++p) {
+                if (p < a.n_dst) {
+                    uint4* d = a.dst[p] + drow + c;
 #pragma unroll
-        for (int p = 0; p < kMaxPeers; ++p) {
-            if (p < a.n_dst) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (ok[u]) a.dst[p][doff[u]] = v[u];
+                    for (int u = 0; u < kPushUnroll; ++u)
+                        if (c + u * step < a.vec_per_row) d[u * step] = v[u];
+                }
             }
         }
     }

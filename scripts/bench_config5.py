@@ -43,25 +43,33 @@ def main():
     for p0 in range(0, n, piece):
         p1 = min(n, p0 + piece)
         x[:, p0:p1] = synth_device(torch, C, p1 - p0, rank * C + p0 // piece, dev)
-    use_peer = world > 1 and os.environ.get("B200GATE_GATHER", "peer") == "peer"
+    transport = os.environ.get("B200GATE_GATHER", "store") if world > 1 else "none"
+    reserve = int(os.environ.get("B200GATE_RESERVE_SMS", "12"))
+    use_peer = transport == "peer"
     dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256, chunk_size=cs, padding=30000,
-                    reserve_sms=16 if (world > 1 and not use_peer) else 0, workspace_limit_bytes=48e9)
+                    reserve_sms=(reserve if transport == "store" else 16 if transport == "nccl" else 0), workspace_limit_bytes=48e9)
     if world == 1:
         dg.noise_stats(x)
     else:
         chained_noise_stats(dg, x, rank, world)
     comm = torch.cuda.Stream()
-    pg = None
-    if world > 1 and os.environ.get("B200GATE_GATHER", "peer") == "peer":
+    pg = ps = None
+    if use_peer:
         from noisereduce_b200.parallel import PeerGather
         pg = PeerGather(world, rank, (2, world, C, args.slab_chunks * cs), torch.float32, dev)
-    buffers = make_slab_ring(C, args.slab_chunks * cs, world, torch.float32, dev) if pg is None else None
+    elif transport == "store":
+        from noisereduce_b200.parallel import PeerStore
+        ps = PeerStore(world, rank, (2, world, C, args.slab_chunks * cs), torch.float32, dev)
+    buffers = make_slab_ring(C, args.slab_chunks * cs, world, torch.float32, dev) if (pg is None and ps is None) else None
     sums = []
 
     def consume(g, first, si):
         return g.sum(dtype=torch.float64)            # stays on the device; read after the timed region
 
     def step():
+        if ps is not None:
+            from noisereduce_b200.parallel import slab_ring_peer_store
+            return slab_ring_peer_store(dg, x, world, args.slab_chunks, consume, ps, push_ctas=reserve)
         return sharded_run_slab_ring(dg, x, world, comm, slab_chunks=args.slab_chunks, consume=consume, buffers=buffers, peer=pg)
 
     def barrier():
@@ -99,7 +107,7 @@ def main():
                                        f"channel-sharded 64 ch/GPU, slab-ring all-gather (configs[4])",
                            "channels_per_gpu": C, "samples_per_channel": n, "chunk_size": cs, "padding": 30000,
                            "slab_chunks": args.slab_chunks, "shard_bytes_in_hbm": C * n * 4,
-                           "gather_transport": "peer-copy-engine" if pg is not None else ("nccl" if world > 1 else "none")},
+                           "gather_transport": {"store": "kernel-nvlink-stores", "peer": "peer-copy-engine", "nccl": "nccl", "none": "none"}[transport]},
                 "all_gather_bytes_received_per_rank": gathered_bytes,
                 "all_gather_GBps_per_rank": gathered_bytes / (ms * 1e-3) / 1e9,
                 "slab_checksum_total": float(checks.sum()), "slabs": len(sums), "checksums_agree_across_ranks": agree,

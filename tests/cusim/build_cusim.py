@@ -21,7 +21,7 @@ def build(force=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DB200_CUSIM_BUILD",
-           "-Wno-unknown-pragmas", "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+           "-Wno-unknown-pragmas", "-pthread", "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"),
            "-x", "c++", os.path.join(CSRC, "gate_host.cu"), os.path.join(HERE, "cusim.cpp"), "-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
