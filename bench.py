@@ -386,8 +386,10 @@ def main():
     #   store  kernel-issued NVLink stores (b200gate_run_sharded: k_peer_push on reserved SMs + device-side barrier)
     #   peer   copy-engine pushes into symmetric memory (round 1)
     #   nccl   all-gather kernels per channel group on a side stream
-    transport = os.environ.get("B200GATE_GATHER", "store") if world > 1 else None
-    reserve = int(os.environ.get("B200GATE_RESERVE_SMS", "12"))
+    # defaults from the measured A/B (profiles/r02_scaling.md): at N = 2 the copy engines hide the 7.4 GB push completely and
+    # cost no SMs; from N = 4 on the step is bound by the NVLink port and the copy kernel (more SMs at N = 8) wins
+    transport = os.environ.get("B200GATE_GATHER", "peer" if world == 2 else "store") if world > 1 else None
+    reserve = int(os.environ.get("B200GATE_RESERVE_SMS", {2: "12", 4: "16"}.get(world, "32")))
     push_ctas = int(os.environ.get("B200GATE_PUSH_CTAS", str(reserve)))       # one SM-filling CTA per reserved SM
     groups = int(os.environ.get("B200GATE_GROUPS", "8"))
     ps = pg = None

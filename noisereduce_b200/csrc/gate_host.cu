@@ -18,6 +18,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <future>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -37,6 +39,7 @@ struct b200gate_handle {
     b200gate_params p{};
     std::string err;
     int num_sm = 148;
+    int device = 0;
     int F = kF;
     // device tables
     float *d_wa = nullptr, *d_ws = nullptr, *d_invn = nullptr, *d_thr4 = nullptr, *d_gco = nullptr,
@@ -96,7 +99,7 @@ struct b200gate_handle {
     void* hp_in[2] = {nullptr, nullptr};           // pinned staging slabs for pageable host rows (pipelined path)
     void* hp_out[2] = {nullptr, nullptr};
     size_t hp_in_bytes[2] = {0, 0}, hp_out_bytes[2] = {0, 0};
-    int host_threads = 16;
+    int host_threads = 24;
     void* d_slab_in[2] = {nullptr, nullptr};       // caller-dtype slabs
     void* d_slab_out[2] = {nullptr, nullptr};
     size_t slab_in_bytes[2] = {0, 0}, slab_out_bytes[2] = {0, 0};
@@ -536,6 +539,36 @@ void parallel_rows_copy(void* dst, size_t dpitch, const void* src, size_t spitch
     for (auto& t : th) t.join();
 }
 
+// Pinned staging slabs are expensive to create (cudaMallocHost of 1 GB: ~0.2 s) and independent of the handle's parameters:
+// they live in a small process-wide pool, borrowed for one run and returned (a handle is created per reduce_noise() call).
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<void*, size_t>> free_list;
+    void* take(size_t bytes, size_t* got) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].second >= bytes) {
+                    void* p = free_list[i].first;
+                    *got = free_list[i].second;
+                    free_list.erase(free_list.begin() + (long)i);
+                    return p;
+                }
+        }
+        void* p = nullptr;
+        if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *got = bytes;
+        return p;
+    }
+    void give(void* p, size_t bytes) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_list.size() >= 8) { cudaFreeHost(p); return; }
+        free_list.emplace_back(p, bytes);
+    }
+};
+PinnedPool g_pinned_pool;
+
 // Fill h->stats from the last run's stream-ordered counter copy and stage events (blocks until that run is done).
 int resolve_stats(b200gate_handle* h) {
     if (!h->stats_pending) return B200GATE_OK;
@@ -612,6 +645,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     h->p = *p;
     int dev = 0;
     cudaGetDevice(&dev);
+    h->device = dev;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) h->num_sm = prop.multiProcessorCount;
     if (p->reserve_sms > 0 && p->reserve_sms < h->num_sm) h->num_sm -= p->reserve_sms;   // leave room for NCCL
@@ -685,7 +719,7 @@ void b200gate_destroy(b200gate_handle* h) {
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     for (cudaEvent_t e : h->group_ev) cudaEventDestroy(e);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
-    for (int i = 0; i < 2; ++i) { if (h->hp_in[i]) cudaFreeHost(h->hp_in[i]); if (h->hp_out[i]) cudaFreeHost(h->hp_out[i]); }
+    for (int i = 0; i < 2; ++i) { g_pinned_pool.give(h->hp_in[i], h->hp_in_bytes[i]); g_pinned_pool.give(h->hp_out[i], h->hp_out_bytes[i]); }
     if (h->d_need_rowmax) cudaFree(h->d_need_rowmax);
     if (h->h_maxabs) cudaFreeHost(h->h_maxabs);
     for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
@@ -1109,18 +1143,16 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         }
         stage_in = !host_pointer_is_pinned(in);
         stage_out = !host_pointer_is_pinned(out);
-        for (int i = 0; i < 2; ++i) {                  // pinned staging slabs for pageable caller memory
+        for (int i = 0; i < 2; ++i) {                  // pinned staging slabs for pageable caller memory (process-wide pool)
             if (stage_in && h->hp_in_bytes[i] < (size_t)C * slab_w * es) {
-                if (h->hp_in[i]) cudaFreeHost(h->hp_in[i]);
-                h->hp_in[i] = nullptr; h->hp_in_bytes[i] = 0;
-                CK(h, cudaMallocHost(&h->hp_in[i], (size_t)C * slab_w * es));
-                h->hp_in_bytes[i] = (size_t)C * slab_w * es;
+                g_pinned_pool.give(h->hp_in[i], h->hp_in_bytes[i]);
+                h->hp_in[i] = g_pinned_pool.take((size_t)C * slab_w * es, &h->hp_in_bytes[i]);
+                if (!h->hp_in[i]) { h->hp_in_bytes[i] = 0; return fail(h, B200GATE_ERR_NOMEM, "pinned staging slab (%zu bytes)", (size_t)C * slab_w * es); }
             }
             if (stage_out && h->hp_out_bytes[i] < (size_t)C * slab_ow * es) {
-                if (h->hp_out[i]) cudaFreeHost(h->hp_out[i]);
-                h->hp_out[i] = nullptr; h->hp_out_bytes[i] = 0;
-                CK(h, cudaMallocHost(&h->hp_out[i], (size_t)C * slab_ow * es));
-                h->hp_out_bytes[i] = (size_t)C * slab_ow * es;
+                g_pinned_pool.give(h->hp_out[i], h->hp_out_bytes[i]);
+                h->hp_out[i] = g_pinned_pool.take((size_t)C * slab_ow * es, &h->hp_out_bytes[i]);
+                if (!h->hp_out[i]) { h->hp_out_bytes[i] = 0; return fail(h, B200GATE_ERR_NOMEM, "pinned staging slab (%zu bytes)", (size_t)C * slab_ow * es); }
             }
         }
         if (const char* e = getenv("B200GATE_HOST_THREADS")) h->host_threads = std::max(1, atoi(e));
@@ -1219,6 +1251,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     size_t bi = 0;
     int nu_prev = 0;
     long long prev_o0 = 0, prev_o1 = 0;
+    std::future<void> out_task;
     cudaEventRecord(evk0, st);
     for (long long u0 = 0; u0 < U; u0 += ub, ++bi) {
         const int nu = (int)std::min(ub, U - u0);
@@ -1244,7 +1277,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     // pageable rows: host threads copy them into this slab's pinned staging buffer (free once the H2D of
                     // slab bi-2 has completed), the copy engine takes them from there
                     if (bi >= 2) CK(h, cudaEventSynchronize(h->pipe_ev[4 * (bi - 2) + 0]));
-                    parallel_rows_copy(h->hp_in[ib], (size_t)(w1 - pw1) * es, src, spitch, (size_t)(w1 - pw1) * es, (size_t)C, h->host_threads);
+                    parallel_rows_copy(h->hp_in[ib], (size_t)(w1 - pw1) * es, src, spitch, (size_t)(w1 - pw1) * es, (size_t)C,
+                                       stage_out ? std::max(1, h->host_threads / 2) : h->host_threads);
                     src = h->hp_in[ib];
                     spitch = (size_t)(w1 - pw1) * es;
                 }
@@ -1720,6 +1754,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
             CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 1], st));
             CK(h, cudaStreamWaitEvent(h->s_d2h, h->pipe_ev[4 * bi + 1], 0));
             if (stage_out) {
+                if (out_task.valid()) out_task.get();       // slab bi-2 has left this staging buffer
                 // pageable result rows: D2H into this slab's pinned staging buffer (its previous content, slab bi-2, was
                 // copied out by the host below), then the host threads move slab bi-1 -- whose D2H has had a whole slab of
                 // kernel time -- into the caller's array
@@ -1727,9 +1762,17 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                                         (size_t)(o1 - o0) * es, (size_t)C, cudaMemcpyDeviceToHost, h->s_d2h));
                 CK(h, cudaEventRecord(h->pipe_ev[4 * bi + 2], h->s_d2h));
                 if (bi >= 1) {
-                    CK(h, cudaEventSynchronize(h->pipe_ev[4 * (bi - 1) + 2]));
-                    parallel_rows_copy((char*)out + (size_t)prev_o0 * es, (size_t)out_stride * es, h->hp_out[ib ^ 1],
-                                       (size_t)(prev_o1 - prev_o0) * es, (size_t)(prev_o1 - prev_o0) * es, (size_t)C, h->host_threads);
+                    // runs beside the next slab's copy-in (joined before that slab's D2H is enqueued into this staging buffer's twin)
+                    cudaEvent_t evd = h->pipe_ev[4 * (bi - 1) + 2];
+                    void* dstp = (char*)out + (size_t)prev_o0 * es;
+                    const void* srcp = h->hp_out[ib ^ 1];
+                    const size_t wbytes = (size_t)(prev_o1 - prev_o0) * es, dp = (size_t)out_stride * es;
+                    const int nth = std::max(1, h->host_threads / 2), dev_now = h->device;
+                    out_task = std::async(std::launch::async, [evd, dstp, srcp, wbytes, dp, C, nth, dev_now]() {
+                        cudaSetDevice(dev_now);
+                        cudaEventSynchronize(evd);
+                        parallel_rows_copy(dstp, dp, srcp, wbytes, wbytes, (size_t)C, nth);
+                    });
                 }
                 prev_o0 = o0; prev_o1 = o1;
             } else {
@@ -1744,6 +1787,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     if (pipelined) {
         CK(h, cudaStreamSynchronize(h->s_d2h));
         CK(h, cudaStreamSynchronize(h->s_h2d));
+        if (out_task.valid()) out_task.get();
         if (stage_out && bi >= 1)                      // the last slab's rows
             parallel_rows_copy((char*)out + (size_t)prev_o0 * es, (size_t)out_stride * es, h->hp_out[(bi - 1) & 1],
                                (size_t)(prev_o1 - prev_o0) * es, (size_t)(prev_o1 - prev_o0) * es, (size_t)C, h->host_threads);

@@ -584,7 +584,7 @@ __device__ __forceinline__ unsigned dp4a_u(unsigned a, unsigned b, unsigned c) {
 }
 
 template <int NTW>
-__global__ void __launch_bounds__(kSmoothThreads) k_smooth_packed(const SmoothPArgs a) {
+__global__ void __launch_bounds__(kSmoothThreads, 3) k_smooth_packed(const SmoothPArgs a) {
     constexpr int RB = smoothp_rowbytes<NTW>();
     constexpr int NB = kSmoothBatch;
     B200_DYN_SMEM(unsigned char, s_raw);                      // [2][NB][4 units][RB]

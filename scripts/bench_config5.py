@@ -44,7 +44,7 @@ def main():
         p1 = min(n, p0 + piece)
         x[:, p0:p1] = synth_device(torch, C, p1 - p0, rank * C + p0 // piece, dev)
     transport = os.environ.get("B200GATE_GATHER", "store") if world > 1 else "none"
-    reserve = int(os.environ.get("B200GATE_RESERVE_SMS", "12"))
+    reserve = int(os.environ.get("B200GATE_RESERVE_SMS", {2: "12", 4: "16"}.get(world, "32")))
     use_peer = transport == "peer"
     dg = DeviceGate(sr=SR, stationary=True, n_fft=1024, hop_length=256, chunk_size=cs, padding=30000,
                     reserve_sms=(reserve if transport == "store" else 16 if transport == "nccl" else 0), workspace_limit_bytes=48e9)
