@@ -569,14 +569,25 @@ def main():
             import noisereduce_b200 as nrb
             ynp = x.cpu().numpy()
             nrb.reduce_noise(y=ynp[:2], sr=SR, stationary=True, n_fft=1024, hop_length=256)
-            t0 = time.perf_counter()
-            res = nrb.reduce_noise(y=ynp, sr=SR, stationary=True, n_fft=1024, hop_length=256)
-            dt = time.perf_counter() - t0
+            calls = []
+            ref_np = ref_out.cpu().numpy()
+            perr = None
+            for rep in range(4):                                # call 0 = first full-size call of the process (cold pools)
+                t0 = time.perf_counter()
+                res = nrb.reduce_noise(y=ynp, sr=SR, stationary=True, n_fft=1024, hop_length=256)
+                calls.append(time.perf_counter() - t0)
+                if perr is None:
+                    perr = float(np.abs(res - ref_np).max())
+                del res                                         # a caller that keeps every result gets fresh buffers instead
+            dt = sorted(calls[1:])[len(calls[1:]) // 2]
             line["e2e_numpy"] = {"value": C * n / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
+                                 "first_call_ms": calls[0] * 1e3, "calls_ms": [c * 1e3 for c in calls],
                                  "call": "noisereduce_b200.reduce_noise(y=float32[64, 28.8M] pageable ndarray, stationary=True)",
-                                 "includes": "noise statistics, pageable H2D / D2H, output allocation",
-                                 "parity_vs_device_path": float(np.abs(res - ref_out.cpu().numpy()).max())}
-            del res, ynp
+                                 "includes": "noise statistics, staging of the pageable input through pinned slabs, H2D / D2H, result array",
+                                 "note": "value = median of calls 2-4: the result array is leased from the library's pinned-buffer pool "
+                                         "(b200gate_host_alloc), which the first call has to fill (first_call_ms)",
+                                 "parity_vs_device_path": perr}
+            del ynp, ref_np
         except Exception as exc:
             line["e2e_numpy"] = {"value": None, "error": repr(exc)[:200]}
         try:

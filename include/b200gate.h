@@ -24,6 +24,7 @@
 #ifndef B200GATE_H
 #define B200GATE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -157,6 +158,15 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
 int b200gate_set_range(b200gate_handle* h, int32_t mode, int64_t a, int64_t b);
 
 int b200gate_get_stats(const b200gate_handle* h, b200gate_stats* out);
+
+/* Page-locked host buffers from the library's process-wide pool (the same pool the slab pipeline stages pageable
+ * caller memory through).  A result array the reference would np.empty() (base.py:181-187 uses a temp-file memmap)
+ * can be leased here instead: b200gate_run then copies device -> host straight into it at PCIe speed, with no page
+ * faults and no staging copy, and a freed buffer is handed to the next call of the same size without paying
+ * cudaMallocHost (~0.1 s per GB) again.  b200gate_host_alloc returns NULL when the memory cannot be pinned (callers fall
+ * back to ordinary memory); b200gate_host_free(NULL) is a no-op.  Thread-safe. */
+void* b200gate_host_alloc(size_t bytes);
+void b200gate_host_free(void* p);
 
 /* ---- multi-GPU (one process per GPU) ---------------------------------------------------
  * The path's one collective -- the all-gather of the final waveform -- is done with NVLink stores issued by a kernel

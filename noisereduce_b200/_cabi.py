@@ -28,6 +28,7 @@ EXPORTS = [
     "b200gate_run", "b200gate_set_range", "b200gate_get_stats", "b200gate_debug_select_unit", "b200gate_debug_dims",
     "b200gate_debug_read_bits", "b200gate_debug_read_mask", "b200gate_debug_read_spec",
     "b200gate_run_sharded", "b200gate_peer_push", "b200gate_peer_barrier", "b200gate_torch_apply_masks",
+    "b200gate_host_alloc", "b200gate_host_free",
 ]
 
 
@@ -105,6 +106,10 @@ class GateLibrary:
         d.b200gate_run_sharded.argtypes = [vp, vp, C.c_int, i64, i64, i64, vp, pvp, vp, pvp, C.c_uint32, i32, i32, i32, i32, vp, vp]
         d.b200gate_peer_push.argtypes = [vp, pvp, i32, i64, i64, i64, i64, i32, vp]
         d.b200gate_peer_barrier.argtypes = [vp, pvp, i32, i32, C.c_uint32, vp]
+        d.b200gate_host_alloc.argtypes = [C.c_size_t]
+        d.b200gate_host_alloc.restype = vp
+        d.b200gate_host_free.argtypes = [vp]
+        d.b200gate_host_free.restype = None
 
 
 def peer_push(lib, src_ptr, peer_ptrs, rows, row_bytes, src_stride_bytes, dst_stride_bytes, n_ctas, stream):
@@ -119,6 +124,58 @@ def peer_barrier(lib, flags_local, flags_peers, rank, world, epoch, stream):
     rc = lib.dll.b200gate_peer_barrier(flags_local, arr, rank, world, epoch, stream)
     if rc != 0:
         raise GateError(rc, "b200gate_peer_barrier")
+
+
+# ---- result arrays in page-locked memory ---------------------------------------------------------------------------
+# A fresh np.empty() result of several GB is written through page faults and a staging copy; a buffer leased from the
+# library's pinned pool (b200gate_host_alloc) takes the device -> host copy directly and is reused by the next call once
+# the caller has dropped the previous result.  Small results and anything beyond the budget stay ordinary arrays.
+PINNED_RESULT_MIN_BYTES = 32 << 20
+_pinned_leased_bytes = 0
+
+
+def _pinned_budget_bytes() -> int:
+    env = os.environ.get("B200GATE_PINNED_RESULT_LIMIT")
+    if env is not None:
+        return int(float(env))
+    try:
+        return int(os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") * 0.25)
+    except (ValueError, OSError):
+        return 8 << 30
+
+
+class _PinnedLease:
+    """Owns one b200gate_host_alloc buffer; the ndarray built on it keeps this object alive through its base chain."""
+
+    def __init__(self, lib: "GateLibrary", nbytes: int):
+        global _pinned_leased_bytes
+        self.lib, self.nbytes = lib, nbytes
+        self.ptr = lib.dll.b200gate_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("b200gate_host_alloc")
+        _pinned_leased_bytes += nbytes
+
+    def __del__(self):
+        global _pinned_leased_bytes
+        if getattr(self, "ptr", None):
+            self.lib.dll.b200gate_host_free(self.ptr)
+            _pinned_leased_bytes -= self.nbytes
+            self.ptr = None
+
+
+def result_empty(lib: "GateLibrary", shape, dtype) -> np.ndarray:
+    """np.empty(shape, dtype) -- in pooled page-locked memory when the array is large and the budget allows."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes >= PINNED_RESULT_MIN_BYTES and _pinned_leased_bytes + nbytes <= _pinned_budget_bytes():
+        try:
+            lease = _PinnedLease(lib, nbytes)
+        except MemoryError:
+            return np.empty(shape, dtype)
+        buf = (C.c_char * nbytes).from_address(lease.ptr)
+        buf._b200_lease = lease              # frombuffer keeps `buf` alive, `buf` keeps the lease: freed with the last view
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return np.empty(shape, dtype)
 
 
 _LIB: Optional[GateLibrary] = None
@@ -217,7 +274,7 @@ class Gate:
     def run_host(self, y2d: np.ndarray, out: Optional[np.ndarray] = None, stream=None) -> np.ndarray:
         y2d = np.ascontiguousarray(y2d)
         if out is None:
-            out = np.empty_like(y2d)
+            out = result_empty(self.lib, y2d.shape, y2d.dtype)
         self._check(self.lib.dll.b200gate_run(
             self._h, y2d.ctypes.data, out.ctypes.data, dtype_code(y2d.dtype), y2d.shape[0], y2d.shape[1],
             y2d.shape[1], out.shape[1], 0, stream))

@@ -7,7 +7,9 @@
 #include "gate_kernels_2k.cuh"
 #include "gate_fused.cuh"
 #include "gate_synth.cuh"
+#include "gate_synth_2k.cuh"
 #include "gate_dual.cuh"
+#include "gate_dual_2k.cuh"
 #include "gate_peer.cuh"
 #include "gate_generic.cuh"
 
@@ -504,6 +506,36 @@ void launch_k1n(const Geom& g, const Tables& tb, const void* x, int kdt, float* 
                     k1n_smem_floats() * 4, st, a1); });
 }
 
+// Float-mask smoothing (non-stationary gate, TorchGate moving-mean gate): the box form for 1 <= nf <= 12 (k_smooth_box,
+// compiled per nf), else the tap-loop streaming kernel, else (ring too large for shared memory) the tile kernel.
+#define B200_SMOOTH_BOX_CASE(NF_) case NF_: { auto kern_ = k_smooth_box<NF_>; \
+        if (set_attr) cudaFuncSetAttribute(kern_, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+        else B200_LAUNCH(kern_, grid, dim3(sa.FPad / 4), smem, st, sa); } break;
+static void smooth_box_dispatch(const SmoothFArgs& sa, int nf, dim3 grid, size_t smem, cudaStream_t st, bool set_attr) {
+    switch (nf) {
+        B200_SMOOTH_BOX_CASE(1) B200_SMOOTH_BOX_CASE(2) B200_SMOOTH_BOX_CASE(3) B200_SMOOTH_BOX_CASE(4)
+        B200_SMOOTH_BOX_CASE(5) B200_SMOOTH_BOX_CASE(6) B200_SMOOTH_BOX_CASE(7) B200_SMOOTH_BOX_CASE(8)
+        B200_SMOOTH_BOX_CASE(9) B200_SMOOTH_BOX_CASE(10) B200_SMOOTH_BOX_CASE(11) B200_SMOOTH_BOX_CASE(12)
+        default: break;
+    }
+}
+static void launch_smooth_float(SmoothFArgs sa, int nf, int nt, int tf_lo, int tf_hi, int nu, int path_flags, cudaStream_t st) {
+    const bool box_ok = nf >= 1 && nf <= 12 && sa.FPad - sa.F >= 12 && smoothb_smem_bytes(sa.FPad, nt) <= 200 * 1024 &&
+                        !(path_flags & 32) && !(path_flags & 128);
+    if (box_ok) {
+        sa.TT = 256;                        // frames per strip (2 nt warm-up rows each)
+        const int strips = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+        smooth_box_dispatch(sa, nf, dim3(strips, nu), smoothb_smem_bytes(sa.FPad, nt), st, false);
+    } else if (smooths_smem_bytes(sa.FPad, nf, nt) <= 200 * 1024 && !(path_flags & 32)) {
+        sa.TT = 256;
+        const int strips = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+        B200_LAUNCH(k_smooth_stream, dim3(strips, nu), dim3(sa.FPad / 4), smooths_smem_bytes(sa.FPad, nf, nt), st, sa);
+    } else {
+        const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
+        B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+    }
+}
+
 // Pageable host memory: cudaMemcpyAsync from / to it is neither asynchronous nor fast (the driver bounces it through a small
 // pinned buffer at ~10 GB/s), and pinning a caller's 7 GB array in place costs a second (measured: cudaHostRegister 8.5 GB/s).
 // The slab pipeline therefore stages pageable rows through its own pinned slabs with a handful of host threads
@@ -544,16 +576,22 @@ void parallel_rows_copy(void* dst, size_t dpitch, const void* src, size_t spitch
 struct PinnedPool {
     std::mutex mu;
     std::vector<std::pair<void*, size_t>> free_list;
+    std::vector<std::pair<void*, size_t>> leased;          // b200gate_host_alloc: sizes of the buffers callers hold
+    // best fit, and never a buffer more than twice the request (a 7 GB result buffer must not end up as a 256 MB slab)
     void* take(size_t bytes, size_t* got) {
         {
             std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_list.size();
             for (size_t i = 0; i < free_list.size(); ++i)
-                if (free_list[i].second >= bytes) {
-                    void* p = free_list[i].first;
-                    *got = free_list[i].second;
-                    free_list.erase(free_list.begin() + (long)i);
-                    return p;
-                }
+                if (free_list[i].second >= bytes && free_list[i].second <= 2 * bytes + (1 << 20) &&
+                    (best == free_list.size() || free_list[i].second < free_list[best].second))
+                    best = i;
+            if (best < free_list.size()) {
+                void* p = free_list[best].first;
+                *got = free_list[best].second;
+                free_list.erase(free_list.begin() + (long)best);
+                return p;
+            }
         }
         void* p = nullptr;
         if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -563,8 +601,32 @@ struct PinnedPool {
     void give(void* p, size_t bytes) {
         if (!p) return;
         std::lock_guard<std::mutex> lk(mu);
-        if (free_list.size() >= 8) { cudaFreeHost(p); return; }
+        if (free_list.size() >= 8) {                       // keep the 8 largest
+            size_t smallest = 0;
+            for (size_t i = 1; i < free_list.size(); ++i)
+                if (free_list[i].second < free_list[smallest].second) smallest = i;
+            if (free_list[smallest].second >= bytes) { cudaFreeHost(p); return; }
+            cudaFreeHost(free_list[smallest].first);
+            free_list.erase(free_list.begin() + (long)smallest);
+        }
         free_list.emplace_back(p, bytes);
+    }
+    void* lease(size_t bytes) {
+        size_t got = 0;
+        void* p = take(bytes, &got);
+        if (!p) return nullptr;
+        std::lock_guard<std::mutex> lk(mu);
+        leased.emplace_back(p, got);
+        return p;
+    }
+    void release(void* p) {
+        size_t bytes = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t i = 0; i < leased.size(); ++i)
+                if (leased[i].first == p) { bytes = leased[i].second; leased.erase(leased.begin() + (long)i); break; }
+        }
+        if (bytes) give(p, bytes);
     }
 };
 PinnedPool g_pinned_pool;
@@ -688,8 +750,11 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaFuncSetAttribute(k1_analyze<8, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1_smem_floats_staged() * 4);
         cudaFuncSetAttribute(k_smooth_f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_smooth_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int nfb = 1; nfb <= 12; ++nfb) smooth_box_dispatch(SmoothFArgs{}, nfb, dim3(1), 0, nullptr, true);
         cudaFuncSetAttribute(k1n_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n2_smem_floats() * 4);
         cudaFuncSetAttribute(k2_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k22_smem_floats() * 4);
+        cudaFuncSetAttribute(k2c_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c2_smem_bytes());
+        cudaFuncSetAttribute(k1nd_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1nd2_smem_bytes());
         for (int dt = 0; dt < 3; ++dt)
             B200_WITH_DTYPE(dt, { cudaFuncSetAttribute(k_fused<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kfused_smem_floats() * 4); });
         cudaFuncSetAttribute(k_smooth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -779,6 +844,23 @@ int b200gate_channel_sum(b200gate_handle* h, const void* y, int dtype, int64_t C
                          int is_device, void* acc, int init, void* stream) {
     if (!h || !y || !acc || C <= 0 || n <= 0 || dtype_size(dtype) == 0) return fail(h, B200GATE_ERR_ARG, "bad argument");
     return channel_sum_impl(h, y, dtype, C, n, stride, is_device, acc, init, (cudaStream_t)stream);
+}
+
+void* b200gate_host_alloc(size_t bytes) {
+    if (bytes == 0) return nullptr;
+#ifdef B200_CUSIM_BUILD
+    return malloc(bytes);
+#else
+    return g_pinned_pool.lease(bytes);
+#endif
+}
+void b200gate_host_free(void* p) {
+    if (!p) return;
+#ifdef B200_CUSIM_BUILD
+    free(p);
+#else
+    g_pinned_pool.release(p);
+#endif
 }
 
 int b200gate_noise_stats_collapsed(b200gate_handle* h, const void* noise_mean, int dtype, int64_t n, int is_device,
@@ -1094,8 +1176,9 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                                   (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
     // spectrum cache: k1 / k1n keep the packed spectrum of every frame pair so k2 does not re-transform
     const int zpairs = (g.T + 1) / 2;
-    const bool use_zcache = !use_fused && !two_k && !generic && !(p.path_flags & 2);
-    const size_t zunit = use_zcache ? (size_t)zpairs * 1024 * sizeof(float2) : 0;
+    const bool use_zcache = !use_fused && !generic && !(p.path_flags & 2);
+    // (n_fft 2048: one half-length spectrum per frame; n_fft 1024: one packed spectrum per frame pair)
+    const size_t zunit = use_zcache ? (size_t)(two_k ? g.T : zpairs) * 1024 * sizeof(float2) : 0;
     // dual kernels (gate_dual.cuh): two channels of a chunk per warp -- stationary numpy-surface gate, even channel count
     const bool use_dual = use_zcache && stat && !torch_sem && native && (C % 2 == 0) && !(p.path_flags & 16);
     // general-geometry family: float64 spectrum, mask, scratch and synthesis frames of every unit
@@ -1613,12 +1696,26 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 cudaEventRecord(h->stage_ev[4 * bi + 0], st);
                 K1n2Args a1{};
                 a1.g = g; a1.tb = t2; a1.x = (const float*)xb; a1.mag = d_mag; a1.dbg = dbg;
+                a1.zcache = d_zcache; a1.z_lo = tf_lo; a1.z_hi = tf_hi + 1;
                 {
                     long long want = (long long)resident * kWarps * 4;
                     long long run = ((long long)nu * g.T + want - 1) / want;
                     a1.run = (int)std::max(4LL, std::min(64LL, run));
                     a1.n_runs = (g.T + a1.run - 1) / a1.run;
                 }
+                if (!(p.path_flags & 16)) {               // two frames per warp (gate_dual_2k.cuh)
+                    K1nd2Args ad{};
+                    ad.g = g; ad.tb = t2; ad.x = (const float*)xb; ad.mag = d_mag; ad.dbg = dbg;
+                    ad.zcache = d_zcache; ad.z_lo = tf_lo; ad.z_hi = tf_hi + 1;
+                    long long want = (long long)h->num_sm * kK1nd2Warps * 4;
+                    long long run = ((long long)nu * g.T + want - 1) / want;
+                    run = std::max(8LL, std::min(64LL, run));
+                    run += run & 1;
+                    ad.run = (int)run;
+                    ad.n_runs = (g.T + ad.run - 1) / ad.run;
+                    B200_LAUNCH(k1nd_magnitude_2k, dim3(grid_1d((long long)nu * ad.n_runs, kK1nd2Warps, h->num_sm)),
+                                dim3(kK1nd2Warps * 32), k1nd2_smem_bytes(), st, ad);
+                } else
                 B200_LAUNCH(k1n_magnitude_2k, dim3(grid_1d((long long)nu * a1.n_runs, kWarps, resident)), dim3(kThreads),
                             k1n2_smem_floats() * 4, st, a1);
                 cudaEventRecord(h->stage_ev[4 * bi + 1], st);
@@ -1641,15 +1738,19 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     sa.F = kF2; sa.FPad = kFPad2;
                     sa.p = (float)p.prop_decrease; sa.one_minus_p = (float)(1.0 - p.prop_decrease);
                     sa.m0 = d_m0; sa.m2 = d_mag;
-                    if (smooths_smem_bytes(sa.FPad, nf, nt) <= 200 * 1024 && !(p.path_flags & 32)) {
-                        sa.TT = 256;                    // frames per strip (2 nt warm-up rows each)
-                        const int strips = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                        B200_LAUNCH(k_smooth_stream, dim3(strips, nu), dim3(sa.FPad / 4), smooths_smem_bytes(sa.FPad, nf, nt), st, sa);
-                    } else {
-                        const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                        B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
-                    }
+                    launch_smooth_float(sa, nf, nt, tf_lo, tf_hi, nu, p.path_flags, st);
                     cudaEventRecord(h->stage_ev[4 * bi + 2], st);
+                    if (use_zcache) {                  // spectra kept by k1n: bulk-staged synthesis (gate_synth_2k.cuh)
+                        K2c2Args ac{};
+                        ac.g = g; ac.tb = t2; ac.y = (float*)yb; ac.fmask = d_mag; ac.zcache = d_zcache; ac.dbg = dbg;
+                        const long long hops = h_hi - h_lo;
+                        long long want = (long long)h->num_sm * kK2c2Warps * 4;
+                        long long run = ((long long)nu * hops + want - 1) / want;
+                        ac.run = (int)std::max(16LL, std::min(128LL, run));
+                        ac.n_runs = (int)((hops + ac.run - 1) / ac.run);
+                        B200_LAUNCH(k2c_synthesize_2k, dim3(grid_1d((long long)nu * ac.n_runs, kK2c2Warps, h->num_sm)),
+                                    dim3(kK2c2Warps * 32), k2c2_smem_bytes(), st, ac);
+                    } else {
                     K22Args a2{};
                     a2.g = g; a2.tb = t2; a2.x = (const float*)xb; a2.y = (float*)yb; a2.fmask = d_mag; a2.dbg = dbg;
                     {
@@ -1661,6 +1762,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     }
                     B200_LAUNCH(k2_synthesize_2k, dim3(grid_1d((long long)nu * a2.n_runs, kWarps, res2)), dim3(kThreads),
                                 k22_smem_floats() * 4, st, a2);
+                    }
                     cudaEventRecord(h->stage_ev[4 * bi + 3], st);
                     launches += 2;
                 }
@@ -1699,13 +1801,8 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     sa.m0 = d_m0; sa.m2 = d_mag;
                     if (h->reuse_masks) {
                         // masks of the last forward
-                    } else if (smooths_smem_bytes(sa.FPad, nf, nt) <= 200 * 1024 && !(p.path_flags & 32)) {
-                        sa.TT = 256;                    // frames per strip (2 nt warm-up rows each)
-                        const int strips = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                        B200_LAUNCH(k_smooth_stream, dim3(strips, nu), dim3(sa.FPad / 4), smooths_smem_bytes(sa.FPad, nf, nt), st, sa);
                     } else {
-                        const int tiles = (tf_hi - tf_lo + sa.TT - 1) / sa.TT;
-                        B200_LAUNCH(k_smooth_f, dim3(tiles, nu), dim3(256), smoothf_smem_bytes(sa.TT, sa.FPad, nf), st, sa);
+                        launch_smooth_float(sa, nf, nt, tf_lo, tf_hi, nu, p.path_flags, st);
                     }
                     cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                     K2Args a2{};

@@ -1061,50 +1061,102 @@ __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)a.n_units * FP) return;
     const int ul = (int)(idx / FP), f = (int)(idx - (long long)ul * FP);
-    const float* A = a.mag + (long long)ul * a.T * FP + f;
+    const float* __restrict__ A = a.mag + (long long)ul * a.T * FP + f;
     float* M = a.m0 + (long long)ul * a.T * FP + f;
     if (f >= FF) {
         for (int t = 0; t < a.T; ++t) M[(long long)t * FP] = 0.f;
         return;
     }
-    // The recurrence state stays in float64 (two FMAs per element: the filter pole 1 - b ~ 0.995 accumulates
-    // rounding over hundreds of frames); the follower ratio, exponential and reciprocal run in float32 (the
-    // float64 exp / divide of the first version made this kernel 3x longer than both FFT kernels together).
+    // The recurrence state stays in float64 (the filter pole 1 - b ~ 0.995 accumulates rounding over hundreds of
+    // frames); the follower ratio, exponential and reciprocal run in float32 (the float64 exp / divide of the first
+    // version made this kernel 3x longer than both FFT kernels together).  The sweeps are serial per (unit, bin), so
+    // what bounds them is the latency of each step: every recurrence is written as ONE fused multiply-add on the
+    // carried value (the input term b x is formed off the chain), and the |X| column is fetched in batches of kB frames,
+    // the next batch requested before the current one is consumed, so no load sits between two steps of the chain.
+    constexpr int kB = 8;
     const double b = a.b, omb = 1.0 - a.b;
     const float n_mult = a.n_mult, slope = a.slope;
+    const int T = a.T;
+    auto fetch_up = [&](float (&x)[kB], int t0) {           // frames t0 .. t0 + kB - 1
+#pragma unroll
+        for (int j = 0; j < kB; ++j) x[j] = (t0 + j < T) ? A[(long long)(t0 + j) * FP] : 0.f;
+    };
+    auto fetch_down = [&](const float* src, float (&x)[kB], int t0) {     // frames t0, t0 - 1, ..
+#pragma unroll
+        for (int j = 0; j < kB; ++j) x[j] = (t0 - j >= 0) ? src[(long long)(t0 - j) * FP] : 0.f;
+    };
     double s = (double)A[0];
     if (a.regen) {
         // The forward sweep is not stored: the backward sweep regenerates it by the inverse recurrence
         // fwd[t-1] = (fwd[t] - b x[t]) / (1 - b) in float64.  Its error grows by 1/(1 - b) per step; the host selects
         // this variant only when (1 - b)^-T * 2^-53 stays far below float32 resolution (T ln(1/(1-b)) < 20), which
         // holds for the reference's time constants (config 3: 6.9).  One read of |X| less, no forward write.
-#pragma unroll 8
-        for (int t = 0; t < a.T; ++t) s = fma(b, (double)A[(long long)t * FP], omb * s);
-        const double inv_omb = 1.0 / omb;
+        {
+            float cur[kB], nxt[kB];
+            fetch_up(cur, 0);
+            for (int t0 = 0; t0 < T; t0 += kB) {
+                fetch_up(nxt, t0 + kB);
+#pragma unroll
+                for (int j = 0; j < kB; ++j)
+                    if (t0 + j < T) s = fma(omb, s, b * (double)cur[j]);
+#pragma unroll
+                for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
+            }
+        }
+        const double inv_omb = 1.0 / omb, nb_inv = -b * inv_omb;
         double f = s;                                          // fwd[T-1]
-#pragma unroll 8
-        for (int t = a.T - 1; t >= 0; --t) {
-            const double x = (double)A[(long long)t * FP];
-            s = fma(b, f, omb * s);
-            const float num = (float)(x - s);
-            const float r = num / (float)s;
-            M[(long long)t * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
-            f = fma(-b, x, f) * inv_omb;
+        float cur[kB], nxt[kB];
+        fetch_down(A, cur, T - 1);
+        for (int t0 = T - 1; t0 >= 0; t0 -= kB) {
+            fetch_down(A, nxt, t0 - kB);
+#pragma unroll
+            for (int j = 0; j < kB; ++j) {
+                if (t0 - j >= 0) {
+                    const double x = (double)cur[j];
+                    s = fma(omb, s, b * f);
+                    const float num = (float)(x - s);
+                    const float r = num / (float)s;
+                    M[(long long)(t0 - j) * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
+                    f = fma(inv_omb, f, nb_inv * x);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
         }
         return;
     }
-#pragma unroll 8
-    for (int t = 0; t < a.T; ++t) {
-        s = fma(b, (double)A[(long long)t * FP], omb * s);
-        M[(long long)t * FP] = (float)s;
+    {
+        float cur[kB], nxt[kB];
+        fetch_up(cur, 0);
+        for (int t0 = 0; t0 < T; t0 += kB) {
+            fetch_up(nxt, t0 + kB);
+#pragma unroll
+            for (int j = 0; j < kB; ++j) {
+                if (t0 + j < T) {
+                    s = fma(omb, s, b * (double)cur[j]);
+                    M[(long long)(t0 + j) * FP] = (float)s;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
+        }
     }
-    s = (double)M[(long long)(a.T - 1) * FP];
-#pragma unroll 8
-    for (int t = a.T - 1; t >= 0; --t) {
-        s = fma(b, (double)M[(long long)t * FP], omb * s);
-        const float num = (float)((double)A[(long long)t * FP] - s);      // |X| - S without float32 cancellation
-        const float r = num / (float)s;
-        M[(long long)t * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
+    // (the stored forward sweep is read back through M itself -- each element before it is overwritten)
+    const float* Mr = M;
+    s = (double)Mr[(long long)(T - 1) * FP];
+    for (int t0 = T - 1; t0 >= 0; t0 -= kB) {
+        float fw[kB], xx[kB];
+        fetch_down(Mr, fw, t0);
+        fetch_down(A, xx, t0);
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+            if (t0 - j >= 0) {
+                s = fma(omb, s, b * (double)fw[j]);
+                const float num = (float)((double)xx[j] - s);      // |X| - S without float32 cancellation
+                const float r = num / (float)s;
+                M[(long long)(t0 - j) * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
+            }
+        }
     }
 }
 
@@ -1217,6 +1269,103 @@ __global__ void __launch_bounds__(288) k_smooth_stream(const SmoothFArgs a) {
         for (int j = 0; j < 4; ++j) {
             const int bin = tid + j * G;
             dst[(long long)t * FP + bin] = bin < FF ? fmaf(o[j] * invD, a.p, a.one_minus_p) : 0.f;      // nonstationary.py:82-84
+        }
+    }
+}
+
+// Box form of the streaming smoothing (the one that normally runs for 1 <= nf <= 12).  The triangle taps
+// (n + 1 - |d|) are the self-convolution of a length-(n + 1) box, so the frequency direction is two sliding box sums
+// instead of 2 nf + 1 multiply-adds per bin: thread i owns the four CONSECUTIVE bins 4i..4i+3 (every shared-memory
+// access is one aligned 128-bit vector), takes the first box sum of each pass directly and the other three by
+// add-one / drop-one.  Per four bins and frame: ~17 vector loads and ~75 floating-point instructions against the
+// tap loops' ~120 scalar loads and ~120 FMAs.  The box sums restart in every thread and every frame, so no rounding
+// accumulates along a row or over time.  Row buffers: rowA = time-smoothed row c[] with 16 zero floats either side,
+// rowB = first box sums b1[g] = sum_{j=0..nf} c[g + j] stored at index g + 12 (g runs from -12: the second pass
+// out[f] = sum_{g=f-nf..f} b1[g] reaches nf bins to the left); bins >= F hold zeros, and FPad - F >= 12.
+inline size_t smoothb_smem_bytes(int FPad, int nt) { return ((size_t)(2 * nt + 1) * FPad + (FPad + 32) + (FPad + 16)) * 4; }
+
+template <int NF>
+__global__ void __launch_bounds__(288) k_smooth_box(const SmoothFArgs a) {
+    static_assert(NF >= 1 && NF <= 12, "box smoothing handles 1 <= nf <= 12");
+    B200_DYN_SMEM(float, s_buf);
+    const int FP = a.FPad, FF = a.F, nt = a.nt, R = 2 * nt + 1;
+    const int G = blockDim.x, tid = threadIdx.x;           // G == FP / 4
+    float* ring = s_buf;                                   // [R][FP]
+    float* rowA = s_buf + (size_t)R * FP;                  // [16 | FP | 16]
+    float* rowB = rowA + FP + 32;                          // [FP + 16]
+    const int ul = blockIdx.y;
+    const int t_begin = a.tf_lo + blockIdx.x * a.TT;
+    if (t_begin >= a.tf_hi) return;
+    const int t_end = min(t_begin + a.TT, a.tf_hi);
+    const float* src = a.m0 + (long long)ul * a.T * FP;
+    float* dst = a.m2 + (long long)ul * a.T * FP;
+    for (int i = tid; i < 2 * FP + 48; i += G) rowA[i] = 0.f;          // rowA and rowB are contiguous
+    const int b0 = 4 * tid;
+    auto load_row = [&](int t, int slot) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < a.T) {
+            v = *reinterpret_cast<const float4*>(src + (long long)t * FP + b0);
+            if (b0 + 0 >= FF) v.x = 0.f;
+            if (b0 + 1 >= FF) v.y = 0.f;
+            if (b0 + 2 >= FF) v.z = 0.f;
+            if (b0 + 3 >= FF) v.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(ring + slot * FP + b0) = v;
+    };
+    for (int k = 0; k < 2 * nt; ++k) load_row(t_begin - nt + k, k);
+    int newest = (2 * nt) % R;
+    const float invD = 1.0f / ((float)((NF + 1) * (NF + 1)) * (float)((nt + 1) * (nt + 1)));
+    __syncthreads();
+    for (int t = t_begin; t < t_end; ++t) {
+        load_row(t + nt, newest);
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        int slot = newest;                                  // frame t + nt; walking back to t - nt
+        for (int b = -nt; b <= nt; ++b) {
+            const float w = (float)(nt + 1 - (b < 0 ? -b : b));
+            const float4 r = *reinterpret_cast<const float4*>(ring + slot * FP + b0);
+            c.x = fmaf(w, r.x, c.x); c.y = fmaf(w, r.y, c.y); c.z = fmaf(w, r.z, c.z); c.w = fmaf(w, r.w, c.w);
+            slot = slot == 0 ? R - 1 : slot - 1;
+        }
+        newest = newest + 1 == R ? 0 : newest + 1;
+        *reinterpret_cast<float4*>(rowA + 16 + b0) = c;     // (the previous frame's first pass finished before its 2nd barrier)
+        __syncthreads();
+        {   // first box: b1[g], g = b0 - 12 + m, from c[g .. g + NF] = rowA[16 + g ..]
+            constexpr int NV = (4 + NF + 3) / 4;
+            float v[4 * NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const float4 q = *reinterpret_cast<const float4*>(rowA + b0 + 4 + 4 * k);
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+            float s0 = v[0];
+#pragma unroll
+            for (int j = 1; j <= NF; ++j) s0 += v[j];
+            const float s1 = s0 + v[NF + 1] - v[0];
+            const float s2 = s1 + v[NF + 2] - v[1];
+            const float s3 = s2 + v[NF + 3] - v[2];
+            *reinterpret_cast<float4*>(rowB + b0) = make_float4(s0, s1, s2, s3);   // (the previous frame's second pass finished before this frame's 1st barrier)
+        }
+        __syncthreads();
+        {   // second box: out[f], f = b0 + m, from b1[f - NF .. f] = rowB[f + 12 - NF .. f + 12]
+            constexpr int A0 = (12 - NF) & ~3, O = (12 - NF) & 3, NV = (16 - A0) / 4;
+            float u[4 * NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const float4 q = *reinterpret_cast<const float4*>(rowB + b0 + A0 + 4 * k);
+                u[4 * k] = q.x; u[4 * k + 1] = q.y; u[4 * k + 2] = q.z; u[4 * k + 3] = q.w;
+            }
+            float o0 = u[O];
+#pragma unroll
+            for (int e = 1; e <= NF; ++e) o0 += u[O + e];
+            const float o1 = o0 + u[O + NF + 1] - u[O];
+            const float o2 = o1 + u[O + NF + 2] - u[O + 1];
+            const float o3 = o2 + u[O + NF + 3] - u[O + 2];
+            float4 r;                                                               // nonstationary.py:82-84
+            r.x = b0 + 0 < FF ? fmaf(o0 * invD, a.p, a.one_minus_p) : 0.f;
+            r.y = b0 + 1 < FF ? fmaf(o1 * invD, a.p, a.one_minus_p) : 0.f;
+            r.z = b0 + 2 < FF ? fmaf(o2 * invD, a.p, a.one_minus_p) : 0.f;
+            r.w = b0 + 3 < FF ? fmaf(o3 * invD, a.p, a.one_minus_p) : 0.f;
+            *reinterpret_cast<float4*>(dst + (long long)t * FP + b0) = r;
         }
     }
 }

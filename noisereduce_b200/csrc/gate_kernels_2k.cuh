@@ -61,6 +61,8 @@ struct K1n2Args {
     float* mag;                // [n_units][T][FPad2]
     DebugTap dbg;              // spec: [T][F2][2]
     int run, n_runs;
+    float2* zcache;            // [n_units][T][1024] packed half-length spectra Z of frames [z_lo, z_hi), or null
+    int z_lo, z_hi;
 };
 
 __host__ __device__ constexpr int k2k_table_floats() { return 2 * 1024 + 2 * 1024 + 2 * kFPad2; }   // wa2, tw, w2k
@@ -99,6 +101,11 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude_2k(const K1n2Args a
             float re[32], im[32];
             load_frame_2k(re, im, xrow, base, i1, g.Lp, g.n_total, s_wa2, lane);
             warp_fft1024(re, im, tile, s_tw, lane);
+            if (a.zcache && t >= a.z_lo && t < a.z_hi) {        // k2c_synthesize_2k loads Z instead of transforming the frame again
+                float2* zp = a.zcache + ((long long)ul * g.T + t) * 1024 + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) zp[32 * q] = make_float2(re[brev5(q)], im[brev5(q)]);
+            }
             float* dst = a.mag + ((long long)ul * g.T + t) * kFPad2;
 #pragma unroll
             for (int q = 0; q < 17; ++q) {

@@ -216,6 +216,37 @@ def test_nonstationary_n_fft_2048(lib):
             assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5
 
 
+def test_float_mask_box_smoothing_and_2k_spectrum_cache(lib):
+    """k_smooth_box (1 <= nf <= 12: two sliding box sums per row) against the oracle and against the tap-loop
+    streaming kernel (path_flags 128); k2c_synthesize_2k (spectra cached by k1n_magnitude_2k) against the
+    re-transforming k2_synthesize_2k (path_flags 2).  The last case has config 3's filter extents (nf 10, nt 4)."""
+    y = synth_small(C=2, n=20000)
+    cases = [(1024, 40, 20), (1024, 70, 70), (1024, 170, 150), (1024, 330, 40), (1024, 390, 100),
+             (2048, 16, 40), (2048, 100, 300), (2048, 160, 130)]
+    for n_fft, hz, ms in cases:
+        cfg = O.GateConfig(sr=SR, stationary=False, n_fft=n_fft, chunk_size=8000, padding=1200, time_constant_s=0.3,
+                           freq_mask_smooth_hz=hz, time_mask_smooth_ms=ms, prop_decrease=0.9)
+        a = P.check_nonstationary(lib, y, cfg, tap_unit=(1, 1))
+        b = P.check_nonstationary(lib, y, cfg, tap_unit=(1, 1), path_flags=128)
+        for r in (a, b):
+            assert r["mask_err"] < P.MASK_TOL_NONSTAT and r["out_relinf"] < P.OUT_TOL_TIGHT * 5, (n_fft, hz, ms, r)
+    cfg = O.GateConfig(sr=SR, stationary=False, n_fft=2048, chunk_size=7000, padding=600, freq_mask_smooth_hz=160,
+                       time_mask_smooth_ms=130)
+    for unit in [(0, 0), (2, 1)]:
+        a = P.check_nonstationary(lib, y, cfg, tap_unit=unit)
+        b = P.check_nonstationary(lib, y, cfg, tap_unit=unit, path_flags=2)
+        c = P.check_nonstationary(lib, y, cfg, tap_unit=unit, path_flags=16)     # one frame per warp (k1n_magnitude_2k)
+        for r in (a, b, c):
+            assert r["spec_err"] < P.SPEC_TOL and r["mask_err"] < P.MASK_TOL_NONSTAT and r["out_relinf"] < P.OUT_TOL_TIGHT * 5
+        assert abs(a["out_relinf"] - b["out_relinf"]) < 1e-6 and abs(a["out_relinf"] - c["out_relinf"]) < 1e-6
+    # the follower with its forward sweep stored (path_flags 64) instead of regenerated, odd batch remainders (T = 17, 30)
+    for n, cs in [(4000, 0), (7400, 0)]:
+        cfg = O.GateConfig(sr=SR, stationary=False, chunk_size=cs or None, padding=300, time_constant_s=0.5)
+        for fl in (0, 64):
+            r = P.check_nonstationary(lib, y[:1, :n], cfg, path_flags=fl)
+            assert r["mask_err"] < P.MASK_TOL_NONSTAT and r["out_relinf"] < P.OUT_TOL_TIGHT * 5, (n, fl, r)
+
+
 def test_python_surface_on_simulator(lib, monkeypatch):
     """reduce_noise() host logic (shapes, dtypes, defaults, errors) with the simulator library."""
     monkeypatch.setattr(_cabi, "_LIB", lib)
