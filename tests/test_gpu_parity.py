@@ -118,6 +118,41 @@ def test_nonstationary_n_fft_2048_config3(lib, golden_dir):
     out = nr.reduce_noise(y=s["y"].astype(np.float64), sr=int(s["sr"]), stationary=False, n_fft=2048,
                           time_constant_s=0.5, prop_decrease=0.9)
     assert out.dtype == np.float64 and P.relinf(out, s["out_nonstat_2048_f64"]) < P.OUT_TOL
+    # the kept variants: tap-loop smoothing (128), one frame per warp in the analysis (16), re-transforming synthesis (2),
+    # stored forward sweep (64)
+    for flags in (128, 16, 2, 64):
+        res = P.check_nonstationary(lib, y, cfg, tap_unit=(1, 0), path_flags=flags)
+        assert res["spec_err"] < P.SPEC_TOL and res["mask_err"] < P.MASK_TOL_NONSTAT, (flags, res)
+        assert res["out_relinf"] < P.OUT_TOL_TIGHT * 5, (flags, res)
+
+
+def test_pooled_result_buffers(lib):
+    """Large results of the numpy surface come back in page-locked memory leased from the library's pool
+    (b200gate_host_alloc): same values as an ordinary array, the lease returns with the last view, and the next call of
+    the same size gets the same buffer back."""
+    import gc
+    import noisereduce_b200 as nr
+    sr = 48000
+    rng = np.random.default_rng(7)
+    y = (0.05 * rng.standard_normal((8, 1_300_000))).astype(np.float32)           # 41.6 MB > PINNED_RESULT_MIN_BYTES
+    a = nr.reduce_noise(y=y, sr=sr, stationary=True, n_fft=1024, hop_length=256)
+    assert _cabi._pinned_leased_bytes >= a.nbytes
+    ptr_a = a.ctypes.data
+    plain = np.empty_like(y)
+    g = _cabi.Gate(lib=lib, **P.gate_params(O.GateConfig(sr=sr, stationary=True, n_fft=1024, hop_length=256)))
+    g.noise_stats_host(y)
+    g.run_host(y, out=plain)
+    g.close()
+    assert np.array_equal(a, plain)
+    view = a[:, 100:200]
+    del a
+    gc.collect()
+    assert _cabi._pinned_leased_bytes >= y.nbytes and float(np.abs(view).max()) >= 0.0
+    del view
+    gc.collect()
+    assert _cabi._pinned_leased_bytes == 0
+    b = nr.reduce_noise(y=y, sr=sr, stationary=True, n_fft=1024, hop_length=256)
+    assert b.ctypes.data == ptr_a and np.array_equal(b, plain)
 
 
 def test_golden_fish_and_small(lib, golden_dir):
