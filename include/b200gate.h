@@ -68,8 +68,12 @@ typedef struct b200gate_params {
                                  * kept for A/B); bit 1: do not cache spectra between analysis and synthesis
                                  * (re-transform instead; saves 8 KB of workspace per frame pair); bit 2: run the
                                  * float64 general-geometry family even for a tuned geometry (cross-check);
-                                 * bit 3 (experimental, unmeasured): k1 streams the next frame pair's float32
-                                 * sample rows into shared memory with cp.async                           */
+                                 * bit 3 (experimental): k1 streams the next frame pair's float32 sample rows into
+                                 * shared memory with cp.async (measured: no gain); bit 4: one unit / one frame per
+                                 * warp in the FFT kernels instead of the dual (packed f32x2) forms; bit 5: tile-based
+                                 * float-mask smoothing; bit 6: the non-stationary follower stores its forward sweep
+                                 * instead of regenerating it; bit 7: tap-loop float-mask smoothing instead of the
+                                 * box-sum form.  Bits 1-7 select kept cross-check variants of the same arithmetic    */
     int64_t chunk_size;         /* <= 0: never chunk (torch surface / chunk_size=None)           */
     int64_t padding;
     double sr;
