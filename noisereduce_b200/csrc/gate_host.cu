@@ -5,11 +5,9 @@
 // k1_analyze -> k_rowfloor -> k_smooth -> k2_synthesize per batch of units on the caller's stream.
 #include "../../include/b200gate.h"
 #include "gate_kernels_2k.cuh"
-#include "gate_fused.cuh"
 #include "gate_synth.cuh"
 #include "gate_synth_2k.cuh"
 #include "gate_dual.cuh"
-#include "gate_dual_2k.cuh"
 #include "gate_peer.cuh"
 #include "gate_generic.cuh"
 
@@ -20,6 +18,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <future>
 #include <mutex>
 #include <string>
@@ -59,12 +59,8 @@ struct b200gate_handle {
     int tthr_units = 0;
     bool have_thresh = false;
     double min_floor_amp = 0.0;                    // min_f 10^((thresh+top_db)/20): smallest |X| that lifts a row
-    bool force_two_pass = false;
     int range_mode = 0;                            // b200gate_set_range
     long long range_a = 0, range_b = 0;
-    unsigned* d_maxabs = nullptr;
-    char* d_fscratch = nullptr;                    // fused kernel: per-warp spectra + decision rows
-    size_t fscratch_bytes = 0;
     std::vector<double> thr, mean, sd;
     // general-geometry family (gate_generic.cuh)
     bool generic = false;
@@ -84,7 +80,6 @@ struct b200gate_handle {
     size_t raw_bytes = 0;
     Counters* d_cnt = nullptr;
     Counters* h_cnt = nullptr;                     // pinned: the run's exactness counters land here (stream-ordered copy)
-    unsigned* h_maxabs = nullptr;                  // pinned (fused path)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_done = nullptr;
     // statistics of a device-pointer run are resolved lazily (b200gate_get_stats): the run itself never blocks the host
     // torch surface: the masks of the last forward stay in the workspace so that the adjoint (= the same synthesis
@@ -93,7 +88,6 @@ struct b200gate_handle {
     long long masks_C = 0, masks_N = 0;
     bool stats_pending = false;
     size_t pend_batches = 0;
-    bool pend_fused = false;
     std::vector<cudaEvent_t> group_ev;             // b200gate_run_sharded: one per channel group + 1
     std::vector<cudaEvent_t> stage_ev;             // 4 per batch: analysis start, analysis end, smoothing end, synthesis end
     std::vector<cudaEvent_t> pipe_ev;              // 4 per batch: input landed, compute done, output landed, seam copied
@@ -550,25 +544,88 @@ bool host_pointer_is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 #endif
 }
-void parallel_rows_copy(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, int nthreads) {
+// Persistent host workers for the staging copies: a slab pipeline of ~50 slabs would otherwise create and join ~15 threads
+// per slab and direction (~1 ms of a ~3 ms slab).  Workers sleep on a condition variable between jobs; one job at a time.
+class HostWorkers {
+public:
+    // run work(id) for id in [0, nt) on nt - 1 pooled threads plus the caller
+    void run(int nt, const std::function<void(int)>& work) {
+        if (nt <= 1) { work(0); return; }
+        std::unique_lock<std::mutex> job_lock(job_mu_);               // one job at a time (handles on several threads share the pool)
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while ((int)threads_.size() < nt - 1) {
+                const int id = (int)threads_.size() + 1;
+                threads_.emplace_back([this, id] { loop(id); });
+            }
+            work_ = &work;
+            nt_ = nt;
+            pending_ = nt - 1;
+            ++generation_;
+        }
+        cv_.notify_all();
+        work(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        work_ = nullptr;
+    }
+    ~HostWorkers() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+
+private:
+    void loop(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* w = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || (generation_ != seen && id < nt_); });
+                if (stop_) return;
+                seen = generation_;
+                w = work_;
+            }
+            (*w)(id);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    std::mutex mu_, job_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)>* work_ = nullptr;
+    int nt_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
+// pool 0: staging of pageable input rows; pool 1: copy-out of results into pageable rows (the two overlap in the slab pipeline)
+HostWorkers& host_workers(int pool) {
+    static HostWorkers* w[2] = {new HostWorkers(), new HostWorkers()};   // (never destroyed: no joins from static destructors at exit)
+    return *w[pool & 1];
+}
+
+void parallel_rows_copy(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, int nthreads,
+                        int pool = 0) {
     if (rows == 0 || width == 0) return;
     // split every row into pieces of >= 1 MB so that few long rows still spread over all threads
     const size_t piece = std::max<size_t>(1 << 20, (width * rows / (size_t)std::max(1, nthreads) + 4095) / 4096 * 4096);
     const size_t per_row = (width + piece - 1) / piece;
     const size_t n_pieces = per_row * rows;
-    const int nt = (int)std::min<size_t>((size_t)std::max(1, nthreads), n_pieces);
-    auto work = [&](int id) {
+    const int nt = (int)std::min<size_t>((size_t)std::max(1, std::min(nthreads, 64)), n_pieces);
+    std::function<void(int)> work = [&](int id) {
         for (size_t k = (size_t)id; k < n_pieces; k += (size_t)nt) {
             const size_t r = k / per_row, off = (k - r * per_row) * piece;
             memcpy((char*)dst + r * dpitch + off, (const char*)src + r * spitch + off, std::min(piece, width - off));
         }
     };
-    if (nt == 1) { work(0); return; }
-    std::vector<std::thread> th;
-    th.reserve((size_t)nt - 1);
-    for (int i = 1; i < nt; ++i) th.emplace_back(work, i);
-    work(0);
-    for (auto& t : th) t.join();
+    host_workers(pool).run(nt, work);
 }
 
 // Pinned staging slabs are expensive to create (cudaMallocHost of 1 GB: ~0.2 s) and independent of the handle's parameters:
@@ -650,7 +707,6 @@ int resolve_stats(b200gate_handle* h) {
         cudaEventElapsedTime(&t1, h->stage_ev[4 * b + 0], h->stage_ev[4 * b + 1]);
         cudaEventElapsedTime(&t2, h->stage_ev[4 * b + 1], h->stage_ev[4 * b + 2]);
         cudaEventElapsedTime(&t3, h->stage_ev[4 * b + 2], h->stage_ev[4 * b + 3]);
-        if (h->pend_fused) { h->stats.fused_ms += t1; continue; }
         h->stats.k1_ms += t1;
         h->stats.smooth_ms += t2;
         h->stats.k2_ms += t3;
@@ -720,11 +776,9 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
     h->F = want_generic ? p->n_fft / 2 + 1 : (p->n_fft == kN2 ? kF2 : kF);
     int rc = want_generic ? build_generic_tables(h) : build_static_tables(h);
     if (rc == B200GATE_OK) {
-        e = cudaMalloc((void**)&h->d_maxabs, sizeof(unsigned));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
+        e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
         if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_need_rowmax, sizeof(unsigned));
         if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_cnt, sizeof(Counters));
-        if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_maxabs, sizeof(unsigned));
         if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
         if (e == cudaSuccess) e = cudaEventCreate(&h->ev_done);
@@ -754,9 +808,6 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
         cudaFuncSetAttribute(k1n_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1n2_smem_floats() * 4);
         cudaFuncSetAttribute(k2_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k22_smem_floats() * 4);
         cudaFuncSetAttribute(k2c_synthesize_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k2c2_smem_bytes());
-        cudaFuncSetAttribute(k1nd_magnitude_2k, cudaFuncAttributeMaxDynamicSharedMemorySize, k1nd2_smem_bytes());
-        for (int dt = 0; dt < 3; ++dt)
-            B200_WITH_DTYPE(dt, { cudaFuncSetAttribute(k_fused<8, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kfused_smem_floats() * 4); });
         cudaFuncSetAttribute(k_smooth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         for (int dt = 0; dt < 3; ++dt)
             B200_WITH_DTYPE(dt, { cudaFuncSetAttribute(gk_stft<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16); });
@@ -775,7 +826,7 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
 void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
-                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_maxabs, h->d_fscratch, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
+                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
                     h->d_dbg_mask, h->d_dbg_bits, h->d_gwa, h->d_gws, h->d_gw2, h->d_gthr, h->d_gcs, h->d_gtthr, h->d_gchirp, h->d_gbbr};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -786,7 +837,6 @@ void b200gate_destroy(b200gate_handle* h) {
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     for (int i = 0; i < 2; ++i) { g_pinned_pool.give(h->hp_in[i], h->hp_in_bytes[i]); g_pinned_pool.give(h->hp_out[i], h->hp_out_bytes[i]); }
     if (h->d_need_rowmax) cudaFree(h->d_need_rowmax);
-    if (h->h_maxabs) cudaFreeHost(h->h_maxabs);
     for (cudaEvent_t e : h->stage_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -1168,15 +1218,12 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
 
     // ---- workspace / batching ---------------------------------------------------------------------
     const bool stat = p.stationary != 0;
-    // single-pass fused kernel: stationary gate, n_fft 1024, filter extents the in-warp smoother handles
-    const bool use_fused = stat && native && !generic && !h->force_two_pass && (p.path_flags & 1) &&
-                           (2 * p.n_grad_freq + 1 <= 12) && (p.n_grad_time + 1 <= 14);
     const size_t per_unit_2pass = (stat ? (size_t)g.T * kFW * 4 + (size_t)kFPad * 4 + (size_t)kFW * 4 + (size_t)num_unit_stride(g.T) * 2 + 64
                                         : 2 * (size_t)g.T * FP * 4 + 64) +
                                   (stat && torch_sem ? (size_t)g.T * kFPad * 4 + 2 * (size_t)kFPad * 4 : 0) + 2048;
     // spectrum cache: k1 / k1n keep the packed spectrum of every frame pair so k2 does not re-transform
     const int zpairs = (g.T + 1) / 2;
-    const bool use_zcache = !use_fused && !generic && !(p.path_flags & 2);
+    const bool use_zcache = !generic && !(p.path_flags & 2);
     // (n_fft 2048: one half-length spectrum per frame; n_fft 1024: one packed spectrum per frame pair)
     const size_t zunit = use_zcache ? (size_t)(two_k ? g.T : zpairs) * 1024 * sizeof(float2) : 0;
     // dual kernels (gate_dual.cuh): two channels of a chunk per warp -- stationary numpy-surface gate, even channel count
@@ -1184,7 +1231,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // general-geometry family: float64 spectrum, mask, scratch and synthesis frames of every unit
     const size_t g_tf = (size_t)g.T * (size_t)h->F, g_tw = (size_t)g.T * (size_t)h->g_W;
     const size_t per_unit_generic = g_tf * 16 + 2 * g_tf * 8 + g_tw * 8 + 2 * (size_t)h->F * 8 + 6 * 256;
-    const size_t per_unit = generic ? per_unit_generic : (use_fused ? 64 : per_unit_2pass + zunit);   // the fused kernel keeps no per-unit buffers
+    const size_t per_unit = generic ? per_unit_generic : per_unit_2pass + zunit;
     // default workspace: up to 24 GiB, never more than 70 % of what is free now (plus what this handle already holds)
     double limit = p.workspace_limit_bytes;
     if (!(limit > 0)) {
@@ -1260,7 +1307,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const size_t goff_thr = goff_fr + al((size_t)ub * g_tw * 8);          // torch surface: per-row thresholds
     const size_t goff_rmax = goff_thr + al((size_t)ub * h->F * 8);         // per-(unit, bin) dB maxima (top_db floor)
     const size_t end_generic = goff_rmax + al((size_t)ub * h->F * 8);
-    const size_t end_base = generic ? end_generic : use_fused ? 4096 : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
+    const size_t end_base = generic ? end_generic : (stat ? (torch_sem ? end_tstat : end_stat) : end_nonstat);
     const size_t off_z = al(end_base);
     const size_t end_all = off_z + al((size_t)ub * zunit);
     {
@@ -1303,23 +1350,6 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     const int nf = p.n_grad_freq, nt = p.n_grad_time;
     const double D = (double)(nf + 1) * (nf + 1) * (nt + 1) * (nt + 1);
     const int resident = h->num_sm * 3;
-    int fused_run = 0, fused_max_pairs = 0;
-    if (use_fused) {
-        const int ntE = (nt + 1) & ~1;
-        const long long hops = h_hi - h_lo;
-        long long want = (long long)resident * kWarps * 3;
-        long long run = ((long long)std::min(ub, U) * hops + want - 1) / want;
-        fused_run = (int)std::max(32LL, std::min(128LL, run));
-        fused_run += fused_run & 1;
-        fused_max_pairs = (fused_run + 4 + 2 * ntE + 2) / 2 + 2;
-        const size_t workers = (size_t)resident * kWarps;
-        const size_t zbytes = workers * (size_t)fused_max_pairs * 1024 * sizeof(float2);
-        const size_t bbytes = workers * (size_t)(2 * fused_max_pairs) * kFusedRowWords * 4;
-        int rc = ensure(h, (void**)&h->d_fscratch, &h->fscratch_bytes, zbytes + bbytes + 256);
-        if (rc) return rc;
-        CK(h, cudaMemsetAsync(h->d_maxabs, 0, sizeof(unsigned), st));
-    }
-
     const size_t n_batches = (size_t)((U + ub - 1) / ub);
     while (h->stage_ev.size() < 4 * n_batches) {
         cudaEvent_t e;
@@ -1483,36 +1513,6 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 (void)W;
                 launches += 2;
             }
-            cudaEventRecord(h->stage_ev[4 * bi + 3], st);
-        } else if (use_fused) {
-            KFArgs fa{};
-            fa.g = g; fa.tb = tb; fa.x = xb; fa.y = yb;
-            const size_t workers = (size_t)resident * kWarps;
-            fa.zscratch = (float2*)h->d_fscratch;
-            fa.bitscratch = (unsigned*)(h->d_fscratch + workers * (size_t)fused_max_pairs * 1024 * sizeof(float2));
-            fa.max_pairs = fused_max_pairs; fa.max_rows = 2 * fused_max_pairs;
-            fa.maxabs = h->d_maxabs; fa.cnt = h->d_cnt;
-            fa.pD = (float)(p.prop_decrease / D); fa.one_minus_p = (float)(1.0 - p.prop_decrease);
-            fa.nf = nf; fa.nt = nt;
-            {
-                unsigned char tb8[12] = {0};
-                for (int d = -nf; d <= nf; ++d) tb8[d + nf] = (unsigned char)(nf + 1 - abs(d));
-                memcpy(fa.taps, tb8, 12);
-            }
-            fa.run = fused_run;
-            fa.n_runs = (int)((h_hi - h_lo + fused_run - 1) / fused_run);
-            fa.dbg = dbg;
-            fa.dbg_bits = dbg.ul >= 0 ? h->d_dbg_bits : nullptr;
-            if (dbg.ul >= 0) CK(h, cudaMemsetAsync(h->d_dbg_bits, 0, (size_t)g.T * kFW * 4, st));
-            cudaEventRecord(h->stage_ev[4 * bi + 0], st);
-            if (tf_hi > tf_lo) {
-                B200_WITH_DTYPE(kdt, { auto kern_ = k_fused<8, T>;
-                    B200_LAUNCH(kern_, dim3(grid_1d((long long)nu * fa.n_runs, kWarps, resident)), dim3(kThreads),
-                                kfused_smem_floats() * 4, st, fa); });
-                ++launches;
-            }
-            cudaEventRecord(h->stage_ev[4 * bi + 1], st);
-            cudaEventRecord(h->stage_ev[4 * bi + 2], st);
             cudaEventRecord(h->stage_ev[4 * bi + 3], st);
         } else if (stat) {
             if (torch_sem) {
@@ -1703,19 +1703,6 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     a1.run = (int)std::max(4LL, std::min(64LL, run));
                     a1.n_runs = (g.T + a1.run - 1) / a1.run;
                 }
-                if (!(p.path_flags & 16)) {               // two frames per warp (gate_dual_2k.cuh)
-                    K1nd2Args ad{};
-                    ad.g = g; ad.tb = t2; ad.x = (const float*)xb; ad.mag = d_mag; ad.dbg = dbg;
-                    ad.zcache = d_zcache; ad.z_lo = tf_lo; ad.z_hi = tf_hi + 1;
-                    long long want = (long long)h->num_sm * kK1nd2Warps * 4;
-                    long long run = ((long long)nu * g.T + want - 1) / want;
-                    run = std::max(8LL, std::min(64LL, run));
-                    run += run & 1;
-                    ad.run = (int)run;
-                    ad.n_runs = (g.T + ad.run - 1) / ad.run;
-                    B200_LAUNCH(k1nd_magnitude_2k, dim3(grid_1d((long long)nu * ad.n_runs, kK1nd2Warps, h->num_sm)),
-                                dim3(kK1nd2Warps * 32), k1nd2_smem_bytes(), st, ad);
-                } else
                 B200_LAUNCH(k1n_magnitude_2k, dim3(grid_1d((long long)nu * a1.n_runs, kWarps, resident)), dim3(kThreads),
                             k1n2_smem_floats() * 4, st, a1);
                 cudaEventRecord(h->stage_ev[4 * bi + 1], st);
@@ -1728,7 +1715,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
                 ia.regen = (ia.b < 0.5 && (double)g.T * -log1p(-ia.b) < 20.0 && !(p.path_flags & 64)) ? 1 : 0;
                 ia.mag = d_mag; ia.m0 = d_m0;
-                B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad2, 128, 1 << 30)), dim3(128), 0, st, ia);
+                B200_LAUNCH(k_iir_sigmoid<kFPad2>, dim3(grid_1d((long long)nu * kFPad2, 128, 1 << 30)), dim3(128), 0, st, ia);
                 launches += 2;
                 cudaEventRecord(h->stage_ev[4 * bi + 2], st);
                 cudaEventRecord(h->stage_ev[4 * bi + 3], st);
@@ -1787,7 +1774,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     ia.n_mult = (float)p.thresh_n_mult; ia.slope = (float)p.sigmoid_slope;
                 ia.regen = (ia.b < 0.5 && (double)g.T * -log1p(-ia.b) < 20.0 && !(p.path_flags & 64)) ? 1 : 0;
                     ia.mag = d_mag; ia.m0 = d_m0;
-                    B200_LAUNCH(k_iir_sigmoid, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
+                    B200_LAUNCH(k_iir_sigmoid<kFPad>, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ia);
                 }
                 launches += 2;
                 cudaEventRecord(h->stage_ev[4 * bi + 2], st);
@@ -1832,7 +1819,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 }
             }
         }
-        if (dbg.ul >= 0 && stat && !use_fused && !generic) {
+        if (dbg.ul >= 0 && stat && !generic) {
             // tapped mask words with the row floor folded in, as the smoothing kernel consumes them
             std::vector<unsigned> fl(kFW);
             CK(h, cudaStreamSynchronize(st));
@@ -1868,7 +1855,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     out_task = std::async(std::launch::async, [evd, dstp, srcp, wbytes, dp, C, nth, dev_now]() {
                         cudaSetDevice(dev_now);
                         cudaEventSynchronize(evd);
-                        parallel_rows_copy(dstp, dp, srcp, wbytes, wbytes, (size_t)C, nth);
+                        parallel_rows_copy(dstp, dp, srcp, wbytes, wbytes, (size_t)C, nth, 1);
                     });
                 }
                 prev_o0 = o0; prev_o1 = o1;
@@ -1887,7 +1874,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         if (out_task.valid()) out_task.get();
         if (stage_out && bi >= 1)                      // the last slab's rows
             parallel_rows_copy((char*)out + (size_t)prev_o0 * es, (size_t)out_stride * es, h->hp_out[(bi - 1) & 1],
-                               (size_t)(prev_o1 - prev_o0) * es, (size_t)(prev_o1 - prev_o0) * es, (size_t)C, h->host_threads);
+                               (size_t)(prev_o1 - prev_o0) * es, (size_t)(prev_o1 - prev_o0) * es, (size_t)C, h->host_threads, 1);
         if (getenv("B200GATE_TRACE")) {                       // slab timeline (ms since the first launch) on stderr
             CK(h, cudaStreamSynchronize(st));
             for (size_t b = 0; b < n_batches; ++b) {
@@ -1926,32 +1913,16 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
     // ---- stats: the counters travel to pinned host memory behind the kernels; a device-pointer run returns
     // here with everything enqueued (b200gate_get_stats waits for it), host-pointer runs return finished -----
     CK(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    if (use_fused) CK(h, cudaMemcpyAsync(h->h_maxabs, h->d_maxabs, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(h, cudaEventRecord(h->ev_done, st));
     h->stats.units = U;
     h->stats.frames = U * g.T;
     h->stats.kernel_launches = launches;
-    h->stats.fused_path = use_fused ? 1 : 0;
+    h->stats.fused_path = 0;
     h->stats_pending = true;
     if (torch_sem && !generic && !two_k && n_batches == 1 && !h->reuse_masks) {
         h->masks_valid = true; h->masks_C = C; h->masks_N = N;
     }
     h->pend_batches = n_batches;
-    h->pend_fused = use_fused;
-    if (use_fused) {
-        CK(h, cudaStreamSynchronize(st));
-        float mx;
-        memcpy(&mx, h->h_maxabs, 4);
-        // |X[f,t]| <= max|x| (the scaled analysis window sums to 1): below the smallest floor no row can be lifted
-        if (!((double)mx < 0.999 * h->min_floor_amp)) {
-            h->force_two_pass = true;
-            h->stats_pending = false;
-            const int rc2 = b200gate_run(h, in, out, dtype, C, N, in_stride, out_stride, is_device, stream);
-            h->force_two_pass = false;
-            h->stats.fused_fallbacks = 1;
-            return rc2;
-        }
-    }
     if (!direct) {                               // host buffers: the result must be in `out` on return
         const int rc = resolve_stats(h);
         if (rc) return rc;

@@ -1056,8 +1056,9 @@ struct IirArgs {
     float* m0;                 // [n_units][T][FPad]: forward sweep, then overwritten by the sigmoid mask
 };
 
+template <int FP>                                       // padded row pitch: 544 (n_fft 1024) or 1056 (n_fft 2048)
 __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
-    const int FP = a.FPad, FF = a.F;
+    const int FF = a.F;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)a.n_units * FP) return;
     const int ul = (int)(idx / FP), f = (int)(idx - (long long)ul * FP);
@@ -1070,20 +1071,36 @@ __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
     // The recurrence state stays in float64 (the filter pole 1 - b ~ 0.995 accumulates rounding over hundreds of
     // frames); the follower ratio, exponential and reciprocal run in float32 (the float64 exp / divide of the first
     // version made this kernel 3x longer than both FFT kernels together).  The sweeps are serial per (unit, bin), so
-    // what bounds them is the latency of each step: every recurrence is written as ONE fused multiply-add on the
-    // carried value (the input term b x is formed off the chain), and the |X| column is fetched in batches of kB frames,
-    // the next batch requested before the current one is consumed, so no load sits between two steps of the chain.
+    // what bounds them is the latency of each step and the instructions around it: every recurrence is ONE fused
+    // multiply-add on the carried value (the input term b x is formed off the chain); the |X| column is fetched in
+    // batches of kB frames through a walking pointer with compile-time offsets (the row pitch is a template parameter),
+    // the next batch requested before the current one is consumed, so no load sits between two steps of the chain;
+    // the ratio is num * rcp(s) and the sigmoid a correctly rounded reciprocal (no division slow paths in the loop).
     constexpr int kB = 8;
     const double b = a.b, omb = 1.0 - a.b;
     const float n_mult = a.n_mult, slope = a.slope;
     const int T = a.T;
-    auto fetch_up = [&](float (&x)[kB], int t0) {           // frames t0 .. t0 + kB - 1
-#pragma unroll
-        for (int j = 0; j < kB; ++j) x[j] = (t0 + j < T) ? A[(long long)(t0 + j) * FP] : 0.f;
+    auto sigmoid_mask = [&](double x, double sm) -> float {
+        const float num = (float)(x - sm);                     // |X| - S without float32 cancellation
+        const float r = num * __frcp_rn((float)sm);
+        return __frcp_rn(1.0f + expf(-(r - n_mult) * slope));
     };
-    auto fetch_down = [&](const float* src, float (&x)[kB], int t0) {     // frames t0, t0 - 1, ..
+    // frames t0 + dir * j, j = 0..kB-1; `full`: all of them exist (compile-time offsets), else clamped (never used)
+    auto fetch = [&](const float* src, float (&x)[kB], int t0, int dir) {
+        const bool full = dir > 0 ? (t0 >= 0 && t0 + kB <= T) : (t0 < T && t0 - kB + 1 >= 0);
+        if (full) {
+            const float* p = src + (long long)t0 * FP;
+            if (dir > 0) {
 #pragma unroll
-        for (int j = 0; j < kB; ++j) x[j] = (t0 - j >= 0) ? src[(long long)(t0 - j) * FP] : 0.f;
+                for (int j = 0; j < kB; ++j) x[j] = p[j * FP];
+            } else {
+#pragma unroll
+                for (int j = 0; j < kB; ++j) x[j] = p[-j * FP];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kB; ++j) x[j] = src[(long long)min(max(t0 + dir * j, 0), T - 1) * FP];
+        }
     };
     double s = (double)A[0];
     if (a.regen) {
@@ -1093,43 +1110,53 @@ __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
         // holds for the reference's time constants (config 3: 6.9).  One read of |X| less, no forward write.
         {
             float cur[kB], nxt[kB];
-            fetch_up(cur, 0);
-            for (int t0 = 0; t0 < T; t0 += kB) {
-                fetch_up(nxt, t0 + kB);
+            fetch(A, cur, 0, 1);
+            int t0 = 0;
+            for (; t0 + kB <= T; t0 += kB) {
+                fetch(A, nxt, t0 + kB, 1);
 #pragma unroll
-                for (int j = 0; j < kB; ++j)
-                    if (t0 + j < T) s = fma(omb, s, b * (double)cur[j]);
+                for (int j = 0; j < kB; ++j) s = fma(omb, s, b * (double)cur[j]);
 #pragma unroll
                 for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
             }
+#pragma unroll
+            for (int j = 0; j < kB; ++j)
+                if (t0 + j < T) s = fma(omb, s, b * (double)cur[j]);
         }
         const double inv_omb = 1.0 / omb, nb_inv = -b * inv_omb;
-        double f = s;                                          // fwd[T-1]
+        double fw = s;                                         // fwd[T-1]
         float cur[kB], nxt[kB];
-        fetch_down(A, cur, T - 1);
-        for (int t0 = T - 1; t0 >= 0; t0 -= kB) {
-            fetch_down(A, nxt, t0 - kB);
+        fetch(A, cur, T - 1, -1);
+        int t0 = T - 1;
+        for (; t0 - kB + 1 >= 0; t0 -= kB) {
+            fetch(A, nxt, t0 - kB, -1);
+            float* mp = M + (long long)t0 * FP;
 #pragma unroll
             for (int j = 0; j < kB; ++j) {
-                if (t0 - j >= 0) {
-                    const double x = (double)cur[j];
-                    s = fma(omb, s, b * f);
-                    const float num = (float)(x - s);
-                    const float r = num / (float)s;
-                    M[(long long)(t0 - j) * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
-                    f = fma(inv_omb, f, nb_inv * x);
-                }
+                const double x = (double)cur[j];
+                s = fma(omb, s, b * fw);
+                mp[-j * FP] = sigmoid_mask(x, s);
+                fw = fma(inv_omb, fw, nb_inv * x);
             }
 #pragma unroll
             for (int j = 0; j < kB; ++j) cur[j] = nxt[j];
+        }
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+            if (t0 - j >= 0) {
+                const double x = (double)cur[j];
+                s = fma(omb, s, b * fw);
+                M[(long long)(t0 - j) * FP] = sigmoid_mask(x, s);
+                fw = fma(inv_omb, fw, nb_inv * x);
+            }
         }
         return;
     }
     {
         float cur[kB], nxt[kB];
-        fetch_up(cur, 0);
+        fetch(A, cur, 0, 1);
         for (int t0 = 0; t0 < T; t0 += kB) {
-            fetch_up(nxt, t0 + kB);
+            fetch(A, nxt, t0 + kB, 1);
 #pragma unroll
             for (int j = 0; j < kB; ++j) {
                 if (t0 + j < T) {
@@ -1145,16 +1172,14 @@ __global__ void __launch_bounds__(128) k_iir_sigmoid(const IirArgs a) {
     const float* Mr = M;
     s = (double)Mr[(long long)(T - 1) * FP];
     for (int t0 = T - 1; t0 >= 0; t0 -= kB) {
-        float fw[kB], xx[kB];
-        fetch_down(Mr, fw, t0);
-        fetch_down(A, xx, t0);
+        float fwv[kB], xx[kB];
+        fetch(Mr, fwv, t0, -1);
+        fetch(A, xx, t0, -1);
 #pragma unroll
         for (int j = 0; j < kB; ++j) {
             if (t0 - j >= 0) {
-                s = fma(omb, s, b * (double)fw[j]);
-                const float num = (float)((double)xx[j] - s);      // |X| - S without float32 cancellation
-                const float r = num / (float)s;
-                M[(long long)(t0 - j) * FP] = 1.0f / (1.0f + expf(-(r - n_mult) * slope));
+                s = fma(omb, s, b * (double)fwv[j]);
+                M[(long long)(t0 - j) * FP] = sigmoid_mask((double)xx[j], s);
             }
         }
     }
@@ -1301,23 +1326,28 @@ __global__ void __launch_bounds__(288) k_smooth_box(const SmoothFArgs a) {
     float* dst = a.m2 + (long long)ul * a.T * FP;
     for (int i = tid; i < 2 * FP + 48; i += G) rowA[i] = 0.f;          // rowA and rowB are contiguous
     const int b0 = 4 * tid;
-    auto load_row = [&](int t, int slot) {
+    auto fetch_row = [&](int t) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t >= 0 && t < a.T) {
-            v = *reinterpret_cast<const float4*>(src + (long long)t * FP + b0);
+            v = __ldg(reinterpret_cast<const float4*>(src + (long long)t * FP + b0));
             if (b0 + 0 >= FF) v.x = 0.f;
             if (b0 + 1 >= FF) v.y = 0.f;
             if (b0 + 2 >= FF) v.z = 0.f;
             if (b0 + 3 >= FF) v.w = 0.f;
         }
-        *reinterpret_cast<float4*>(ring + slot * FP + b0) = v;
+        return v;
     };
-    for (int k = 0; k < 2 * nt; ++k) load_row(t_begin - nt + k, k);
+    for (int k = 0; k < 2 * nt; ++k) *reinterpret_cast<float4*>(ring + k * FP + b0) = fetch_row(t_begin - nt + k);
     int newest = (2 * nt) % R;
     const float invD = 1.0f / ((float)((NF + 1) * (NF + 1)) * (float)((nt + 1) * (nt + 1)));
+    // the rows of the next two frames are requested while this frame is being smoothed: the only global load of the loop
+    // otherwise sits right in front of its first use (long-scoreboard stalls were 3.8 cycles per issued instruction)
+    float4 pre0 = fetch_row(t_begin + nt), pre1 = fetch_row(t_begin + nt + 1);
     __syncthreads();
     for (int t = t_begin; t < t_end; ++t) {
-        load_row(t + nt, newest);
+        *reinterpret_cast<float4*>(ring + newest * FP + b0) = pre0;
+        pre0 = pre1;
+        pre1 = (t + 2 < t_end) ? fetch_row(t + nt + 2) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
         int slot = newest;                                  // frame t + nt; walking back to t - nt
         for (int b = -nt; b <= nt; ++b) {
