@@ -597,7 +597,7 @@ def main():
         # ---- BASELINE configs 3 and 4 -----------------------------------------------------------------
         extra = {}
         try:
-            dg3 = DeviceGate(sr=SR, stationary=False, n_fft=2048, workspace_limit_bytes=64e9)
+            dg3 = DeviceGate(sr=SR, stationary=False, n_fft=2048, workspace_limit_bytes=72e9)   # all 3072 units in one batch (66 GB of 180)
             for _ in range(2):
                 dg3.run(x, out)
             torch.cuda.synchronize()

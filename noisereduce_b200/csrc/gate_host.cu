@@ -146,12 +146,73 @@ struct Scratch {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// A reduce_noise() call creates a handle, runs once and destroys it: its large device buffers (workspace, slabs, staging)
+// would be cudaMalloc'ed and cudaFree'd every call (~15 ms together at config-2 sizes).  Destroyed handles leave them in a
+// small process-wide cache instead (per device; bounded: B200GATE_DEVICE_CACHE_MB, default 4096, 0 disables), and ensure()
+// looks there first.  Buffers enter the cache only after the device is idle (b200gate_destroy synchronises).
+struct DevicePool {
+    struct Item { void* p; size_t bytes; int dev; };
+    std::mutex mu;
+    std::vector<Item> items;
+    size_t cached = 0;
+    static size_t cap() {
+        static const size_t c = [] {
+            const char* e = getenv("B200GATE_DEVICE_CACHE_MB");
+            return (size_t)(e ? std::max(0LL, atoll(e)) : 4096LL) << 20;
+        }();
+        return c;
+    }
+    void* take(size_t bytes, int dev, size_t* got) {
+        std::lock_guard<std::mutex> lk(mu);
+        size_t best = items.size();
+        for (size_t i = 0; i < items.size(); ++i)
+            if (items[i].dev == dev && items[i].bytes >= bytes && items[i].bytes <= bytes + bytes / 4 + (1 << 20) &&
+                (best == items.size() || items[i].bytes < items[best].bytes))
+                best = i;
+        if (best == items.size()) return nullptr;
+        void* p = items[best].p;
+        *got = items[best].bytes;
+        cached -= items[best].bytes;
+        items.erase(items.begin() + (long)best);
+        return p;
+    }
+    void give(void* p, size_t bytes, int dev) {            // the device must be idle with respect to p
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (bytes >= (1 << 20) && cached + bytes <= cap() && items.size() < 16) {
+                items.push_back(Item{p, bytes, dev});
+                cached += bytes;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+    void drop_all(int dev) {                               // out of memory: give everything cached on this device back
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = items.size(); i-- > 0;)
+            if (items[i].dev == dev) { cudaFree(items[i].p); cached -= items[i].bytes; items.erase(items.begin() + (long)i); }
+    }
+};
+DevicePool g_device_pool;
+
 int ensure(b200gate_handle* h, void** p, size_t* have, size_t need) {
     if (*have >= need) return B200GATE_OK;
-    if (*p) cudaFree(*p);
+    if (*p) cudaFree(*p);                                   // (synchronises: work still using the old buffer has finished)
     *p = nullptr;
     *have = 0;
+    size_t got = 0;
+    if (void* c = g_device_pool.take(need, h->device, &got)) {
+        *p = c;
+        *have = got;
+        return B200GATE_OK;
+    }
     cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_device_pool.drop_all(h->device);
+        e = cudaMalloc(p, need);
+    }
     if (e != cudaSuccess) return fail(h, B200GATE_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
     *have = need;
     return B200GATE_OK;
@@ -454,6 +515,73 @@ void launch_channel_sum(const void* y, long long C, long long n, long long strid
     B200_LAUNCH(kern, dim3(grid_1d(n, 256, 4096)), dim3(256), 0, st, (const Tin*)y, C, n, stride, (Tacc*)acc, init);
 }
 
+// Persistent host workers for the staging copies: a slab pipeline of ~50 slabs would otherwise create and join ~15 threads
+// per slab and direction (~1 ms of a ~3 ms slab).  Workers sleep on a condition variable between jobs; one job at a time.
+class HostWorkers {
+public:
+    // run work(id) for id in [0, nt) on nt - 1 pooled threads plus the caller
+    void run(int nt, const std::function<void(int)>& work) {
+        if (nt <= 1) { work(0); return; }
+        std::unique_lock<std::mutex> job_lock(job_mu_);               // one job at a time (handles on several threads share the pool)
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while ((int)threads_.size() < nt - 1) {
+                const int id = (int)threads_.size() + 1;
+                threads_.emplace_back([this, id] { loop(id); });
+            }
+            work_ = &work;
+            nt_ = nt;
+            pending_ = nt - 1;
+            ++generation_;
+        }
+        cv_.notify_all();
+        work(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        work_ = nullptr;
+    }
+    ~HostWorkers() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+
+private:
+    void loop(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* w = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || (generation_ != seen && id < nt_); });
+                if (stop_) return;
+                seen = generation_;
+                w = work_;
+            }
+            (*w)(id);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    std::mutex mu_, job_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)>* work_ = nullptr;
+    int nt_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
+// pool 0: staging of pageable input rows; pool 1: copy-out of results into pageable rows (the two overlap in the slab pipeline)
+HostWorkers& host_workers(int pool) {
+    static HostWorkers* w[2] = {new HostWorkers(), new HostWorkers()};   // (never destroyed: no joins from static destructors at exit)
+    return *w[pool & 1];
+}
+
 // device-resident (or staged) y -> running channel-order sum in acc
 int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, long long n, long long stride,
                      int is_device, void* acc, int init, cudaStream_t st) {
@@ -461,6 +589,47 @@ int channel_sum_impl(b200gate_handle* h, const void* y, int dtype, long long C, 
     const void* src = y;
     long long sstride = stride;
     Scratch tmp;
+    if (!is_device && init) {
+        // host rows: the channel-order sum is taken by the host workers (the same sequential additions in the same type, so
+        // the same bits as k0_channel_sum) and only the n sums cross PCIe -- not C rows of pageable memory (64 x 600000 float32
+        // through the driver's bounce buffer cost ~15 ms per reduce_noise() call)
+        const size_t as = (dtype == B200GATE_F32) ? 4 : 8;
+        std::vector<unsigned char> hacc((size_t)n * as);
+        const long long blk = 8192;
+        const long long n_blk = (n + blk - 1) / blk;
+        const int nt = (int)std::max<long long>(1, std::min<long long>(std::min(h->host_threads, 32), n_blk));
+        std::function<void(int)> work = [&](int id) {
+            for (long long bix = id; bix < n_blk; bix += nt) {
+                const long long i0 = bix * blk, i1 = std::min(n, i0 + blk);
+                if (dtype == B200GATE_F32) {
+                    float* a = (float*)hacc.data();
+                    for (long long i = i0; i < i1; ++i) a[i] = 0.f;
+                    for (long long c = 0; c < C; ++c) {
+                        const float* r = (const float*)y + c * stride;
+                        for (long long i = i0; i < i1; ++i) a[i] = a[i] + r[i];
+                    }
+                } else if (dtype == B200GATE_I16) {
+                    double* a = (double*)hacc.data();
+                    for (long long i = i0; i < i1; ++i) a[i] = 0.0;
+                    for (long long c = 0; c < C; ++c) {
+                        const short* r = (const short*)y + c * stride;
+                        for (long long i = i0; i < i1; ++i) a[i] = a[i] + (double)r[i];
+                    }
+                } else {
+                    double* a = (double*)hacc.data();
+                    for (long long i = i0; i < i1; ++i) a[i] = 0.0;
+                    for (long long c = 0; c < C; ++c) {
+                        const double* r = (const double*)y + c * stride;
+                        for (long long i = i0; i < i1; ++i) a[i] = a[i] + r[i];
+                    }
+                }
+            }
+        };
+        host_workers(0).run(nt, work);
+        CK(h, cudaMemcpyAsync(acc, hacc.data(), (size_t)n * as, cudaMemcpyHostToDevice, st));
+        CK(h, cudaStreamSynchronize(st));                      // (hacc is freed on return)
+        return B200GATE_OK;
+    }
     if (!is_device) {
         CK(h, tmp.alloc((size_t)C * n * es));
         CK(h, cudaMemcpy2DAsync(tmp.p, (size_t)n * es, y, (size_t)stride * es, (size_t)n * es, (size_t)C,
@@ -544,73 +713,6 @@ bool host_pointer_is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 #endif
 }
-// Persistent host workers for the staging copies: a slab pipeline of ~50 slabs would otherwise create and join ~15 threads
-// per slab and direction (~1 ms of a ~3 ms slab).  Workers sleep on a condition variable between jobs; one job at a time.
-class HostWorkers {
-public:
-    // run work(id) for id in [0, nt) on nt - 1 pooled threads plus the caller
-    void run(int nt, const std::function<void(int)>& work) {
-        if (nt <= 1) { work(0); return; }
-        std::unique_lock<std::mutex> job_lock(job_mu_);               // one job at a time (handles on several threads share the pool)
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            while ((int)threads_.size() < nt - 1) {
-                const int id = (int)threads_.size() + 1;
-                threads_.emplace_back([this, id] { loop(id); });
-            }
-            work_ = &work;
-            nt_ = nt;
-            pending_ = nt - 1;
-            ++generation_;
-        }
-        cv_.notify_all();
-        work(0);
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [this] { return pending_ == 0; });
-        work_ = nullptr;
-    }
-    ~HostWorkers() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto& t : threads_) t.join();
-    }
-
-private:
-    void loop(int id) {
-        unsigned long long seen = 0;
-        for (;;) {
-            const std::function<void(int)>* w = nullptr;
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || (generation_ != seen && id < nt_); });
-                if (stop_) return;
-                seen = generation_;
-                w = work_;
-            }
-            (*w)(id);
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (--pending_ == 0) done_cv_.notify_one();
-            }
-        }
-    }
-    std::mutex mu_, job_mu_;
-    std::condition_variable cv_, done_cv_;
-    std::vector<std::thread> threads_;
-    const std::function<void(int)>* work_ = nullptr;
-    int nt_ = 0, pending_ = 0;
-    unsigned long long generation_ = 0;
-    bool stop_ = false;
-};
-// pool 0: staging of pageable input rows; pool 1: copy-out of results into pageable rows (the two overlap in the slab pipeline)
-HostWorkers& host_workers(int pool) {
-    static HostWorkers* w[2] = {new HostWorkers(), new HostWorkers()};   // (never destroyed: no joins from static destructors at exit)
-    return *w[pool & 1];
-}
-
 void parallel_rows_copy(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, int nthreads,
                         int pool = 0) {
     if (rows == 0 || width == 0) return;
@@ -825,8 +927,16 @@ int b200gate_create(const b200gate_params* p, b200gate_handle** out) {
 
 void b200gate_destroy(b200gate_handle* h) {
     if (!h) return;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cur_dev != h->device) cudaSetDevice(h->device);
+    cudaDeviceSynchronize();                                 // nothing of this handle is in flight when its buffers change hands
+    g_device_pool.give(h->d_ws_buf, h->ws_bytes, h->device);
+    g_device_pool.give(h->d_in, h->in_bytes, h->device);
+    g_device_pool.give(h->d_out, h->out_bytes, h->device);
+    g_device_pool.give(h->d_raw, h->raw_bytes, h->device);
     void* ptrs[] = {h->d_wa, h->d_ws, h->d_invn, h->d_thr4, h->d_gco, h->d_floor4, h->d_ef, h->d_tw, h->d_thr2_64,
-                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_ws_buf, h->d_in, h->d_out, h->d_raw, h->d_cnt, h->d_dbg_spec,
+                    h->d_wa64, h->d_cs64, h->d_tthr, h->d_wa2, h->d_ws2, h->d_w2k, h->d_invn2, h->d_cnt, h->d_dbg_spec,
                     h->d_dbg_mask, h->d_dbg_bits, h->d_gwa, h->d_gws, h->d_gw2, h->d_gthr, h->d_gcs, h->d_gtthr, h->d_gchirp, h->d_gbbr};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -842,9 +952,10 @@ void b200gate_destroy(b200gate_handle* h) {
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     for (int i = 0; i < 2; ++i) {
-        if (h->d_slab_in[i]) cudaFree(h->d_slab_in[i]);
-        if (h->d_slab_out[i]) cudaFree(h->d_slab_out[i]);
+        g_device_pool.give(h->d_slab_in[i], h->slab_in_bytes[i], h->device);
+        g_device_pool.give(h->d_slab_out[i], h->slab_out_bytes[i], h->device);
     }
+    if (cur_dev != h->device) cudaSetDevice(cur_dev);
     delete h;
 }
 
@@ -1253,6 +1364,14 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
         if (use_dual) nub &= ~1LL;
         if (nub < (use_dual ? 2 : 1)) return B200GATE_ERR_NOMEM;     // (message set by ensure)
         ub = nub;
+    }
+    if (!pipelined && ub < U) {
+        // several batches: equal ones (a full batch followed by a small remainder would end every kernel of the remainder
+        // in a partial wave); the slab pipeline sizes its batches itself below
+        const long long nb = (U + ub - 1) / ub;
+        long long eq = (U + nb - 1) / nb;
+        if (use_dual) eq += eq & 1;
+        ub = std::min(ub, std::max(eq, use_dual ? 2LL : 1LL));
     }
     long long slab_chunks = 0, slab_w = 0, slab_ow = 0;
     bool stage_in = false, stage_out = false;

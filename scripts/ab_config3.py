@@ -19,7 +19,7 @@ x = synth_device(torch, C_PER_GPU, n, 0, dev)
 out = torch.empty_like(x)
 base = None
 for f in flags:
-    dg = DeviceGate(sr=SR, stationary=False, n_fft=2048, workspace_limit_bytes=64e9, path_flags=f)
+    dg = DeviceGate(sr=SR, stationary=False, n_fft=2048, workspace_limit_bytes=72e9, path_flags=f)
     for _ in range(2):
         dg.run(x, out)
     torch.cuda.synchronize()
