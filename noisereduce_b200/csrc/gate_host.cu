@@ -1184,7 +1184,7 @@ int b200gate_torch_set_noise(b200gate_handle* h, const void* xn, int dtype, int6
     TStatArgs ta{};
     ta.n_units = (int)Bn; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64; ta.top_db = (float)h->p.top_db;
     ta.n_std = (float)h->p.n_std_thresh; ta.ddof = h->p.std_ddof; ta.mag = mag; ta.rowmax = rowmax; ta.thr = h->d_tthr;
-    B200_LAUNCH(k_tgate_stats, dim3(grid_1d(Bn * kFPad, 128, 1 << 30)), dim3(128), 0, st, ta);
+    B200_LAUNCH(k_tgate_stats, dim3((unsigned)(Bn * kFW)), dim3(kTgWarps * 32), 0, st, ta);
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(st));
     h->tthr_units = (int)Bn;
@@ -1643,7 +1643,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                 ta.n_units = nu; ta.T = g.T; ta.in_scale = (float)h->sum_w; ta.eps = (float)kEps64;
                 ta.top_db = (float)p.top_db; ta.n_std = (float)p.n_std_thresh; ta.ddof = p.std_ddof;
                 ta.mag = d_tdb; ta.rowmax = d_trow; ta.thr = d_tthr_self;
-                B200_LAUNCH(k_tgate_stats, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ta);
+                B200_LAUNCH(k_tgate_stats, dim3((unsigned)((long long)nu * kFW)), dim3(kTgWarps * 32), 0, st, ta);
                 TBitsArgs ba{};
                 ba.n_units = nu; ba.T = g.T; ba.top_db = (float)p.top_db; ba.db = d_tdb; ba.rowmax = d_trow; ba.bits = d_bits;
                 if (h->tthr_units > 0) {
@@ -1653,7 +1653,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     ba.thr = d_tthr_self;
                     ba.thr_units = nu;
                 }
-                B200_LAUNCH(k_tgate_bits, dim3((unsigned)(((long long)nu * kFPad + 127) / 128)), dim3(128), 0, st, ba);
+                B200_LAUNCH(k_tgate_bits, dim3((unsigned)((long long)nu * kFW)), dim3(kTgWarps * 32), 0, st, ba);
                 CK(h, cudaMemsetAsync(d_rowflag, 0, (size_t)nu * kFW * 4, st));
                 ++launches;
                 }
@@ -1882,7 +1882,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     TMovArgs ma{};
                     ma.n_units = nu; ma.T = g.T; ma.n_movemean = p.n_movemean; ma.n_thresh = (float)p.thresh_n_mult;
                     ma.inv_temp = (float)p.sigmoid_slope; ma.p = (float)p.prop_decrease; ma.mag = d_mag; ma.m0 = d_m0;
-                    B200_LAUNCH(k_tgate_movmean, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ma);
+                    B200_LAUNCH(k_tgate_movmean, dim3((unsigned)((long long)nu * kFW)), dim3(kTgWarps * 32), 0, st, ma);
                 } else {
                     IirArgs ia{};
                     ia.n_units = nu; ia.T = g.T; ia.F = kF; ia.FPad = kFPad;

@@ -28,6 +28,19 @@ struct Tables2 {
     float ws_to_w;
 };
 
+// |X| for the non-stationary follower: one MUFU.SQRT (relative error <= 2^-22) instead of the correctly rounded sqrtf
+// (reciprocal square root + Newton step + slow path, ~10 instructions, 34 of them per frame).  The magnitudes only feed the
+// follower's ratio and sigmoid -- a soft mask with tolerance 1e-5 -- never a binary decision.
+__device__ __forceinline__ float sqrt_approx(float x) {
+#if defined(B200_CUSIM_BUILD) || defined(B200_EXACT_SQRT_2K)
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+
 // frame samples -> packed complex input of the 1024-point FFT, windowed
 __device__ __forceinline__ void load_frame_2k(float (&re)[32], float (&im)[32], const float* __restrict__ xrow,
                                               long long base, long long i1, long long Lp, long long n_total,
@@ -123,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 3) k1n_magnitude_2k(const K1n2Args a
                 const float Xr = Er + Tr, Xi = Ei + Ti;              // X[k]
                 const float Yr = Er - Tr, Yi = Ti - Ei;              // X[1024-k] = conj(E - T)
                 if (valid) {
-                    dst[k] = sqrtf(fmaf(Xr, Xr, Xi * Xi));
-                    if (k != 512) dst[1024 - k] = sqrtf(fmaf(Yr, Yr, Yi * Yi));
+                    dst[k] = sqrt_approx(fmaf(Xr, Xr, Xi * Xi));
+                    if (k != 512) dst[1024 - k] = sqrt_approx(fmaf(Yr, Yr, Yi * Yi));
                     if (a.dbg.ul == ul) {
                         float* sp = a.dbg.spec + ((long long)t * kF2) * 2;
                         sp[2 * k] = Xr; sp[2 * k + 1] = Xi;

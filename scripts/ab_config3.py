@@ -12,14 +12,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import synth_device, SR, C_PER_GPU  # noqa: E402
 from noisereduce_b200.device import DeviceGate  # noqa: E402
 
-flags = [int(a) for a in sys.argv[1:]] or [0, 128, 16, 2, 64]
+flags = [a for a in sys.argv[1:]] or ["0", "128", "2", "64"]     # an argument "v:NAME" times libb200gate_NAME.so (scripts/build_variant.py) with path_flags 0
 dev = torch.device("cuda", 0)
 n = 10 * 60 * SR
 x = synth_device(torch, C_PER_GPU, n, 0, dev)
 out = torch.empty_like(x)
 base = None
-for f in flags:
-    dg = DeviceGate(sr=SR, stationary=False, n_fft=2048, workspace_limit_bytes=72e9, path_flags=f)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for arg in flags:
+    lib = None
+    f = 0
+    if arg.startswith("v:"):
+        from noisereduce_b200 import _cabi
+        lib = _cabi.GateLibrary(os.path.join(ROOT, "noisereduce_b200", f"libb200gate_{arg[2:]}.so"))
+    else:
+        f = int(arg)
+    dg = DeviceGate(sr=SR, stationary=False, n_fft=2048, workspace_limit_bytes=72e9, path_flags=f, lib=lib)
     for _ in range(2):
         dg.run(x, out)
     torch.cuda.synchronize()
@@ -35,7 +43,7 @@ for f in flags:
     sub = out[:, : 3 * 600000].clone()
     if base is None:
         base = sub
-    print(json.dumps({"path_flags": f, "ms_per_step": round(ms, 2), "gsamples_per_s": round(C_PER_GPU * n / ms / 1e6, 2),
+    print(json.dumps({"variant": arg, "path_flags": f, "ms_per_step": round(ms, 2), "gsamples_per_s": round(C_PER_GPU * n / ms / 1e6, 2),
                       "analysis_ms": round(s["k1_ms"], 2), "follower+smoothing_ms": round(s["smooth_ms"], 2),
                       "synthesis_ms": round(s["k2_ms"], 2), "launches": s["kernel_launches"],
                       "max_abs_diff_vs_first": float((sub - base).abs().max().item()),
