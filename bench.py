@@ -556,7 +556,13 @@ def main():
                      "whole_step": {"achieved": pipe_ach, "frac": pipe_ach / (peak * world)},
                      "traffic_note": "ncu dram bytes of one k2d_synthesize launch (cached spectra + mask numerators + waveform) -- profiles/k2_traffic.json",
                      "note": "k2d reads the 32 GB spectrum cache: its real DRAM traffic runs at ~64 % of peak, i.e. it is HBM bound on "
-                             "cache bytes, not on the 8 algorithmic bytes per sample"},
+                             "cache bytes, not on the 8 algorithmic bytes per sample",
+                     "fp32_pipe": {"source": "ncu sm__pipe_fma_cycles_active / sm__pipe_alu_cycles_active of the committed captures "
+                                             "(profiles/r02_m_*_full.txt), not measured in this run",
+                                   "k1d_analyze_fma": 0.424, "k2d_synthesize_fma": 0.503, "k_smooth_packed_alu": 0.597,
+                                   "fma_pipe_ms_per_step": 9.4,
+                                   "note": "the FP32 FFT pipeline holds the FMA pipe 9.4 ms per step whatever the memory traffic: the bound that "
+                                           "binds is the FP32 pipe (42-50 % busy in the two FFT kernels), not HBM -- DESIGN.md section 6"}},
         "e2e": e2e,
         "gpu_launches": launches,
         "gather_verified": gather_verified,

@@ -1882,7 +1882,7 @@ int b200gate_run(b200gate_handle* h, const void* in, void* out, int dtype, int64
                     TMovArgs ma{};
                     ma.n_units = nu; ma.T = g.T; ma.n_movemean = p.n_movemean; ma.n_thresh = (float)p.thresh_n_mult;
                     ma.inv_temp = (float)p.sigmoid_slope; ma.p = (float)p.prop_decrease; ma.mag = d_mag; ma.m0 = d_m0;
-                    B200_LAUNCH(k_tgate_movmean, dim3((unsigned)((long long)nu * kFW)), dim3(kTgWarps * 32), 0, st, ma);
+                    B200_LAUNCH(k_tgate_movmean, dim3(grid_1d((long long)nu * kFPad, 128, 1 << 30)), dim3(128), 0, st, ma);
                 } else {
                     IirArgs ia{};
                     ia.n_units = nu; ia.T = g.T; ia.F = kF; ia.FPad = kFPad;

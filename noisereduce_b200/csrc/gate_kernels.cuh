@@ -1307,9 +1307,7 @@ __global__ void __launch_bounds__(288) k_smooth_stream(const SmoothFArgs a) {
 // accumulates along a row or over time.  Row buffers: rowA = time-smoothed row c[] with 16 zero floats either side,
 // rowB = first box sums b1[g] = sum_{j=0..nf} c[g + j] stored at index g + 12 (g runs from -12: the second pass
 // out[f] = sum_{g=f-nf..f} b1[g] reaches nf bins to the left); bins >= F hold zeros, and FPad - F >= 12.
-inline size_t smoothb_smem_bytes(int FPad, int nt) {
-    return ((size_t)(2 * nt + 1) * FPad + (FPad + 32) + (FPad + 16) + 2 * (2 * nt + 1) + 8) * 4;
-}
+inline size_t smoothb_smem_bytes(int FPad, int nt) { return ((size_t)(2 * nt + 1) * FPad + (FPad + 32) + (FPad + 16)) * 4; }
 
 template <int NF>
 __global__ void __launch_bounds__(288) k_smooth_box(const SmoothFArgs a) {
@@ -1320,7 +1318,6 @@ __global__ void __launch_bounds__(288) k_smooth_box(const SmoothFArgs a) {
     float* ring = s_buf;                                   // [R][FP]
     float* rowA = s_buf + (size_t)R * FP;                  // [16 | FP | 16]
     float* rowB = rowA + FP + 32;                          // [FP + 16]
-    float* wtab = rowB + FP + 16;                          // [2 R]: wtab[j] = time tap of the row that is (j mod R) frames older than the newest
     const int ul = blockIdx.y;
     const int t_begin = a.tf_lo + blockIdx.x * a.TT;
     if (t_begin >= a.tf_hi) return;
@@ -1328,10 +1325,6 @@ __global__ void __launch_bounds__(288) k_smooth_box(const SmoothFArgs a) {
     const float* src = a.m0 + (long long)ul * a.T * FP;
     float* dst = a.m2 + (long long)ul * a.T * FP;
     for (int i = tid; i < 2 * FP + 48; i += G) rowA[i] = 0.f;          // rowA and rowB are contiguous
-    for (int j = tid; j < 2 * R; j += G) {
-        const int age = j % R;                              // age 0 = frame t + nt ... age 2 nt = frame t - nt
-        wtab[j] = (float)(nt + 1 - (age > nt ? age - nt : nt - age));
-    }
     const int b0 = 4 * tid;
     auto fetch_row = [&](int t) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1355,12 +1348,11 @@ __global__ void __launch_bounds__(288) k_smooth_box(const SmoothFArgs a) {
         *reinterpret_cast<float4*>(ring + newest * FP + b0) = pre0;
         pre0 = pre1;
         pre1 = (t + 2 < t_end) ? fetch_row(t + nt + 2) : make_float4(0.f, 0.f, 0.f, 0.f);
-        // time direction: the ring rows in PHYSICAL order (no wrap logic in the loop); the row in slot s is
-        // (newest - s) mod R frames older than the newest one and takes its tap from the rotating window of wtab
         float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-#ifdef B200_SMOOTH_LOGICAL_WALK                            // A/B: the first form of the loop (logical order, taps recomputed)
         {
-            int slot = newest;
+            // (measured and dropped: walking the ring in physical order with a rotating tap table -- fewer instructions per
+            //  tap, 1 ms slower per config-3 step; profiles/r02_experiments.md)
+            int slot = newest;                              // frame t + nt; walking back to t - nt
             for (int b = -nt; b <= nt; ++b) {
                 const float w = (float)(nt + 1 - (b < 0 ? -b : b));
                 const float4 r = *reinterpret_cast<const float4*>(ring + slot * FP + b0);
@@ -1368,19 +1360,6 @@ __global__ void __launch_bounds__(288) k_smooth_box(const SmoothFArgs a) {
                 slot = slot == 0 ? R - 1 : slot - 1;
             }
         }
-#else
-        {
-            const float* rp = ring + b0;
-            const float* wp = wtab + newest + R;            // tap of slot s: wp[-s]
-#pragma unroll 3
-            for (int sl = 0; sl < R; ++sl) {
-                const float w = wp[-sl];
-                const float4 r = *reinterpret_cast<const float4*>(rp);
-                c.x = fmaf(w, r.x, c.x); c.y = fmaf(w, r.y, c.y); c.z = fmaf(w, r.z, c.z); c.w = fmaf(w, r.w, c.w);
-                rp += FP;
-            }
-        }
-#endif
         newest = newest + 1 == R ? 0 : newest + 1;
         *reinterpret_cast<float4*>(rowA + 16 + b0) = c;     // (the previous frame's first pass finished before its 2nd barrier)
         __syncthreads();
@@ -1548,25 +1527,21 @@ struct TMovArgs {
     float* m0;                 // blended sigmoid mask, prop_decrease * (m - 1) + 1 (torchgate.py:241)
 };
 
-// (one CTA per (unit, 32-bin group) like k_tgate_stats; warp w walks the contiguous frames [w L, (w + 1) L) and starts its
-//  running window sum afresh -- at most n_movemean additions)
-__global__ void __launch_bounds__(kTgWarps * 32) k_tgate_movmean(const TMovArgs a) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int ul = blockIdx.x / kFW, grp = blockIdx.x - ul * kFW;
-    const int f = grp * 32 + lane;
+__global__ void __launch_bounds__(128) k_tgate_movmean(const TMovArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.n_units * kFPad) return;
+    const int ul = (int)(idx / kFPad), f = (int)(idx - (long long)ul * kFPad);
     const float* A = a.mag + (long long)ul * a.T * kFPad + f;
     float* M = a.m0 + (long long)ul * a.T * kFPad + f;
-    const int L = (a.T + kTgWarps - 1) / kTgWarps;
-    const int ta = w * L, tb = min(a.T, ta + L);
     if (f >= kF) {
-        for (int t = ta; t < tb; ++t) M[(long long)t * kFPad] = 0.f;
+        for (int t = 0; t < a.T; ++t) M[(long long)t * kFPad] = 0.f;
         return;
     }
     // conv1d(ones(n), padding="same"): window [t - left, t + right], zero padded, left = (n-1)/2
     const int n = a.n_movemean, left = (n - 1) / 2, right = n - 1 - left;
     double run = 0.0;
-    for (int t = max(0, ta - left); t <= ta + right && t < a.T; ++t) run += (double)A[(long long)t * kFPad];
-    for (int t = ta; t < tb; ++t) {
+    for (int t = 0; t <= right && t < a.T; ++t) run += (double)A[(long long)t * kFPad];
+    for (int t = 0; t < a.T; ++t) {
         const float Av = A[(long long)t * kFPad];
         const float S = (float)(run / (double)n);
         const float r = (Av - S) / S;
