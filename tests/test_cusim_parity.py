@@ -206,6 +206,39 @@ def test_float_mask_box_smoothing_and_2k_spectrum_cache(lib):
             assert r["mask_err"] < P.MASK_TOL_NONSTAT and r["out_relinf"] < P.OUT_TOL_TIGHT * 5, (n, fl, r)
 
 
+def test_pooled_result_arrays_lease_lifetime(lib, monkeypatch):
+    """_cabi.result_empty: large results are leased from b200gate_host_alloc (plain malloc in the simulator build), stay alive
+    through views, return with the last one, respect the budget and fall back to np.empty for small arrays."""
+    import gc
+    base = _cabi._pinned_leased_bytes
+    a = _cabi.result_empty(lib, (4, 10_000_000), np.float32)             # 160 MB
+    assert isinstance(a, np.ndarray) and a.shape == (4, 10_000_000) and a.flags.writeable
+    assert _cabi._pinned_leased_bytes == base + a.nbytes
+    a[:] = 2.0
+    v = a[1:3, 5:50]
+    del a
+    gc.collect()
+    assert _cabi._pinned_leased_bytes == base + 160_000_000 and float(v.sum()) == 2.0 * 2 * 45
+    del v
+    gc.collect()
+    assert _cabi._pinned_leased_bytes == base
+    small = _cabi.result_empty(lib, (4, 100), np.int16)
+    assert small.dtype == np.int16 and _cabi._pinned_leased_bytes == base
+    monkeypatch.setenv("B200GATE_PINNED_RESULT_LIMIT", "1000000")         # budget smaller than the request: ordinary memory
+    big = _cabi.result_empty(lib, (4, 10_000_000), np.float32)
+    assert _cabi._pinned_leased_bytes == base and big.shape == (4, 10_000_000)
+    # run_host without `out` takes the same route and returns the gate's result
+    y = synth_small(C=2, n=9000)
+    cfg = O.GateConfig(sr=SR, stationary=True, chunk_size=4000, padding=500)
+    g = _cabi.Gate(lib=lib, **P.gate_params(cfg))
+    g.noise_stats_host(y)
+    out = g.run_host(y)
+    ref = np.empty_like(y)
+    g.run_host(y, out=ref)
+    g.close()
+    assert np.array_equal(out, ref)
+
+
 def test_python_surface_on_simulator(lib, monkeypatch):
     """reduce_noise() host logic (shapes, dtypes, defaults, errors) with the simulator library."""
     monkeypatch.setattr(_cabi, "_LIB", lib)
