@@ -42,6 +42,11 @@ class SpectralGate:
         self.sr = sr
         self.flat = False
         y = np.asarray(y)              # (the reference copies with np.array; nothing here writes to the caller's samples)
+        if np.iscomplexobj(y):
+            # the reference fails inside scipy / numpy broadcasting on complex samples (a ValueError); fail before the device
+            raise ValueError("Waveform must be real-valued")
+        if y.size == 0:
+            raise ValueError("zero-size array to reduction operation maximum which has no identity")     # what the reference's _amp_to_db raises
         # reshape data to (#channels, #frames)                      (base.py:54-62)
         if len(y.shape) == 1:
             self.y = np.expand_dims(y, 0)

@@ -53,9 +53,36 @@ class SpectralGateStationary(SpectralGate):
         self._gate = _cabi.Gate(**params)
         # stationary.py:61-81 on the device: channel mean in the input dtype, clip, STFT, dB with the
         # 80 dB floor, per-bin mean / std over time, threshold
-        self._gate.noise_stats_host(self._samples_for_device(noise))
-        self.mean_freq_noise, self.std_freq_noise = self._gate.noise_mean_std()
-        self.noise_thresh = self._gate.noise_threshold()
+        clip = noise
+        if noise.dtype not in (np.float32, np.int16, np.float64):
+            # the reference collapses the clip with np.mean in the clip's own dtype rules (stationary.py:61): float16 stays
+            # float16 (float32 accumulation, rounded), integers / bool become float64 -- numpy decides, the device gets the result
+            clip = np.mean(noise, axis=0)[None, :]
+            if clip.dtype not in (np.float32, np.float64):
+                clip = clip.astype(np.float32)
+        n_eff = clip.shape[1]
+        if clip_noise_stationary and self._chunk_size is not None:
+            n_eff = min(n_eff, int(self._chunk_size))                         # stationary.py:63-64
+        noverlap = self._win_length - self._hop_length
+        if n_eff < self._win_length:
+            # scipy.signal.stft on a clip shorter than the window shrinks the window to the clip (nperseg = len(x), with a
+            # warning) and then insists on noverlap < nperseg; the reference inherits both behaviours (stationary.py:67-73)
+            if noverlap >= n_eff:
+                raise ValueError("noverlap must be less than nperseg.")
+            short = dict(params)
+            short.update(win_length=int(n_eff), hop_length=int(n_eff - noverlap))
+            stats_gate = _cabi.Gate(**short)
+            try:
+                stats_gate.noise_stats_host(self._samples_for_device(clip[:, :n_eff]))
+                self.mean_freq_noise, self.std_freq_noise = stats_gate.noise_mean_std()
+                self.noise_thresh = stats_gate.noise_threshold()
+            finally:
+                stats_gate.close()
+            self._gate.set_noise_threshold(self.noise_thresh)
+        else:
+            self._gate.noise_stats_host(self._samples_for_device(clip))
+            self.mean_freq_noise, self.std_freq_noise = self._gate.noise_mean_std()
+            self.noise_thresh = self._gate.noise_threshold()
 
     def _unit_gate_params(self):
         p = dict(self._params)

@@ -239,6 +239,34 @@ def test_pooled_result_arrays_lease_lifetime(lib, monkeypatch):
     assert np.array_equal(out, ref)
 
 
+def _replay_edge_cases(nr, golden_dir):
+    """reduce_noise() on the edge cases of tests/golden/edge_cases.py against the reference's stored outputs."""
+    import os
+    from tests.golden import edge_cases as E
+    g = np.load(os.path.join(golden_dir, "edge_cases.npz"))
+    for name, (y, kw) in E.cases().items():
+        out, ref = nr.reduce_noise(y=y, sr=E.SR, **kw), g[name]
+        assert out.shape == ref.shape and out.dtype == ref.dtype, name
+        if np.issubdtype(ref.dtype, np.integer):
+            assert np.abs(out.astype(np.int64) - ref.astype(np.int64)).max() <= 1, name
+        else:
+            assert np.array_equal(np.isnan(out), np.isnan(ref)), name           # (all-zero input: the reference returns NaN)
+            tol = 1e-3 if ref.dtype == np.float16 else P.OUT_TOL
+            assert P.relinf(np.nan_to_num(out), np.nan_to_num(ref)) < tol, name
+    for name, (y, kw, exc, msg) in E.refused().items():
+        with pytest.raises(exc, match=msg):
+            nr.reduce_noise(y=y, sr=E.SR, **kw)
+
+
+def test_edge_cases_like_the_reference_on_simulator(lib, monkeypatch, golden_dir):
+    """Short clips (scipy shrinks the STFT window to a noise clip shorter than it, or refuses), ragged chunks, zero padding,
+    non-contiguous views, float16 / int32 / uint8 samples, all-zero and constant input, and the inputs the reference
+    refuses -- outputs of the unmodified reference (tests/golden/make_golden_edge.py)."""
+    monkeypatch.setattr(_cabi, "_LIB", lib)
+    import noisereduce_b200 as nr
+    _replay_edge_cases(nr, golden_dir)
+
+
 def test_python_surface_on_simulator(lib, monkeypatch):
     """reduce_noise() host logic (shapes, dtypes, defaults, errors) with the simulator library."""
     monkeypatch.setattr(_cabi, "_LIB", lib)

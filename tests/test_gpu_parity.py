@@ -407,3 +407,10 @@ def test_non_power_of_two_n_fft_golden(lib, golden_dir):
             xt = torch.from_numpy(x.astype(dt)).cuda()
             yt = TorchGate(sr=16000, **kw)(xt)
             assert tuple(yt.shape) == gt[key].shape and P.relinf(yt.cpu().numpy(), gt[key]) < 5e-5, key
+
+
+def test_edge_cases_like_the_reference(lib, golden_dir):
+    """The edge cases pinned by tests/golden/edge_cases.npz (outputs of the unmodified reference) on the GPU."""
+    import noisereduce_b200 as nr
+    from tests.test_cusim_parity import _replay_edge_cases
+    _replay_edge_cases(nr, golden_dir)
